@@ -1,0 +1,660 @@
+/*
+ * ccd_oracle.c -- TEST INFRASTRUCTURE ONLY (never linked into, imported by, or
+ * called from the product path).
+ *
+ * A plain-C, single-threaded-by-default CPU restatement of the Scalable-CCD hot
+ * path (AABB build -> sort-and-sweep broad phase -> Tight-Inclusion narrow
+ * phase), used as the parity checker for the CUDA kernels in
+ * scalable-ccd_b200/csrc and as the "port" CPU baseline in bench.py.
+ *
+ * Every function cites the reference file:line (relative to /root/reference)
+ * whose behaviour it restates.  Arithmetic follows the contract in SURVEY.md
+ * section 8a: IEEE double, FMA exactly where nvcc contracts the reference's
+ * expressions (checked against the reference's own SASS), IEEE division.
+ * Compile with -ffp-contract=off so that the ONLY fused operations are the
+ * explicit fma() calls below.
+ *
+ * Parity pinning: the broad-phase half is pinned against the unmodified
+ * reference CPU sources built by oracle/Makefile into oracle/_ref/ (run in the
+ * build container, see tests/test_oracle_vs_ref.py); the narrow-phase half is
+ * pinned against the unmodified reference CUDA sources (oracle/_ref/
+ * libref_sccd_cuda.so) run on a B200 and frozen as tests/golden/ fixtures.
+ */
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* Same 64-byte layout as the reference's cuda::AABB (double build):
+ * cuda/broad_phase/aabb.cuh:12-96 -- Scalar3 min, Scalar3 max, int3
+ * vertex_ids, int element_id. */
+typedef struct {
+    double min[3];
+    double max[3];
+    int32_t vertex_ids[3];
+    int32_t element_id;
+} orc_aabb;
+
+/* scalar.hpp:31-49 */
+static inline double nextafter_down(double x) { return nextafter(x, -DBL_MAX); }
+static inline double nextafter_up(double x) { return nextafter(x, DBL_MAX); }
+
+/* cuda/broad_phase/aabb.cu:19-35 (from_point + conservative_inflation),
+ * CPU twin broad_phase/aabb.cpp:17-36. */
+static inline void point_box(const double p[3], double r, double mn[3], double mx[3])
+{
+    const double ru = nextafter_up(r);
+    for (int k = 0; k < 3; k++) {
+        mn[k] = nextafter_down(p[k]) - ru;
+        mx[k] = nextafter_up(p[k]) + ru;
+    }
+}
+
+/* cuda/broad_phase/aabb.cu:146-184: build_vertex_boxes(V0, V1, r).
+ * V0/V1 are nV x 3 COLUMN-major (Eigen default; device_matrix.cuh:77-81). */
+void orc_build_vertex_boxes(
+    const double* V0, const double* V1, int64_t nV, double r, orc_aabb* out)
+{
+    for (int64_t i = 0; i < nV; i++) {
+        double p0[3] = { V0[i], V0[i + nV], V0[i + 2 * nV] };
+        double p1[3] = { V1[i], V1[i + nV], V1[i + 2 * nV] };
+        double a0[3], a1[3], b0[3], b1[3];
+        point_box(p0, r, a0, a1);
+        point_box(p1, r, b0, b1);
+        for (int k = 0; k < 3; k++) {
+            /* aabb.cuh:18-28: AABB(a, b) = (min of mins, max of maxs) */
+            out[i].min[k] = a0[k] < b0[k] ? a0[k] : b0[k];
+            out[i].max[k] = a1[k] > b1[k] ? a1[k] : b1[k];
+        }
+        /* aabb.cu:180-181 */
+        out[i].vertex_ids[0] = (int32_t)i;
+        out[i].vertex_ids[1] = (int32_t)(-i - 1);
+        out[i].vertex_ids[2] = (int32_t)(-i - 1);
+        out[i].element_id = (int32_t)i;
+    }
+}
+
+/* cuda/broad_phase/aabb.cu:186-206.  E is nE x 2 column-major int32. */
+void orc_build_edge_boxes(
+    const orc_aabb* vb, const int32_t* E, int64_t nE, orc_aabb* out)
+{
+    for (int64_t i = 0; i < nE; i++) {
+        const int32_t e0 = E[i], e1 = E[i + nE];
+        for (int k = 0; k < 3; k++) {
+            out[i].min[k] = fmin(vb[e0].min[k], vb[e1].min[k]);
+            out[i].max[k] = fmax(vb[e0].max[k], vb[e1].max[k]);
+        }
+        out[i].vertex_ids[0] = e0;
+        out[i].vertex_ids[1] = e1;
+        out[i].vertex_ids[2] = -e0 - 1;
+        out[i].element_id = (int32_t)i;
+    }
+}
+
+/* cuda/broad_phase/aabb.cu:208-229.  F is nF x 3 column-major int32. */
+void orc_build_face_boxes(
+    const orc_aabb* vb, const int32_t* F, int64_t nF, orc_aabb* out)
+{
+    for (int64_t i = 0; i < nF; i++) {
+        const int32_t f0 = F[i], f1 = F[i + nF], f2 = F[i + 2 * nF];
+        for (int k = 0; k < 3; k++) {
+            out[i].min[k] = fmin(fmin(vb[f0].min[k], vb[f1].min[k]), vb[f2].min[k]);
+            out[i].max[k] = fmax(fmax(vb[f0].max[k], vb[f1].max[k]), vb[f2].max[k]);
+        }
+        out[i].vertex_ids[0] = f0;
+        out[i].vertex_ids[1] = f1;
+        out[i].vertex_ids[2] = f2;
+        out[i].element_id = (int32_t)i;
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* Broad phase                                                               */
+
+/* cuda/broad_phase/collision.cuh:17-21, broad_phase/sort_and_sweep.cpp:22-28 */
+static inline int share_a_vertex(const int32_t* a, const int32_t* b)
+{
+    return a[0] == b[0] || a[0] == b[1] || a[0] == b[2] || a[1] == b[0]
+        || a[1] == b[1] || a[1] == b[2] || a[2] == b[0] || a[2] == b[1]
+        || a[2] == b[2];
+}
+
+/* broad_phase/aabb.cpp:24-29 and cuda/broad_phase/aabb.cuh:67-72 (closed). */
+static inline int intersects(const orc_aabb* a, const orc_aabb* b)
+{
+    return a->min[0] <= b->max[0] && b->min[0] <= a->max[0]
+        && a->min[1] <= b->max[1] && b->min[1] <= a->max[1]
+        && a->min[2] <= b->max[2] && b->min[2] <= a->max[2];
+}
+
+typedef struct {
+    int32_t a, b;
+} orc_pair;
+
+static int g_axis;
+static int cmp_min_axis(const void* pa, const void* pb)
+{
+    const double a = ((const orc_aabb*)pa)->min[g_axis];
+    const double b = ((const orc_aabb*)pb)->min[g_axis];
+    return (a > b) - (a < b);
+}
+
+/* broad_phase/sort_and_sweep.cpp:176-195: next sort axis = argmax of
+ * sum(c^2) - sum(c)^2 / n over box centres (serial accumulation order). */
+static int next_axis(const orc_aabb* boxes, int64_t n)
+{
+    double s[3] = { 0, 0, 0 }, s2[3] = { 0, 0, 0 };
+    for (int64_t i = 0; i < n; i++)
+        for (int k = 0; k < 3; k++) {
+            const double c = (boxes[i].min[k] + boxes[i].max[k]) / 2;
+            s[k] += c;
+            s2[k] += c * c;
+        }
+    double var[3];
+    for (int k = 0; k < 3; k++)
+        var[k] = s2[k] - s[k] * s[k] / (double)n;
+    int ax = 0;
+    if (var[1] > var[0])
+        ax = 1;
+    if (var[2] > var[ax])
+        ax = 2;
+    return ax;
+}
+
+/* broad_phase/sort_and_sweep.cpp:78-125 (batched_sweep) over boxes already
+ * sorted on min[axis]; two-list mode expects list-A ids already flipped
+ * (-id-1), as sort_and_sweep.cpp:229-231 / cuda broad_phase.cu:20-26 do.
+ * Emits (vertex, face) in two-list mode and (min id, max id) otherwise --
+ * identical to cuda/broad_phase/sweep.cu:152-164.
+ * Returns the number of overlaps found; writes at most cap of them. */
+static int64_t sweep_sorted(
+    const orc_aabb* boxes, int64_t n, int axis, int two_lists, orc_pair* out,
+    int64_t cap)
+{
+    int64_t count = 0;
+    for (int64_t i = 0; i < n; i++) {
+        const orc_aabb* a = &boxes[i];
+        for (int64_t j = i + 1; j < n; j++) {
+            const orc_aabb* b = &boxes[j];
+            if (a->max[axis] < b->min[axis])
+                break;
+            if (two_lists
+                && !((a->element_id >= 0 && b->element_id < 0)
+                     || (a->element_id < 0 && b->element_id >= 0)))
+                continue;
+            if (!intersects(a, b) || share_a_vertex(a->vertex_ids, b->vertex_ids))
+                continue;
+            if (count < cap) {
+                if (two_lists) {
+                    out[count].a = a->element_id < 0 ? -a->element_id - 1
+                                                     : -b->element_id - 1;
+                    out[count].b = a->element_id < 0 ? b->element_id : a->element_id;
+                } else {
+                    out[count].a = a->element_id < b->element_id ? a->element_id
+                                                                 : b->element_id;
+                    out[count].b = a->element_id < b->element_id ? b->element_id
+                                                                 : a->element_id;
+                }
+            }
+            count++;
+        }
+    }
+    return count;
+}
+
+/* broad_phase/sort_and_sweep.cpp:198-211 (single list). */
+int64_t orc_sort_and_sweep(
+    const orc_aabb* boxes_in, int64_t n, int* sort_axis, orc_pair* out, int64_t cap)
+{
+    if (n == 0)
+        return 0;
+    orc_aabb* boxes = (orc_aabb*)malloc(sizeof(orc_aabb) * (size_t)n);
+    memcpy(boxes, boxes_in, sizeof(orc_aabb) * (size_t)n);
+    g_axis = *sort_axis;
+    qsort(boxes, (size_t)n, sizeof(orc_aabb), cmp_min_axis);
+    const int64_t c = sweep_sorted(boxes, n, *sort_axis, 0, out, cap);
+    *sort_axis = next_axis(boxes, n);
+    free(boxes);
+    return c;
+}
+
+/* broad_phase/sort_and_sweep.cpp:213-239 (two lists: A = vertices, B = faces). */
+int64_t orc_sort_and_sweep_two_lists(
+    const orc_aabb* A, int64_t nA, const orc_aabb* B, int64_t nB, int* sort_axis,
+    orc_pair* out, int64_t cap)
+{
+    if (nA == 0 || nB == 0)
+        return 0;
+    const int64_t n = nA + nB;
+    orc_aabb* boxes = (orc_aabb*)malloc(sizeof(orc_aabb) * (size_t)n);
+    memcpy(boxes, A, sizeof(orc_aabb) * (size_t)nA);
+    memcpy(boxes + nA, B, sizeof(orc_aabb) * (size_t)nB);
+    for (int64_t i = 0; i < nA; i++)
+        boxes[i].element_id = -boxes[i].element_id - 1;
+    g_axis = *sort_axis;
+    qsort(boxes, (size_t)n, sizeof(orc_aabb), cmp_min_axis);
+    const int64_t c = sweep_sorted(boxes, n, *sort_axis, 1, out, cap);
+    *sort_axis = next_axis(boxes, n);
+    free(boxes);
+    return c;
+}
+
+/* O(n^2) definition of the overlap set: all closed-
+ * intersecting, type-valid, non-incident pairs.  Small n only. */
+int64_t orc_brute_force(
+    const orc_aabb* A, int64_t nA, const orc_aabb* B, int64_t nB, orc_pair* out,
+    int64_t cap)
+{
+    int64_t count = 0;
+    if (B) {
+        for (int64_t i = 0; i < nA; i++)
+            for (int64_t j = 0; j < nB; j++)
+                if (intersects(&A[i], &B[j])
+                    && !share_a_vertex(A[i].vertex_ids, B[j].vertex_ids)) {
+                    if (count < cap) {
+                        out[count].a = A[i].element_id;
+                        out[count].b = B[j].element_id;
+                    }
+                    count++;
+                }
+    } else {
+        for (int64_t i = 0; i < nA; i++)
+            for (int64_t j = i + 1; j < nA; j++)
+                if (intersects(&A[i], &A[j])
+                    && !share_a_vertex(A[i].vertex_ids, A[j].vertex_ids)) {
+                    if (count < cap) {
+                        const int32_t x = A[i].element_id, y = A[j].element_id;
+                        out[count].a = x < y ? x : y;
+                        out[count].b = x < y ? y : x;
+                    }
+                    count++;
+                }
+    }
+    return count;
+}
+
+/* ------------------------------------------------------------------------- */
+/* Narrow phase (Tight-Inclusion, Scalable-CCD GPU variant)                  */
+
+/* Per-query data: the first 192 bytes of the reference's CCDData
+ * (cuda/narrow_phase/ccd_data.cuh:8-26): v0s v1s v2s v3s v0e v1e v2e v3e. */
+typedef struct {
+    double s[4][3]; /* vertices at t=0 */
+    double e[4][3]; /* vertices at t=1 */
+} orc_query;
+
+typedef struct {
+    double tol[3];
+    double err[3];
+} orc_bounds;
+
+static inline double linf3(const double* a, const double* b)
+{
+    /* (b - a).lpNorm<Infinity>() */
+    const double x = fabs(b[0] - a[0]), y = fabs(b[1] - a[1]), z = fabs(b[2] - a[2]);
+    return fmax(fmax(x, y), z);
+}
+
+/* cuda/narrow_phase/root_finder.cu:31-46 */
+static inline double max_linf_4(
+    const double* p1, const double* p2, const double* p3, const double* p4,
+    const double* p1e, const double* p2e, const double* p3e, const double* p4e)
+{
+    return fmax(
+        fmax(linf3(p1, p1e), linf3(p2, p2e)), fmax(linf3(p3, p3e), linf3(p4, p4e)));
+}
+
+static inline void sub3(const double* a, const double* b, double* r)
+{
+    r[0] = a[0] - b[0];
+    r[1] = a[1] - b[1];
+    r[2] = a[2] - b[2];
+}
+
+/* cuda/narrow_phase/root_finder.cu:48-88 (tolerances) and :90-135 (error). */
+void orc_compute_bounds(
+    const orc_query* q, int is_vf, double co_domain_tol, int use_ms, orc_bounds* out)
+{
+    double p000[3], p001[3], p011[3], p010[3], p100[3], p101[3], p111[3], p110[3];
+    if (is_vf) {
+        /* root_finder.cu:50-59 */
+        double tmp[3];
+        sub3(q->s[0], q->s[1], p000);
+        sub3(q->s[0], q->s[3], p001);
+        for (int k = 0; k < 3; k++)
+            tmp[k] = (q->s[2][k] + q->s[3][k]) - q->s[1][k];
+        sub3(q->s[0], tmp, p011);
+        sub3(q->s[0], q->s[2], p010);
+        sub3(q->e[0], q->e[1], p100);
+        sub3(q->e[0], q->e[3], p101);
+        for (int k = 0; k < 3; k++)
+            tmp[k] = (q->e[2][k] + q->e[3][k]) - q->e[1][k];
+        sub3(q->e[0], tmp, p111);
+        sub3(q->e[0], q->e[2], p110);
+        /* root_finder.cu:61-66 */
+        out->tol[0] = co_domain_tol
+            / (3 * max_linf_4(p000, p001, p011, p010, p100, p101, p111, p110));
+        out->tol[1] = co_domain_tol
+            / (3 * max_linf_4(p000, p100, p101, p001, p010, p110, p111, p011));
+        out->tol[2] = co_domain_tol
+            / (3 * max_linf_4(p000, p100, p110, p010, p001, p101, p111, p011));
+    } else {
+        /* root_finder.cu:73-80 */
+        sub3(q->s[0], q->s[2], p000);
+        sub3(q->s[0], q->s[3], p001);
+        sub3(q->s[1], q->s[2], p010);
+        sub3(q->s[1], q->s[3], p011);
+        sub3(q->e[0], q->e[2], p100);
+        sub3(q->e[0], q->e[3], p101);
+        sub3(q->e[1], q->e[2], p110);
+        sub3(q->e[1], q->e[3], p111);
+        /* root_finder.cu:82-87 -- tol[1] deliberately equals tol[0] */
+        out->tol[0] = co_domain_tol
+            / (3 * max_linf_4(p000, p001, p011, p010, p100, p101, p111, p110));
+        out->tol[1] = out->tol[0];
+        out->tol[2] = co_domain_tol
+            / (3 * max_linf_4(p000, p100, p101, p001, p010, p110, p111, p011));
+    }
+    /* root_finder.cu:93-122 (double build) */
+    double filter;
+    if (!use_ms)
+        filter = is_vf ? 6.661338147750939e-15 : 6.217248937900877e-15;
+    else
+        filter = is_vf ? 7.549516567451064e-15 : 7.105427357601002e-15;
+    /* root_finder.cu:124-134 */
+    for (int k = 0; k < 3; k++) {
+        double m = 1.0;
+        for (int v = 0; v < 4; v++) {
+            m = fmax(m, fabs(q->s[v][k]));
+            m = fmax(m, fabs(q->e[v][k]));
+        }
+        out->err[k] = m * m * m * filter;
+    }
+}
+
+/* cuda/narrow_phase/root_finder.cu:137-155: F at one (t,u,v) corner with the
+ * FMA contraction nvcc applies to the reference's expressions. */
+static inline void eval_corner(
+    const orc_query* q, int is_vf, double t, double u, double v, double* r)
+{
+    for (int k = 0; k < 3; k++) {
+        const double a0 = fma(q->e[0][k] - q->s[0][k], t, q->s[0][k]);
+        const double a1 = fma(q->e[1][k] - q->s[1][k], t, q->s[1][k]);
+        const double a2 = fma(q->e[2][k] - q->s[2][k], t, q->s[2][k]);
+        const double a3 = fma(q->e[3][k] - q->s[3][k], t, q->s[3][k]);
+        if (is_vf) {
+            /* v - (t1-t0)*u - (t2-t0)*v - t0, root_finder.cu:144 */
+            double x = fma(-(a2 - a1), u, a0);
+            x = fma(-(a3 - a1), v, x);
+            r[k] = x - a1;
+        } else {
+            /* ((ea1-ea0)*u+ea0) - ((eb1-eb0)*v+eb0), root_finder.cu:154 */
+            const double x = fma(a1 - a0, u, a0);
+            const double y = fma(a3 - a2, v, a2);
+            r[k] = x - y;
+        }
+    }
+}
+
+typedef struct {
+    double lo[3], hi[3];
+} orc_box;
+
+/* cuda/narrow_phase/root_finder.cu:157-198 */
+static inline int origin_in_inclusion(
+    const orc_query* q, const orc_bounds* b, int is_vf, double ms,
+    const orc_box* box, double* true_tol, int* box_in)
+{
+    double cmin[3] = { DBL_MAX, DBL_MAX, DBL_MAX };
+    double cmax[3] = { -DBL_MAX, -DBL_MAX, -DBL_MAX };
+    for (int c = 0; c < 8; c++) {
+        /* interval.cuh:52-57: bit0 -> t, bit1 -> u, bit2 -> v */
+        const double t = (c & 1) ? box->hi[0] : box->lo[0];
+        const double u = (c & 2) ? box->hi[1] : box->lo[1];
+        const double v = (c & 4) ? box->hi[2] : box->lo[2];
+        double r[3];
+        eval_corner(q, is_vf, t, u, v, r);
+        for (int k = 0; k < 3; k++) {
+            cmin[k] = fmin(cmin[k], r[k]);
+            cmax[k] = fmax(cmax[k], r[k]);
+        }
+    }
+    const double w0 = cmax[0] - cmin[0], w1 = cmax[1] - cmin[1], w2 = cmax[2] - cmin[2];
+    *true_tol = fmax(0.0, fmax(fmax(w0, w1), w2));
+    *box_in = 1;
+    for (int k = 0; k < 3; k++)
+        if (cmin[k] - ms > b->err[k] || cmax[k] + ms < -b->err[k])
+            return 0;
+    for (int k = 0; k < 3; k++)
+        if (cmin[k] + ms < -b->err[k] || cmax[k] - ms > b->err[k])
+            *box_in = 0;
+    return 1;
+}
+
+/* cuda/narrow_phase/root_finder.cu:200-211 */
+static inline int split_dimension(const orc_bounds* b, const double* w)
+{
+    const double r0 = w[0] / b->tol[0], r1 = w[1] / b->tol[1], r2 = w[2] / b->tol[2];
+    if (r0 >= r1 && r0 >= r2)
+        return 0;
+    if (r1 >= r0 && r1 >= r2)
+        return 1;
+    return 2;
+}
+
+/* Statistics the bench reports (box checks = ccd_kernel invocations that
+ * reach origin_in_inclusion_function). */
+typedef struct {
+    int64_t box_checks;
+    int64_t max_stack;
+    int64_t capped_queries;
+} orc_np_stats;
+
+#define ORC_STACK_MAX 4096
+
+/*
+ * One query, depth-first, earliest-t child first.  Restates
+ * cuda/narrow_phase/root_finder.cu:277-370 (ccd_kernel) + :213-254 (bisect).
+ * With max_iter < 0 the accepted minimum is independent of traversal order
+ * (SURVEY.md 8a "arithmetic contract"), so DFS == the reference's BFS.
+ *
+ * prune_toi: pointer to the bound used for pruning and lowered on accept
+ *   (the per-query toi in TOI_PER_QUERY mode, narrow_phase.cu:69-71 /
+ *   root_finder.cu:296-297; the global toi otherwise, root_finder.cu:295).
+ * max_iter >= 0: the reference silently DROPS boxes once the racy per-query
+ *   counter passes the cap (root_finder.cu:288-305).  cap_mode 0 restates
+ *   that (serialised, depth-first: non-conservative, like the reference);
+ *   cap_mode 1 is the conservative rule the B200 path uses: a box popped after
+ *   the cap is ACCEPTED at its t_lo, which can only make the answer earlier.
+ */
+static void solve_query(
+    const orc_query* q, int is_vf, double ms, int max_iter, double co_tol,
+    int allow_zero_toi, int cap_mode, double* prune_toi, double* global_toi,
+    orc_np_stats* st)
+{
+    orc_bounds bd;
+    orc_compute_bounds(q, is_vf, co_tol, ms > 0, &bd);
+
+    static __thread orc_box stack[ORC_STACK_MAX];
+    int sp = 0;
+    for (int k = 0; k < 3; k++) {
+        stack[0].lo[k] = 0.0;
+        stack[0].hi[k] = 1.0;
+    }
+    sp = 1;
+    int64_t checks = 0;
+    const double one_plus = 1 / (1 - DBL_EPSILON); /* root_finder.cu:24 */
+    int capped = 0;
+
+    while (sp > 0) {
+        if (sp > st->max_stack)
+            st->max_stack = sp;
+        const orc_box box = stack[--sp];
+        const double min_t = box.lo[0];
+        const int64_t seen = checks++; /* root_finder.cu:288-289 */
+        if (min_t >= *prune_toi) /* root_finder.cu:295-300 */
+            continue;
+        if (max_iter >= 0 && seen > max_iter) { /* root_finder.cu:303-305 */
+            capped = 1;
+            if (cap_mode == 1) {
+                if (min_t < *prune_toi)
+                    *prune_toi = min_t;
+                if (min_t < *global_toi)
+                    *global_toi = min_t;
+            }
+            continue;
+        }
+        st->box_checks++;
+        double true_tol;
+        int box_in;
+        if (!origin_in_inclusion(q, &bd, is_vf, ms, &box, &true_tol, &box_in))
+            continue;
+        const double w[3] = { box.hi[0] - box.lo[0], box.hi[1] - box.lo[1],
+                              box.hi[2] - box.lo[2] };
+        int accept = 0;
+        /* Condition 1, root_finder.cu:322 */
+        if (w[0] <= bd.tol[0] && w[1] <= bd.tol[1] && w[2] <= bd.tol[2])
+            accept = 1;
+        /* Condition 2, root_finder.cu:331 */
+        else if (box_in && (allow_zero_toi || min_t > 0))
+            accept = 1;
+        /* Condition 3, root_finder.cu:340-341 */
+        else if (true_tol <= co_tol && (allow_zero_toi || min_t > 0))
+            accept = 1;
+        if (!accept) {
+            const int split = split_dimension(&bd, w);
+            /* interval.cuh:18-27 */
+            const double mid = (box.lo[split] + box.hi[split]) / 2;
+            /* Condition 4, root_finder.cu:222-225,362 */
+            if (box.lo[split] >= mid || mid >= box.hi[split]) {
+                accept = 1;
+            } else {
+                orc_box first = box, second = box;
+                first.hi[split] = mid;
+                second.lo[split] = mid;
+                int push_second;
+                if (split == 0) /* root_finder.cu:229-232 */
+                    push_second = mid <= *prune_toi;
+                else if (is_vf) /* root_finder.cu:234-247 */
+                    push_second = (mid + box.lo[split == 1 ? 2 : 1]) <= one_plus;
+                else /* root_finder.cu:249 */
+                    push_second = 1;
+                if (sp + 2 > ORC_STACK_MAX)
+                    abort();
+                if (push_second)
+                    stack[sp++] = second;
+                stack[sp++] = first; /* popped first: earliest / lower half */
+            }
+        }
+        if (accept) {
+            if (min_t < *prune_toi)
+                *prune_toi = min_t;
+            if (min_t < *global_toi)
+                *global_toi = min_t;
+        }
+    }
+    if (capped)
+        st->capped_queries++;
+}
+
+/*
+ * cuda/narrow_phase/narrow_phase.cu:108-206 + root_finder.cu:372-457 on direct
+ * query arrays.
+ *   toi_per_query == NULL : reference default build -- one shared running toi
+ *                           (in/out, ccd.cu:125 starts it at 1.0).
+ *   toi_per_query != NULL : SCALABLE_CCD_TOI_PER_QUERY build -- per-query toi
+ *                           initialised to INFINITY (narrow_phase.cu:70), hit
+ *                           <=> toi < 1 (narrow_phase.cu:77-82); *toi still
+ *                           receives the global minimum.
+ */
+void orc_narrow_phase(
+    const orc_query* queries, int64_t n, int is_vf, double ms, int max_iter,
+    double tol, int allow_zero_toi, int cap_mode, double* toi, double* toi_per_query,
+    orc_np_stats* stats)
+{
+    orc_np_stats total = { 0, 0, 0 };
+    if (toi_per_query) {
+        double g = *toi;
+#pragma omp parallel
+        {
+            orc_np_stats st = { 0, 0, 0 };
+            double lg = g;
+#pragma omp for schedule(dynamic, 256)
+            for (int64_t i = 0; i < n; i++) {
+                double tq = INFINITY;
+                solve_query(
+                    &queries[i], is_vf, ms, max_iter, tol, allow_zero_toi, cap_mode,
+                    &tq, &lg, &st);
+                toi_per_query[i] = tq;
+            }
+#pragma omp critical
+            {
+                if (lg < g)
+                    g = lg;
+                total.box_checks += st.box_checks;
+                total.capped_queries += st.capped_queries;
+                if (st.max_stack > total.max_stack)
+                    total.max_stack = st.max_stack;
+            }
+        }
+        *toi = g;
+    } else {
+        /* shared running toi: sequential so the pruning bound is well defined;
+         * the final minimum is order-independent for max_iter < 0. */
+        double g = *toi;
+        for (int64_t i = 0; i < n && g > 0; i++) { /* narrow_phase.cu:136 */
+            double dummy = g;
+            solve_query(
+                &queries[i], is_vf, ms, max_iter, tol, allow_zero_toi, cap_mode, &g,
+                &dummy, &total);
+        }
+        *toi = g;
+    }
+    if (stats)
+        *stats = total;
+}
+
+/* cuda/narrow_phase/narrow_phase.cu:24-74 (add_data): gather the 8 vertices of
+ * each overlap into the query array.  V0/V1 column-major nV x 3; E nE x 2,
+ * F nF x 3 column-major int32; pairs = (vertex, face) or (edge a, edge b). */
+void orc_gather_queries(
+    const double* V0, const double* V1, int64_t nV, const int32_t* E, int64_t nE,
+    const int32_t* F, int64_t nF, const orc_pair* pairs, int64_t n, int is_vf,
+    orc_query* out)
+{
+    for (int64_t i = 0; i < n; i++) {
+        int32_t v[4];
+        if (is_vf) {
+            v[0] = pairs[i].a;
+            v[1] = F[pairs[i].b];
+            v[2] = F[pairs[i].b + nF];
+            v[3] = F[pairs[i].b + 2 * nF];
+        } else {
+            v[0] = E[pairs[i].a];
+            v[1] = E[pairs[i].a + nE];
+            v[2] = E[pairs[i].b];
+            v[3] = E[pairs[i].b + nE];
+        }
+        for (int j = 0; j < 4; j++)
+            for (int k = 0; k < 3; k++) {
+                out[i].s[j][k] = V0[v[j] + k * nV];
+                out[i].e[j][k] = V1[v[j] + k * nV];
+            }
+    }
+}
+
+int orc_sizeof_aabb(void) { return (int)sizeof(orc_aabb); }
+int orc_sizeof_query(void) { return (int)sizeof(orc_query); }
+int orc_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
