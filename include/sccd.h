@@ -1,0 +1,209 @@
+/*
+ * sccd.h -- C ABI of the B200-native continuous-collision-detection hot path.
+ *
+ * This is the drop-in boundary for the Scalable-CCD GPU path (reference paths are
+ * relative to /root/reference/src/scalable_ccd).  The reference exposes a C++17
+ * API with Eigen matrices; each entry point below names the reference interface it
+ * replaces.  The header-only C++ shim include/sccd.hpp re-creates the reference's
+ * names (scalable_ccd::cuda::ccd, BroadPhase, narrow_phase, ...) on top of this ABI.
+ *
+ * Conventions (identical to the reference):
+ *   - V0, V1 : nV x 3 float64, COLUMN-major (Eigen default; cuda/utils/device_matrix.cuh:77-81)
+ *   - E      : nE x 2 int32,   F : nF x 3 int32, column-major
+ *   - pairs  : int2 (a, b); vertex-face = (vertex id, face id), edge-edge =
+ *              (min edge id, max edge id)          (cuda/broad_phase/sweep.cu:152-164)
+ *   - toi    : earliest time of impact in [0, 1]; 1.0 = no collision (cuda/ccd.cu:125)
+ *   - Scalar : double (the reference's default SCALABLE_CCD_USE_DOUBLE build)
+ *
+ * All functions return SCCD_OK (0) or a negative error code; sccd_last_error()
+ * gives the message (the C++ shim rethrows it as std::runtime_error, the
+ * reference's convention, cuda/utils/assert.cuh:12-28).  There is no CPU fallback:
+ * every call fails with SCCD_ERR_CUDA if no sm_100 device is usable.
+ *
+ * A context is bound to one device and one stream and is not thread-safe (neither
+ * is the reference: global __constant__ CONFIG, cuda/narrow_phase/root_finder.cu:19).
+ * Different contexts may be used concurrently from different threads.
+ */
+#ifndef SCCD_H
+#define SCCD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCCD_OK 0
+#define SCCD_ERR_CUDA (-1)   /* CUDA runtime error / no usable device        */
+#define SCCD_ERR_ARG (-2)    /* bad argument                                 */
+#define SCCD_ERR_STATE (-3)  /* call order (e.g. broad phase before build)   */
+#define SCCD_ERR_MEMORY (-4) /* memory budget too small for a single box     */
+
+#define SCCD_VF 0 /* vertex-face  (two lists: vertices, faces) */
+#define SCCD_EE 1 /* edge-edge    (single list)                */
+
+typedef struct sccd_ctx sccd_ctx;
+
+/* int2 of the reference's overlap lists (cuda/broad_phase/broad_phase.cuh:58-60). */
+typedef struct {
+    int32_t a, b;
+} sccd_pair;
+
+/* Same 64-byte layout as the reference's cuda::AABB in the double build
+ * (cuda/broad_phase/aabb.cuh:12-96). */
+typedef struct {
+    double min[3];
+    double max[3];
+    int32_t vertex_ids[3];
+    int32_t element_id;
+} sccd_aabb;
+
+/* Counters and device timings (ms, CUDA events on the context's stream) of the
+ * most recent pipeline call.  Replaces the reference's SCALABLE_CCD_*_PROFILE_POINT
+ * instrumentation (utils/profiler.hpp:15-18). */
+typedef struct {
+    int64_t n_boxes[2];      /* boxes swept: [VF list (nV+nF), EE list (nE)]            */
+    int64_t n_pairs[2];      /* candidate pairs emitted                                 */
+    int64_t n_candidates[2]; /* f32-prefilter survivors that reached the exact test     */
+    int64_t n_queries[2];    /* narrow-phase queries run                                */
+    int64_t n_box_checks[2]; /* inclusion-function evaluations (ccd_kernel bodies)      */
+    int64_t n_donated[2];    /* sub-boxes handed to other lanes through the work queue  */
+    int64_t n_capped[2];     /* queries that hit max_iter (conservatively accepted)     */
+    int64_t n_launches;      /* kernels this library launched in the call               */
+    int64_t queue_overflow;  /* 1 if the bounded work queue ever refused a donation     */
+    float ms_build;          /* AABB build                                              */
+    float ms_sort;           /* radix sort + record gather                              */
+    float ms_sweep[2];       /* sweep count + scan + fill                               */
+    float ms_narrow[2];      /* narrow phase                                            */
+    float ms_total;          /* whole call, device time                                 */
+} sccd_stats;
+
+/* ---- context ------------------------------------------------------------------ */
+
+/* stream: a cudaStream_t (may be NULL = the legacy default stream).  Work is only
+ * ever enqueued on this stream. */
+int sccd_create(int device, void* stream, sccd_ctx** out);
+void sccd_destroy(sccd_ctx* ctx);
+const char* sccd_last_error(const sccd_ctx* ctx);
+
+/* MemoryHandler::memory_limit_GB (cuda/memory_handler.hpp:33; ccd.cuh:38).
+ * 0 = 95 % of free device memory (memory_handler.cpp:19-29).  Bounds the candidate
+ * pair buffer; larger overlap sets are produced in owner-range chunks. */
+int sccd_set_memory_limit(sccd_ctx* ctx, size_t bytes);
+
+/* Cap on pairs per sccd_broad_phase_partial() call (0 = derive from the memory
+ * limit).  Test hook for the chunking path (MAX_OVERLAP_CUTOFF semantics,
+ * cuda/broad_phase/broad_phase.cu:194-207). */
+int sccd_set_max_pairs_per_chunk(sccd_ctx* ctx, int64_t max_pairs);
+
+/* Capacity (items) of the bounded narrow-phase work queue (0 = default).  Replaces
+ * MemoryHandler::MAX_UNIT_SIZE (cuda/memory_handler.cpp:81-122). */
+int sccd_set_queue_capacity(sccd_ctx* ctx, int64_t items);
+
+/* Multi-GPU sharding: this context sweeps only the rank-th of `world` owner slices
+ * of each sorted list (slices balanced by sweep-window length) and therefore emits
+ * a disjoint part of the global pair list.  rank 0 / world 1 = everything. */
+int sccd_set_shard(sccd_ctx* ctx, int rank, int world);
+
+/* ---- mesh + boxes --------------------------------------------------------------- */
+
+/* DeviceMatrix uploads of ccd() (cuda/ccd.cu:103-106).  on_device != 0: the four
+ * pointers are device pointers valid on the context's device (no copy is made of V0/V1
+ * beyond the packed vertex table). */
+int sccd_upload_mesh(
+    sccd_ctx* ctx, const double* V0, const double* V1, int64_t nV, const int32_t* E,
+    int64_t nE, const int32_t* F, int64_t nF, int on_device);
+
+/* build_vertex_boxes + build_edge_boxes + build_face_boxes + the three DeviceAABBs
+ * constructors (cuda/broad_phase/aabb.cu:75-229), on the device: boxes are built
+ * from the uploaded mesh, keyed on min.x and radix-sorted (vertices+faces as one
+ * tagged list, edges as another). */
+int sccd_build_boxes(sccd_ctx* ctx, double inflation_radius);
+
+/* Boxes in the reference's host AABB format and element order, for parity checks
+ * (what build_*_boxes return; cuda/broad_phase/aabb.cuh:150-188).
+ * which: 0 vertices, 1 edges, 2 faces.  out: host array of nV / nE / nF boxes. */
+int sccd_get_boxes(sccd_ctx* ctx, int which, sccd_aabb* out);
+
+/* ---- broad phase ---------------------------------------------------------------- */
+
+/* BroadPhase::build (cuda/broad_phase/broad_phase.cu:29-101) for kind = SCCD_VF
+ * (vertex list, face list) or SCCD_EE (edge list).  Requires sccd_build_boxes. */
+int sccd_broad_phase_begin(sccd_ctx* ctx, int kind);
+
+/* BroadPhase::detect_overlaps_partial (broad_phase.cu:121-224): next chunk of the
+ * deterministic pair list, ordered by (owner position, candidate position) in the
+ * sorted list.  *d_pairs is device memory owned by the context, valid until the
+ * next call on it. */
+int sccd_broad_phase_partial(sccd_ctx* ctx, const sccd_pair** d_pairs, int64_t* n_pairs);
+
+/* BroadPhase::is_complete (broad_phase.cuh:50).  Returns 1 / 0, negative on error. */
+int sccd_broad_phase_is_complete(sccd_ctx* ctx);
+
+/* BroadPhase::detect_overlaps (broad_phase.cu:226-252): run all chunks and copy the
+ * pairs to host.  out may be NULL (count only); at most cap pairs are written;
+ * *n_total receives the full count. */
+int sccd_broad_phase(
+    sccd_ctx* ctx, int kind, sccd_pair* out, int64_t cap, int64_t* n_total);
+
+/* ---- narrow phase --------------------------------------------------------------- */
+
+/* narrow_phase<is_vf> (cuda/narrow_phase/narrow_phase.cuh:30-46) over a device pair
+ * list against the uploaded mesh.
+ *   ms, max_iter, tol, allow_zero_toi: as in the reference (max_iter < 0 = no cap).
+ *   toi_inout (host): running earliest toi, lowered in place (ccd.cu:125-143).
+ *   d_toi_per_query (device, n doubles, may be NULL): SCALABLE_CCD_TOI_PER_QUERY
+ *     semantics -- every query is solved against its OWN bound (init +inf) and its
+ *     earliest toi is stored; hit <=> value < 1 (narrow_phase.cu:69-82).  With NULL
+ *     the shared running toi prunes all queries (default reference build).
+ * Deviation (documented in DESIGN.md): a query that exceeds max_iter >= 0 has its
+ * remaining boxes ACCEPTED at their t_lo instead of silently dropped
+ * (root_finder.cu:303-305), so the result is never later than the reference's. */
+int sccd_narrow_phase(
+    sccd_ctx* ctx, int kind, const sccd_pair* d_pairs, int64_t n, double ms, int max_iter,
+    double tol, int allow_zero_toi, double* toi_inout, double* d_toi_per_query);
+
+/* Root finder on explicit query arrays: ccd<is_vf>(d_data, ...)
+ * (cuda/narrow_phase/root_finder.cuh:41-50).  queries: n x 24 doubles laid out like
+ * the first 192 bytes of CCDData (ccd_data.cuh:8-18): v0s v1s v2s v3s v0e v1e v2e v3e.
+ * on_device != 0: queries is a device pointer. */
+int sccd_narrow_phase_queries(
+    sccd_ctx* ctx, int kind, const double* queries, int64_t n, int on_device, double ms,
+    int max_iter, double tol, int allow_zero_toi, double* toi_inout, double* d_toi_per_query);
+
+/* ---- pipelines ------------------------------------------------------------------ */
+
+/* ccd() without the upload (cuda/ccd.cu:108-146): boxes -> VF broad+narrow ->
+ * EE broad+narrow on the mesh already uploaded.  *toi (host) receives the result. */
+int sccd_ccd(
+    sccd_ctx* ctx, double min_distance, int max_iter, double tol, int allow_zero_toi,
+    double* toi);
+
+/* ccd() of the TOI_PER_QUERY build (ccd.cuh:35-37): additionally returns the
+ * collisions (aid, bid, toi < 1).  ids/tois may be NULL; at most cap are written;
+ * VF collisions come first, then EE; *n_vf / *n_ee receive the full counts. */
+int sccd_ccd_collisions(
+    sccd_ctx* ctx, double min_distance, int max_iter, double tol, int allow_zero_toi,
+    double* toi, sccd_pair* ids, double* tois, int64_t cap, int64_t* n_vf, int64_t* n_ee);
+
+/* Whole ccd() including the host->device upload (cuda/ccd.cuh:26-38). */
+int sccd_ccd_host(
+    sccd_ctx* ctx, const double* V0, const double* V1, int64_t nV, const int32_t* E,
+    int64_t nE, const int32_t* F, int64_t nF, double min_distance, int max_iter, double tol,
+    int allow_zero_toi, double* toi);
+
+/* ipc_ccd_strategy() without the upload (cuda/ipc_ccd_strategy.cu:108-152). */
+int sccd_ipc_ccd_strategy(
+    sccd_ctx* ctx, double min_distance, int max_iter, double tol, double* toi);
+
+/* ---- introspection -------------------------------------------------------------- */
+int sccd_get_stats(const sccd_ctx* ctx, sccd_stats* out);
+int sccd_synchronize(sccd_ctx* ctx);
+/* "major.minor.patch sm_100a" */
+const char* sccd_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCCD_H */

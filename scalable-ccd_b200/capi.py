@@ -1,0 +1,259 @@
+"""ctypes binding of the C ABI in include/sccd.h (libsccd_b200.so).
+
+Thin by design: every method is one C call on HOST numpy buffers or raw DEVICE pointers
+(ints, e.g. torch.Tensor.data_ptr()).  There is no CPU fallback -- if the CUDA library is
+missing or no sm_100 device is usable, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsccd_b200.so")
+
+VF, EE = 0, 1
+OK, ERR_CUDA, ERR_ARG, ERR_STATE, ERR_MEMORY = 0, -1, -2, -3, -4
+
+AABB_DTYPE = np.dtype(
+    [("min", np.float64, 3), ("max", np.float64, 3), ("vids", np.int32, 3), ("elem", np.int32)])
+
+# every symbol include/sccd.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "sccd_create", "sccd_destroy", "sccd_last_error", "sccd_set_memory_limit",
+    "sccd_set_max_pairs_per_chunk", "sccd_set_queue_capacity", "sccd_set_shard",
+    "sccd_upload_mesh", "sccd_build_boxes", "sccd_get_boxes", "sccd_broad_phase_begin",
+    "sccd_broad_phase_partial", "sccd_broad_phase_is_complete", "sccd_broad_phase",
+    "sccd_narrow_phase", "sccd_narrow_phase_queries", "sccd_ccd", "sccd_ccd_collisions",
+    "sccd_ccd_host", "sccd_ipc_ccd_strategy", "sccd_get_stats", "sccd_synchronize",
+    "sccd_version",
+]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("n_boxes", C.c_int64 * 2), ("n_pairs", C.c_int64 * 2), ("n_candidates", C.c_int64 * 2),
+        ("n_queries", C.c_int64 * 2), ("n_box_checks", C.c_int64 * 2),
+        ("n_donated", C.c_int64 * 2), ("n_capped", C.c_int64 * 2), ("n_launches", C.c_int64),
+        ("queue_overflow", C.c_int64), ("ms_build", C.c_float), ("ms_sort", C.c_float),
+        ("ms_sweep", C.c_float * 2), ("ms_narrow", C.c_float * 2), ("ms_total", C.c_float),
+    ]
+
+    def as_dict(self):
+        out = {}
+        for name, _ in self._fields_:
+            v = getattr(self, name)
+            out[name] = list(v) if hasattr(v, "__len__") else v
+        return out
+
+
+class SccdError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"sccd error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Load libsccd_b200.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(
+                f"{LIB_PATH} not found: build it with `make -C {HERE}/csrc` "
+                "(or __graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        L.sccd_last_error.restype = C.c_char_p
+        L.sccd_version.restype = C.c_char_p
+        L.sccd_destroy.restype = None
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    """numpy array -> void*; int -> device pointer; None -> NULL."""
+    if a is None:
+        return C.c_void_p(0)
+    if isinstance(a, (int, np.integer)):
+        return C.c_void_p(int(a))
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One sccd_ctx: a device + stream + persistent device buffers."""
+
+    def __init__(self, device: int = 0, stream: int = 0):
+        self.L = load()
+        self._h = C.c_void_p(0)
+        rc = self.L.sccd_create(C.c_int(device), C.c_void_p(stream), C.byref(self._h))
+        if rc != OK:
+            raise SccdError(rc, "sccd_create failed (no usable sm_100 CUDA device?)")
+        self.device = device
+        self._keep = []
+
+    def close(self):
+        if self._h:
+            self.L.sccd_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc < 0:
+            raise SccdError(rc, self.L.sccd_last_error(self._h).decode())
+        return rc
+
+    # ---- configuration
+    def set_memory_limit(self, nbytes: int):
+        self._chk(self.L.sccd_set_memory_limit(self._h, C.c_size_t(nbytes)))
+
+    def set_max_pairs_per_chunk(self, n: int):
+        self._chk(self.L.sccd_set_max_pairs_per_chunk(self._h, C.c_int64(n)))
+
+    def set_queue_capacity(self, n: int):
+        self._chk(self.L.sccd_set_queue_capacity(self._h, C.c_int64(n)))
+
+    def set_shard(self, rank: int, world: int):
+        self._chk(self.L.sccd_set_shard(self._h, C.c_int(rank), C.c_int(world)))
+
+    # ---- mesh + boxes
+    def upload_mesh(self, V0, V1, E, F, sizes=None):
+        """Host numpy arrays (column-major) or device pointers with sizes=(nV, nE, nF)."""
+        if sizes is None:
+            for a, cols in ((V0, 3), (V1, 3), (E, 2), (F, 3)):
+                if a.ndim != 2 or a.shape[1] != cols or not a.flags.f_contiguous:
+                    raise ValueError("mesh arrays must be (n, cols) column-major")
+            if V0.dtype != np.float64 or V1.dtype != np.float64:
+                raise ValueError("V0/V1 must be float64")
+            if E.dtype != np.int32 or F.dtype != np.int32:
+                raise ValueError("E/F must be int32")
+            if V0.shape != V1.shape:
+                raise ValueError("V0 and V1 must have the same shape")
+            nV, nE, nF = V0.shape[0], E.shape[0], F.shape[0]
+            self._keep = [V0, V1, E, F]
+            on_dev = 0
+        else:
+            nV, nE, nF = sizes
+            on_dev = 1
+        self._chk(self.L.sccd_upload_mesh(
+            self._h, _ptr(V0), _ptr(V1), C.c_int64(nV), _ptr(E), C.c_int64(nE), _ptr(F),
+            C.c_int64(nF), C.c_int(on_dev)))
+        self.nV, self.nE, self.nF = nV, nE, nF
+
+    def build_boxes(self, inflation_radius: float = 0.0):
+        self._chk(self.L.sccd_build_boxes(self._h, C.c_double(inflation_radius)))
+
+    def get_boxes(self):
+        """(vertex, edge, face) boxes in the reference's host AABB format."""
+        out = []
+        for which, n in ((0, self.nV), (1, self.nE), (2, self.nF)):
+            a = np.zeros(max(n, 1), AABB_DTYPE)
+            self._chk(self.L.sccd_get_boxes(self._h, C.c_int(which), _ptr(a)))
+            out.append(a[:n])
+        return tuple(out)
+
+    # ---- broad phase
+    def broad_phase(self, kind: int, want_pairs: bool = True):
+        """detect_overlaps(): all pairs on the host, (n, 2) int32."""
+        n = C.c_int64(0)
+        self._chk(self.L.sccd_broad_phase(self._h, C.c_int(kind), None, C.c_int64(0), C.byref(n)))
+        if not want_pairs:
+            return n.value
+        out = np.empty((max(n.value, 1), 2), np.int32)
+        self._chk(self.L.sccd_broad_phase(
+            self._h, C.c_int(kind), _ptr(out), C.c_int64(n.value), C.byref(n)))
+        return out[:n.value]
+
+    def broad_phase_begin(self, kind: int):
+        self._chk(self.L.sccd_broad_phase_begin(self._h, C.c_int(kind)))
+
+    def broad_phase_partial(self):
+        """-> (device pointer, n_pairs) of the next chunk."""
+        p = C.c_void_p(0)
+        n = C.c_int64(0)
+        self._chk(self.L.sccd_broad_phase_partial(self._h, C.byref(p), C.byref(n)))
+        return (p.value or 0), n.value
+
+    def broad_phase_is_complete(self) -> bool:
+        return bool(self._chk(self.L.sccd_broad_phase_is_complete(self._h)))
+
+    # ---- narrow phase
+    def narrow_phase(self, kind, d_pairs: int, n: int, ms=0.0, max_iter=-1, tol=1e-6,
+                     allow_zero_toi=True, toi=1.0, d_toi_per_query: int = 0) -> float:
+        t = C.c_double(toi)
+        self._chk(self.L.sccd_narrow_phase(
+            self._h, C.c_int(kind), C.c_void_p(d_pairs), C.c_int64(n), C.c_double(ms),
+            C.c_int(max_iter), C.c_double(tol), C.c_int(int(allow_zero_toi)), C.byref(t),
+            C.c_void_p(d_toi_per_query)))
+        return t.value
+
+    def narrow_phase_queries(self, kind, queries, n=None, ms=0.0, max_iter=-1, tol=1e-6,
+                             allow_zero_toi=True, toi=1.0, d_toi_per_query: int = 0) -> float:
+        """queries: host (n, 24) float64 array, or a device pointer with n given."""
+        on_dev = isinstance(queries, (int, np.integer))
+        if not on_dev:
+            queries = np.ascontiguousarray(queries, dtype=np.float64).reshape(-1, 24)
+            n = len(queries)
+        t = C.c_double(toi)
+        self._chk(self.L.sccd_narrow_phase_queries(
+            self._h, C.c_int(kind), _ptr(queries), C.c_int64(n), C.c_int(int(on_dev)),
+            C.c_double(ms), C.c_int(max_iter), C.c_double(tol), C.c_int(int(allow_zero_toi)),
+            C.byref(t), C.c_void_p(d_toi_per_query)))
+        return t.value
+
+    # ---- pipelines
+    def ccd(self, ms=0.0, max_iter=-1, tol=1e-6, allow_zero_toi=True) -> float:
+        t = C.c_double(1.0)
+        self._chk(self.L.sccd_ccd(
+            self._h, C.c_double(ms), C.c_int(max_iter), C.c_double(tol),
+            C.c_int(int(allow_zero_toi)), C.byref(t)))
+        return t.value
+
+    def ccd_host(self, V0, V1, E, F, ms=0.0, max_iter=-1, tol=1e-6, allow_zero_toi=True) -> float:
+        t = C.c_double(1.0)
+        self._chk(self.L.sccd_ccd_host(
+            self._h, _ptr(V0), _ptr(V1), C.c_int64(V0.shape[0]), _ptr(E), C.c_int64(E.shape[0]),
+            _ptr(F), C.c_int64(F.shape[0]), C.c_double(ms), C.c_int(max_iter), C.c_double(tol),
+            C.c_int(int(allow_zero_toi)), C.byref(t)))
+        self.nV, self.nE, self.nF = V0.shape[0], E.shape[0], F.shape[0]
+        return t.value
+
+    def ccd_collisions(self, ms=0.0, max_iter=-1, tol=1e-6, allow_zero_toi=True):
+        """TOI_PER_QUERY build of ccd(): -> (toi, vf (ids, toi), ee (ids, toi))."""
+        t = C.c_double(1.0)
+        nvf, nee = C.c_int64(0), C.c_int64(0)
+        self._chk(self.L.sccd_ccd_collisions(
+            self._h, C.c_double(ms), C.c_int(max_iter), C.c_double(tol),
+            C.c_int(int(allow_zero_toi)), C.byref(t), None, None, C.c_int64(0), C.byref(nvf),
+            C.byref(nee)))
+        k = nvf.value + nee.value
+        ids = np.empty((max(k, 1), 2), np.int32)
+        tois = np.empty(max(k, 1), np.float64)
+        self._chk(self.L.sccd_ccd_collisions(
+            self._h, C.c_double(ms), C.c_int(max_iter), C.c_double(tol),
+            C.c_int(int(allow_zero_toi)), C.byref(t), _ptr(ids), _ptr(tois), C.c_int64(k),
+            C.byref(nvf), C.byref(nee)))
+        a = nvf.value
+        return t.value, (ids[:a], tois[:a]), (ids[a:k], tois[a:k])
+
+    def ipc_ccd_strategy(self, min_distance=0.0, max_iter=-1, tol=1e-6) -> float:
+        t = C.c_double(1.0)
+        self._chk(self.L.sccd_ipc_ccd_strategy(
+            self._h, C.c_double(min_distance), C.c_int(max_iter), C.c_double(tol), C.byref(t)))
+        return t.value
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._chk(self.L.sccd_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def synchronize(self):
+        self._chk(self.L.sccd_synchronize(self._h))

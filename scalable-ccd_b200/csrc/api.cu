@@ -1,0 +1,901 @@
+// Context, pipeline drivers and the C ABI (include/sccd.h).
+//
+// Host-side counterpart of the reference's cuda/ccd.cu, cuda/ipc_ccd_strategy.cu,
+// BroadPhase (cuda/broad_phase/broad_phase.cu) and MemoryHandler
+// (cuda/memory_handler.cpp): one stream, grow-only device buffers that persist across
+// calls, and exactly one host synchronisation per broad-phase list (to size the pair
+// buffer) and one per narrow-phase batch (to read the toi) -- against two syncs and two
+// D2H copies per BFS level plus one per kernel in the reference.
+#include "common.cuh"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace sccd {
+namespace {
+__global__ void find_splits_kernel(
+    const unsigned long long* __restrict__ offsets, int n, int world, int* out)
+{
+    // out[r] = first owner of slice r, chosen so every slice has ~equal window work
+    const int r = threadIdx.x;
+    if (r > world)
+        return;
+    if (r == 0) {
+        out[0] = 0;
+        return;
+    }
+    if (r == world) {
+        out[world] = n;
+        return;
+    }
+    const unsigned long long total = offsets[n];
+    const unsigned long long target = (total / (unsigned long long)world) * r;
+    int a = 0, b = n;
+    while (a < b) {
+        const int mid = (a + b) >> 1;
+        if (offsets[mid] < target)
+            a = mid + 1;
+        else
+            b = mid;
+    }
+    out[r] = a;
+}
+} // namespace
+} // namespace sccd
+
+using namespace sccd;
+
+struct sccd_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int num_sms = 148;
+    std::string error;
+
+    size_t memory_limit = 0;
+    int64_t max_pairs_per_chunk = 0;
+    int64_t queue_cap = 0;
+    int rank = 0, world = 1;
+
+    // mesh
+    int nV = 0, nE = 0, nF = 0;
+    bool have_mesh = false, have_boxes = false;
+    const double *dV0 = nullptr, *dV1 = nullptr;
+    const int32_t *dE = nullptr, *dF = nullptr;
+    DevBuf bV0, bV1, bE, bF;
+    DevBuf b_vtab, b_vbox;
+
+    // box lists: [0] = vertex+face (two lists), [1] = edges
+    struct ListBufs {
+        DevBuf ux, uyz, uid;     // unsorted exact records
+        DevBuf keys, keys_tmp, idx, idx_out;
+        DevBuf sx, syz, sid;     // sorted exact
+        DevBuf pxmin, pxmax, pyz; // sorted f32 prefilter
+        SortedList sorted;
+        BoxArrays unsorted;
+    } lists[2];
+    DevBuf b_sort_temp;
+
+    // broad-phase state
+    int bp_kind = -1;
+    int shard_lo = 0, shard_hi = 0, bp_cursor = 0;
+    unsigned long long bp_total = 0, bp_emitted = 0;
+    DevBuf b_counts, b_offsets, b_scan_temp, b_pairs, b_small;
+    int* h_small = nullptr; // pinned scratch for tiny D2H results
+
+    // narrow-phase state
+    DevBuf b_counters, b_queue, b_toi_q, b_checks_q, b_queries;
+    NarrowCounters* h_counters = nullptr; // pinned
+    unsigned long long q_ticket = 0;
+    long long queue_items = 0;
+
+    sccd_stats stats {};
+    LaunchCounter lc;
+    cudaEvent_t ev[16] {};
+
+    ~sccd_ctx()
+    {
+        if (h_small)
+            cudaFreeHost(h_small);
+        if (h_counters)
+            cudaFreeHost(h_counters);
+        for (auto& e : ev)
+            if (e)
+                cudaEventDestroy(e);
+    }
+};
+
+namespace {
+
+enum { EV_T0, EV_BUILD, EV_SORT, EV_SW0A, EV_SW0B, EV_NP0A, EV_NP0B, EV_SW1A, EV_SW1B,
+       EV_NP1A, EV_NP1B, EV_T1, EV_TMPA, EV_TMPB };
+
+void use_device(sccd_ctx* c) { SCCD_CUDA(cudaSetDevice(c->device)); }
+
+template <typename F> int guarded(sccd_ctx* c, F&& f)
+{
+    if (!c)
+        return SCCD_ERR_ARG;
+    try {
+        use_device(c);
+        return f();
+    } catch (const CudaError& e) {
+        c->error = e.what();
+        (void)cudaGetLastError();
+        return SCCD_ERR_CUDA;
+    } catch (const std::invalid_argument& e) {
+        c->error = e.what();
+        return SCCD_ERR_ARG;
+    } catch (const std::logic_error& e) {
+        c->error = e.what();
+        return SCCD_ERR_STATE;
+    } catch (const std::bad_alloc&) {
+        c->error = "out of host memory";
+        return SCCD_ERR_MEMORY;
+    } catch (const std::exception& e) {
+        c->error = e.what();
+        return SCCD_ERR_MEMORY;
+    }
+}
+
+void record(sccd_ctx* c, int which) { SCCD_CUDA(cudaEventRecord(c->ev[which], c->stream)); }
+float elapsed(sccd_ctx* c, int a, int b)
+{
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0.f;
+    }
+    return ms;
+}
+
+size_t budget_bytes(sccd_ctx* c)
+{
+    size_t free_b = 0, total_b = 0;
+    SCCD_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    // memory_handler.cpp:11-30: 95 % of what is free, or the user's limit if smaller
+    size_t avail = (size_t)(0.95 * (double)free_b);
+    if (c->memory_limit) {
+        const size_t used = total_b - free_b;
+        const size_t user = c->memory_limit > used ? c->memory_limit - used : avail;
+        avail = std::min(avail, user);
+    }
+    return avail;
+}
+
+void upload_mesh(
+    sccd_ctx* c, const double* V0, const double* V1, int64_t nV, const int32_t* E, int64_t nE,
+    const int32_t* F, int64_t nF, bool on_device)
+{
+    if (nV < 0 || nE < 0 || nF < 0 || nV >= (1ll << 31) || nE >= (1ll << 31) || nF >= (1ll << 31))
+        throw std::invalid_argument("upload_mesh: sizes out of range");
+    if ((nV && (!V0 || !V1)) || (nE && !E) || (nF && !F))
+        throw std::invalid_argument("upload_mesh: null pointer");
+    c->nV = (int)nV;
+    c->nE = (int)nE;
+    c->nF = (int)nF;
+    if (on_device) {
+        c->dV0 = V0;
+        c->dV1 = V1;
+        c->dE = E;
+        c->dF = F;
+    } else {
+        const size_t vb = sizeof(double) * 3 * (size_t)nV;
+        c->bV0.reserve(vb + 16);
+        c->bV1.reserve(vb + 16);
+        c->bE.reserve(sizeof(int32_t) * 2 * (size_t)nE + 16);
+        c->bF.reserve(sizeof(int32_t) * 3 * (size_t)nF + 16);
+        SCCD_CUDA(cudaMemcpyAsync(c->bV0.ptr, V0, vb, cudaMemcpyHostToDevice, c->stream));
+        SCCD_CUDA(cudaMemcpyAsync(c->bV1.ptr, V1, vb, cudaMemcpyHostToDevice, c->stream));
+        SCCD_CUDA(cudaMemcpyAsync(
+            c->bE.ptr, E, sizeof(int32_t) * 2 * (size_t)nE, cudaMemcpyHostToDevice, c->stream));
+        SCCD_CUDA(cudaMemcpyAsync(
+            c->bF.ptr, F, sizeof(int32_t) * 3 * (size_t)nF, cudaMemcpyHostToDevice, c->stream));
+        c->dV0 = c->bV0.as<double>();
+        c->dV1 = c->bV1.as<double>();
+        c->dE = c->bE.as<int32_t>();
+        c->dF = c->bF.as<int32_t>();
+    }
+    c->have_mesh = true;
+    c->have_boxes = false;
+    c->bp_kind = -1;
+}
+
+void prepare_list(sccd_ctx* c, int which, int n, bool two_lists)
+{
+    auto& L = c->lists[which];
+    const size_t m = (size_t)std::max(n, 1);
+    L.unsorted.x = (double2*)L.ux.reserve(m * sizeof(double2));
+    L.unsorted.yz = (double4*)L.uyz.reserve(m * sizeof(double4));
+    L.unsorted.id = (int4*)L.uid.reserve(m * sizeof(int4));
+    L.keys.reserve(m * 4);
+    L.keys_tmp.reserve(m * 4);
+    L.idx.reserve(m * 4);
+    L.idx_out.reserve(m * 4);
+    L.sorted.n = n;
+    L.sorted.two_lists = two_lists;
+    L.sorted.box.x = (double2*)L.sx.reserve(m * sizeof(double2));
+    L.sorted.box.yz = (double4*)L.syz.reserve(m * sizeof(double4));
+    L.sorted.box.id = (int4*)L.sid.reserve(m * sizeof(int4));
+    L.sorted.pf.xmin = (float*)L.pxmin.reserve(m * 4);
+    L.sorted.pf.xmax = (float*)L.pxmax.reserve(m * 4);
+    L.sorted.pf.yz = (float4*)L.pyz.reserve(m * sizeof(float4));
+}
+
+void build_boxes(sccd_ctx* c, double inflation_radius)
+{
+    if (!c->have_mesh)
+        throw std::logic_error("build_boxes: no mesh uploaded");
+    const int nV = c->nV, nE = c->nE, nF = c->nF;
+    const long long nVF = (long long)nV + nF;
+    if (nVF >= (1ll << 27) || nE >= (1 << 27))
+        throw std::invalid_argument("build_boxes: more than 2^27 boxes in one list");
+    c->b_vtab.reserve(sizeof(VertexRec) * (size_t)std::max(nV, 1));
+    c->b_vbox.reserve(sizeof(double) * 6 * (size_t)std::max(nV, 1));
+    prepare_list(c, 0, (int)nVF, true);
+    prepare_list(c, 1, nE, false);
+    const size_t temp = std::max(sort_temp_bytes((int)nVF), sort_temp_bytes(nE));
+    c->b_sort_temp.reserve(temp);
+
+    // aabb.cu:31-34: the radius itself is rounded up once
+    const double radius_up = std::nextafter(inflation_radius, DBL_MAX);
+    auto& LV = c->lists[0];
+    auto& LE = c->lists[1];
+    launch_vertex_boxes(
+        c->dV0, c->dV1, nV, radius_up, c->b_vtab.as<VertexRec>(), c->b_vbox.as<double>(),
+        LV.unsorted, LV.keys.as<uint32_t>(), c->stream, c->lc);
+    launch_element_boxes(
+        c->b_vbox.as<double>(), c->dE, nE, c->dF, nF, nV, LE.unsorted, LE.keys.as<uint32_t>(),
+        LV.unsorted, LV.keys.as<uint32_t>(), c->stream, c->lc);
+    record(c, EV_BUILD);
+    launch_sort_and_gather(
+        (int)nVF, LV.keys.as<uint32_t>(), LV.keys_tmp.as<uint32_t>(), LV.idx.as<uint32_t>(),
+        LV.idx_out.as<uint32_t>(), c->b_sort_temp.ptr, c->b_sort_temp.cap, LV.unsorted,
+        LV.sorted, c->stream, c->lc);
+    launch_sort_and_gather(
+        nE, LE.keys.as<uint32_t>(), LE.keys_tmp.as<uint32_t>(), LE.idx.as<uint32_t>(),
+        LE.idx_out.as<uint32_t>(), c->b_sort_temp.ptr, c->b_sort_temp.cap, LE.unsorted,
+        LE.sorted, c->stream, c->lc);
+    record(c, EV_SORT);
+    c->have_boxes = true;
+    c->bp_kind = -1;
+    c->stats.n_boxes[0] = nVF;
+    c->stats.n_boxes[1] = nE;
+}
+
+void small_scratch(sccd_ctx* c)
+{
+    c->b_small.reserve(256);
+    if (!c->h_small)
+        SCCD_CUDA(cudaMallocHost((void**)&c->h_small, 256));
+}
+
+// BroadPhase::build: choose the list, the owner slice of this rank, run the count pass and
+// the scan.  One host sync (the total).
+void broad_phase_begin(sccd_ctx* c, int kind)
+{
+    if (!c->have_boxes)
+        throw std::logic_error("Must initialize build broad phase before detecting overlaps!");
+    if (kind != SCCD_VF && kind != SCCD_EE)
+        throw std::invalid_argument("broad_phase: kind must be SCCD_VF or SCCD_EE");
+    const SortedList& L = c->lists[kind].sorted;
+    small_scratch(c);
+    c->bp_kind = kind;
+    c->shard_lo = 0;
+    c->shard_hi = L.n;
+    c->stats.n_pairs[kind] = 0;
+    c->stats.n_candidates[kind] = 0;
+    record(c, kind == SCCD_VF ? EV_SW0A : EV_SW1A);
+    if (c->world > 1 && L.n > 0) {
+        // balance owner slices by sweep-window length
+        c->b_counts.reserve(((size_t)L.n + 1) * 4);
+        c->b_offsets.reserve(((size_t)L.n + 1) * 8);
+        c->b_scan_temp.reserve(scan_temp_bytes(L.n));
+        SCCD_CUDA(cudaMemsetAsync(c->b_counts.as<uint32_t>() + L.n, 0, 4, c->stream));
+        launch_sweep_windows(L, c->b_counts.as<uint32_t>(), c->stream, c->lc);
+        launch_scan_u32_to_u64(
+            c->b_counts.as<uint32_t>(), c->b_offsets.as<unsigned long long>(), L.n,
+            c->b_scan_temp.ptr, c->b_scan_temp.cap, c->stream, c->lc);
+        if (c->world + 1 > 60)
+            throw std::invalid_argument("set_shard: world too large");
+        find_splits_kernel<<<1, 64, 0, c->stream>>>(
+            c->b_offsets.as<unsigned long long>(), L.n, c->world, c->b_small.as<int>());
+        SCCD_CUDA(cudaGetLastError());
+        c->lc.n++;
+        SCCD_CUDA(cudaMemcpyAsync(
+            c->h_small, c->b_small.ptr, sizeof(int) * (c->world + 1), cudaMemcpyDeviceToHost,
+            c->stream));
+        SCCD_CUDA(cudaStreamSynchronize(c->stream));
+        c->shard_lo = c->h_small[c->rank];
+        c->shard_hi = c->h_small[c->rank + 1];
+    }
+    const int m = c->shard_hi - c->shard_lo;
+    c->bp_cursor = c->shard_lo;
+    c->bp_total = 0;
+    c->bp_emitted = 0;
+    if (m <= 0)
+        return;
+    c->b_counts.reserve(((size_t)m + 1) * 4);
+    c->b_offsets.reserve(((size_t)m + 1) * 8);
+    c->b_scan_temp.reserve(scan_temp_bytes(m));
+    SCCD_CUDA(cudaMemsetAsync(c->b_counts.as<uint32_t>() + m, 0, 4, c->stream));
+    unsigned long long* d_cand = reinterpret_cast<unsigned long long*>(c->b_small.as<char>() + 128);
+    SCCD_CUDA(cudaMemsetAsync(d_cand, 0, 8, c->stream));
+    launch_sweep_count(
+        L, c->shard_lo, c->shard_hi, c->b_counts.as<uint32_t>(), d_cand, c->stream, c->lc);
+    launch_scan_u32_to_u64(
+        c->b_counts.as<uint32_t>(), c->b_offsets.as<unsigned long long>(), m,
+        c->b_scan_temp.ptr, c->b_scan_temp.cap, c->stream, c->lc);
+    unsigned long long* h = reinterpret_cast<unsigned long long*>(c->h_small);
+    SCCD_CUDA(cudaMemcpyAsync(
+        &h[0], c->b_offsets.as<unsigned long long>() + m, 8, cudaMemcpyDeviceToHost, c->stream));
+    SCCD_CUDA(cudaMemcpyAsync(&h[1], d_cand, 8, cudaMemcpyDeviceToHost, c->stream));
+    SCCD_CUDA(cudaStreamSynchronize(c->stream));
+    c->bp_total = h[0];
+    c->stats.n_candidates[kind] = (int64_t)h[1];
+}
+
+bool broad_phase_complete(sccd_ctx* c) { return c->bp_cursor >= c->shard_hi; }
+
+// BroadPhase::detect_overlaps_partial
+void broad_phase_partial(sccd_ctx* c, const sccd_pair** d_pairs, int64_t* n_pairs)
+{
+    if (c->bp_kind < 0)
+        throw std::logic_error("Must initialize build broad phase before detecting overlaps!");
+    *d_pairs = nullptr;
+    *n_pairs = 0;
+    if (broad_phase_complete(c))
+        return;
+    const int kind = c->bp_kind;
+    const SortedList& L = c->lists[kind].sorted;
+    const unsigned long long remaining = c->bp_total - c->bp_emitted;
+    unsigned long long budget;
+    if (c->max_pairs_per_chunk > 0)
+        budget = (unsigned long long)c->max_pairs_per_chunk;
+    else // pair (8 B) + per-query narrow-phase state; MemoryHandler::per_overlap_memory_size
+        budget = std::max<size_t>(budget_bytes(c) + c->b_pairs.cap, 1 << 20) / 32;
+    int end = c->shard_hi;
+    unsigned long long n_chunk = remaining;
+    if (remaining > budget) {
+        const int lo = c->bp_cursor - c->shard_lo, hi = c->shard_hi - c->shard_lo;
+        launch_find_chunk_end(
+            c->b_offsets.as<unsigned long long>(), lo, hi, budget, c->b_small.as<int>(),
+            c->stream, c->lc);
+        SCCD_CUDA(cudaMemcpyAsync(
+            c->h_small, c->b_small.ptr, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        SCCD_CUDA(cudaStreamSynchronize(c->stream));
+        const int e = c->h_small[0];
+        if (e <= lo) // memory_handler.cpp:65-69
+            throw std::runtime_error(
+                "Insufficient memory to increase overlap size; "
+                "cannot allocate even a single box's overlaps.");
+        end = c->shard_lo + e;
+        unsigned long long* h = reinterpret_cast<unsigned long long*>(c->h_small);
+        SCCD_CUDA(cudaMemcpyAsync(
+            &h[0], c->b_offsets.as<unsigned long long>() + e, 8, cudaMemcpyDeviceToHost,
+            c->stream));
+        SCCD_CUDA(cudaMemcpyAsync(
+            &h[1], c->b_offsets.as<unsigned long long>() + lo, 8, cudaMemcpyDeviceToHost,
+            c->stream));
+        SCCD_CUDA(cudaStreamSynchronize(c->stream));
+        n_chunk = h[0] - h[1];
+    }
+    if (n_chunk > 0) {
+        c->b_pairs.reserve((size_t)n_chunk * sizeof(sccd_pair));
+        launch_sweep_fill(
+            L, c->shard_lo, c->bp_cursor, end, c->b_offsets.as<unsigned long long>(),
+            c->b_pairs.as<sccd_pair>(), c->stream, c->lc);
+    }
+    c->bp_cursor = end;
+    c->bp_emitted += n_chunk;
+    c->stats.n_pairs[kind] += (int64_t)n_chunk;
+    record(c, kind == SCCD_VF ? EV_SW0B : EV_SW1B);
+    *d_pairs = c->b_pairs.as<sccd_pair>();
+    *n_pairs = (int64_t)n_chunk;
+}
+
+void narrow_setup(sccd_ctx* c)
+{
+    if (!c->h_counters)
+        SCCD_CUDA(cudaMallocHost((void**)&c->h_counters, sizeof(NarrowCounters)));
+    c->b_counters.reserve(sizeof(NarrowCounters));
+    const long long lanes = 2ll * c->num_sms * 256;
+    long long cap = c->queue_cap > 0 ? c->queue_cap : 8 * lanes;
+    cap = std::max(cap, 4 * lanes);
+    if (cap != c->queue_items || !c->b_queue.ptr) {
+        c->b_queue.reserve((size_t)cap * sizeof(WorkItem));
+        SCCD_CUDA(cudaMemsetAsync(c->b_queue.ptr, 0, (size_t)cap * sizeof(WorkItem), c->stream));
+        c->queue_items = cap;
+    }
+}
+
+// One narrow-phase batch: the body of narrow_phase<is_vf>() (narrow_phase.cu:108-206).
+void narrow_run(
+    sccd_ctx* c, int kind, const NarrowInput& in, double ms, int max_iter, double tol,
+    bool allow_zero_toi, double* toi_inout, double* d_toi_per_query)
+{
+    if (!(*toi_inout >= 0))
+        throw std::invalid_argument("narrow_phase: toi must be >= 0");
+    c->stats.n_queries[kind] += in.n;
+    if (in.n <= 0)
+        return;
+    if (in.n >= (1ll << 32))
+        throw std::invalid_argument("narrow_phase: more than 2^32 queries in one batch");
+    if (!d_toi_per_query && *toi_inout <= 0) // narrow_phase.cu:136: nothing can be earlier
+        return;
+    narrow_setup(c);
+    NarrowParams P;
+    P.ms = ms;
+    P.tol = tol;
+    P.max_iter = max_iter;
+    P.allow_zero_toi = allow_zero_toi ? 1 : 0;
+    P.use_ms = ms > 0 ? 1 : 0;
+
+    NarrowCounters init {};
+    init.next_query = 0;
+    init.q_tail = init.q_head = c->q_ticket; // tickets never repeat across launches
+    init.outstanding = 0;
+    init.toi = *toi_inout;
+    *c->h_counters = init;
+    SCCD_CUDA(cudaMemcpyAsync(
+        c->b_counters.ptr, c->h_counters, sizeof(NarrowCounters), cudaMemcpyHostToDevice,
+        c->stream));
+    if (d_toi_per_query)
+        launch_fill_f64(d_toi_per_query, in.n, INFINITY, c->stream, c->lc);
+    unsigned int* checks = nullptr;
+    if (max_iter >= 0) {
+        checks = (unsigned int*)c->b_checks_q.reserve((size_t)in.n * 4);
+        SCCD_CUDA(cudaMemsetAsync(checks, 0, (size_t)in.n * 4, c->stream));
+    }
+    launch_narrow_phase(
+        kind == SCCD_VF, in, P, c->b_counters.as<NarrowCounters>(), c->b_queue.as<WorkItem>(),
+        c->queue_items, d_toi_per_query, checks, c->num_sms, c->stream, c->lc);
+    SCCD_CUDA(cudaMemcpyAsync(
+        c->h_counters, c->b_counters.ptr, sizeof(NarrowCounters), cudaMemcpyDeviceToHost,
+        c->stream));
+    SCCD_CUDA(cudaStreamSynchronize(c->stream));
+    const NarrowCounters& r = *c->h_counters;
+    c->q_ticket = r.q_tail;
+    c->stats.n_box_checks[kind] += (int64_t)r.box_checks;
+    c->stats.n_donated[kind] += (int64_t)r.donated;
+    c->stats.n_capped[kind] += (int64_t)r.capped;
+    if (r.overflow)
+        c->stats.queue_overflow = 1;
+    if (r.overflow == 2)
+        throw std::runtime_error(
+            "narrow phase: work queue too small to re-root a sub-tree deeper than 128 levels; "
+            "raise it with sccd_set_queue_capacity");
+    if (r.toi < *toi_inout)
+        *toi_inout = r.toi;
+}
+
+NarrowInput mesh_input(sccd_ctx* c, const sccd_pair* d_pairs, int64_t n)
+{
+    if (!c->have_boxes)
+        throw std::logic_error("narrow_phase: call sccd_build_boxes first");
+    NarrowInput in;
+    in.vtab = c->b_vtab.as<VertexRec>();
+    in.E = c->dE;
+    in.F = c->dF;
+    in.nE = c->nE;
+    in.nF = c->nF;
+    in.pairs = d_pairs;
+    in.n = n;
+    return in;
+}
+
+void reset_stats(sccd_ctx* c)
+{
+    c->stats = sccd_stats {};
+    c->lc.n = 0;
+}
+
+void finish_stats(sccd_ctx* c, bool pipeline)
+{
+    c->stats.n_launches = c->lc.n;
+    if (!pipeline)
+        return;
+    SCCD_CUDA(cudaEventSynchronize(c->ev[EV_T1]));
+    c->stats.ms_build = elapsed(c, EV_T0, EV_BUILD);
+    c->stats.ms_sort = elapsed(c, EV_BUILD, EV_SORT);
+    c->stats.ms_sweep[0] = elapsed(c, EV_SW0A, EV_SW0B);
+    c->stats.ms_sweep[1] = elapsed(c, EV_SW1A, EV_SW1B);
+    c->stats.ms_narrow[0] = elapsed(c, EV_NP0A, EV_NP0B);
+    c->stats.ms_narrow[1] = elapsed(c, EV_NP1A, EV_NP1B);
+    c->stats.ms_total = elapsed(c, EV_T0, EV_T1);
+}
+
+// ccd() body (ccd.cu:108-146) and ipc_ccd_strategy() body (ipc_ccd_strategy.cu:108-152).
+void run_pipeline(
+    sccd_ctx* c, double min_distance, int max_iter, double tol, bool allow_zero_toi, bool ipc,
+    double* toi_out, bool want_collisions, std::vector<sccd_pair>* coll_ids,
+    std::vector<double>* coll_toi, int64_t* n_coll)
+{
+    reset_stats(c);
+    record(c, EV_T0);
+    build_boxes(c, min_distance);
+    double toi = 1.0; // ccd.cu:125
+    for (int kind = 0; kind < 2; kind++) {
+        broad_phase_begin(c, kind);
+        bool first = true;
+        if (broad_phase_complete(c)) {
+            record(c, kind == SCCD_VF ? EV_SW0B : EV_SW1B);
+            record(c, kind == SCCD_VF ? EV_NP0A : EV_NP1A);
+        }
+        while (!broad_phase_complete(c)) {
+            const sccd_pair* d_pairs = nullptr;
+            int64_t n = 0;
+            broad_phase_partial(c, &d_pairs, &n);
+            if (first)
+                record(c, kind == SCCD_VF ? EV_NP0A : EV_NP1A);
+            first = false;
+            const NarrowInput in = mesh_input(c, d_pairs, n);
+            double* d_tq = nullptr;
+            if (want_collisions && n > 0)
+                d_tq = (double*)c->b_toi_q.reserve((size_t)n * 8);
+            if (!ipc) {
+                narrow_run(c, kind, in, min_distance, max_iter, tol, allow_zero_toi, &toi, d_tq);
+            } else {
+                // ipc_ccd_strategy.cu:54-92
+                const double before = toi;
+                narrow_run(c, kind, in, min_distance, max_iter, tol, true, &toi, nullptr);
+                if (toi < 1e-6) {
+                    toi = before;
+                    narrow_run(c, kind, in, 0.0, -1, tol, false, &toi, nullptr);
+                    toi *= 0.8;
+                }
+            }
+            if (d_tq) {
+                // copy_out_collisions (narrow_phase.cu:84-103)
+                small_scratch(c);
+                unsigned long long* d_cnt =
+                    reinterpret_cast<unsigned long long*>(c->b_small.as<char>() + 192);
+                SCCD_CUDA(cudaMemsetAsync(d_cnt, 0, 8, c->stream));
+                sccd_pair* d_ids = (sccd_pair*)c->b_queries.reserve((size_t)n * 16);
+                double* d_t = reinterpret_cast<double*>(d_ids + n);
+                launch_compact_collisions(d_pairs, d_tq, n, d_ids, d_t, d_cnt, c->stream, c->lc);
+                unsigned long long* h = reinterpret_cast<unsigned long long*>(c->h_small);
+                SCCD_CUDA(cudaMemcpyAsync(&h[2], d_cnt, 8, cudaMemcpyDeviceToHost, c->stream));
+                SCCD_CUDA(cudaStreamSynchronize(c->stream));
+                const size_t k = (size_t)h[2], old = coll_ids->size();
+                coll_ids->resize(old + k);
+                coll_toi->resize(old + k);
+                if (k) {
+                    SCCD_CUDA(cudaMemcpyAsync(
+                        coll_ids->data() + old, d_ids, k * sizeof(sccd_pair),
+                        cudaMemcpyDeviceToHost, c->stream));
+                    SCCD_CUDA(cudaMemcpyAsync(
+                        coll_toi->data() + old, d_t, k * 8, cudaMemcpyDeviceToHost, c->stream));
+                    SCCD_CUDA(cudaStreamSynchronize(c->stream));
+                }
+                n_coll[kind] += (int64_t)k;
+            }
+        }
+        record(c, kind == SCCD_VF ? EV_NP0B : EV_NP1B);
+    }
+    record(c, EV_T1);
+    finish_stats(c, true);
+    *toi_out = toi;
+}
+
+} // namespace
+
+// =================================================================================== C ABI
+extern "C" {
+
+const char* sccd_version(void) { return "0.1.0 sm_100a"; }
+
+int sccd_create(int device, void* stream, sccd_ctx** out)
+{
+    if (!out)
+        return SCCD_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+        (void)cudaGetLastError();
+        return SCCD_ERR_CUDA; // no CPU fallback
+    }
+    sccd_ctx* c = new (std::nothrow) sccd_ctx();
+    if (!c)
+        return SCCD_ERR_MEMORY;
+    c->device = device;
+    c->stream = (cudaStream_t)stream;
+    const int rc = guarded(c, [&] {
+        cudaDeviceProp prop;
+        SCCD_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10)
+            throw CudaError("sccd: this library is built for sm_100a (B200) only");
+        c->num_sms = prop.multiProcessorCount;
+        for (auto& e : c->ev)
+            SCCD_CUDA(cudaEventCreate(&e));
+        return SCCD_OK;
+    });
+    if (rc != SCCD_OK) {
+        delete c;
+        return rc;
+    }
+    *out = c;
+    return SCCD_OK;
+}
+
+void sccd_destroy(sccd_ctx* ctx)
+{
+    if (!ctx)
+        return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    delete ctx;
+}
+
+const char* sccd_last_error(const sccd_ctx* ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+
+int sccd_set_memory_limit(sccd_ctx* ctx, size_t bytes)
+{
+    if (!ctx)
+        return SCCD_ERR_ARG;
+    ctx->memory_limit = bytes;
+    return SCCD_OK;
+}
+
+int sccd_set_max_pairs_per_chunk(sccd_ctx* ctx, int64_t max_pairs)
+{
+    if (!ctx || max_pairs < 0)
+        return SCCD_ERR_ARG;
+    ctx->max_pairs_per_chunk = max_pairs;
+    return SCCD_OK;
+}
+
+int sccd_set_queue_capacity(sccd_ctx* ctx, int64_t items)
+{
+    if (!ctx || items < 0)
+        return SCCD_ERR_ARG;
+    ctx->queue_cap = items;
+    return SCCD_OK;
+}
+
+int sccd_set_shard(sccd_ctx* ctx, int rank, int world)
+{
+    if (!ctx || world < 1 || rank < 0 || rank >= world || world > 16)
+        return SCCD_ERR_ARG;
+    ctx->rank = rank;
+    ctx->world = world;
+    ctx->bp_kind = -1;
+    return SCCD_OK;
+}
+
+int sccd_upload_mesh(
+    sccd_ctx* ctx, const double* V0, const double* V1, int64_t nV, const int32_t* E, int64_t nE,
+    const int32_t* F, int64_t nF, int on_device)
+{
+    return guarded(ctx, [&] {
+        upload_mesh(ctx, V0, V1, nV, E, nE, F, nF, on_device != 0);
+        return SCCD_OK;
+    });
+}
+
+int sccd_build_boxes(sccd_ctx* ctx, double inflation_radius)
+{
+    return guarded(ctx, [&] {
+        record(ctx, EV_T0);
+        build_boxes(ctx, inflation_radius);
+        return SCCD_OK;
+    });
+}
+
+int sccd_get_boxes(sccd_ctx* ctx, int which, sccd_aabb* out)
+{
+    return guarded(ctx, [&] {
+        if (!ctx->have_boxes)
+            throw std::logic_error("get_boxes: call sccd_build_boxes first");
+        if (which < 0 || which > 2 || !out)
+            throw std::invalid_argument("get_boxes: bad argument");
+        const int n = which == 0 ? ctx->nV : (which == 1 ? ctx->nE : ctx->nF);
+        const auto& U = ctx->lists[which == 1 ? 1 : 0].unsorted;
+        const size_t off = which == 2 ? (size_t)ctx->nV : 0;
+        std::vector<double2> x(n);
+        std::vector<double4> yz(n);
+        std::vector<int4> id(n);
+        SCCD_CUDA(cudaStreamSynchronize(ctx->stream));
+        SCCD_CUDA(cudaMemcpy(x.data(), U.x + off, sizeof(double2) * n, cudaMemcpyDeviceToHost));
+        SCCD_CUDA(cudaMemcpy(yz.data(), U.yz + off, sizeof(double4) * n, cudaMemcpyDeviceToHost));
+        SCCD_CUDA(cudaMemcpy(id.data(), U.id + off, sizeof(int4) * n, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n; i++) {
+            out[i].min[0] = x[i].x;
+            out[i].max[0] = x[i].y;
+            out[i].min[1] = yz[i].x;
+            out[i].min[2] = yz[i].y;
+            out[i].max[1] = yz[i].z;
+            out[i].max[2] = yz[i].w;
+            out[i].vertex_ids[0] = id[i].x;
+            out[i].vertex_ids[1] = id[i].y;
+            out[i].vertex_ids[2] = id[i].z;
+            // vertices carry the flipped id on the device; the reference's host boxes do not
+            out[i].element_id = which == 0 ? -id[i].w - 1 : id[i].w;
+        }
+        return SCCD_OK;
+    });
+}
+
+int sccd_broad_phase_begin(sccd_ctx* ctx, int kind)
+{
+    return guarded(ctx, [&] {
+        broad_phase_begin(ctx, kind);
+        return SCCD_OK;
+    });
+}
+
+int sccd_broad_phase_partial(sccd_ctx* ctx, const sccd_pair** d_pairs, int64_t* n_pairs)
+{
+    return guarded(ctx, [&] {
+        if (!d_pairs || !n_pairs)
+            throw std::invalid_argument("broad_phase_partial: null output");
+        broad_phase_partial(ctx, d_pairs, n_pairs);
+        return SCCD_OK;
+    });
+}
+
+int sccd_broad_phase_is_complete(sccd_ctx* ctx)
+{
+    if (!ctx)
+        return SCCD_ERR_ARG;
+    if (ctx->bp_kind < 0) {
+        ctx->error = "Must initialize build broad phase before detecting overlaps!";
+        return SCCD_ERR_STATE;
+    }
+    return broad_phase_complete(ctx) ? 1 : 0;
+}
+
+int sccd_broad_phase(sccd_ctx* ctx, int kind, sccd_pair* out, int64_t cap, int64_t* n_total)
+{
+    return guarded(ctx, [&] {
+        broad_phase_begin(ctx, kind);
+        int64_t written = 0, total = 0;
+        while (!broad_phase_complete(ctx)) {
+            const sccd_pair* d = nullptr;
+            int64_t n = 0;
+            broad_phase_partial(ctx, &d, &n);
+            if (out && written < cap && n > 0) {
+                const int64_t k = std::min(n, cap - written);
+                SCCD_CUDA(cudaMemcpyAsync(
+                    out + written, d, (size_t)k * sizeof(sccd_pair), cudaMemcpyDeviceToHost,
+                    ctx->stream));
+                SCCD_CUDA(cudaStreamSynchronize(ctx->stream));
+                written += k;
+            }
+            total += n;
+        }
+        if (n_total)
+            *n_total = total;
+        ctx->stats.n_launches = ctx->lc.n;
+        return SCCD_OK;
+    });
+}
+
+int sccd_narrow_phase(
+    sccd_ctx* ctx, int kind, const sccd_pair* d_pairs, int64_t n, double ms, int max_iter,
+    double tol, int allow_zero_toi, double* toi_inout, double* d_toi_per_query)
+{
+    return guarded(ctx, [&] {
+        if (!toi_inout || (n > 0 && !d_pairs) || n < 0 || (kind != SCCD_VF && kind != SCCD_EE))
+            throw std::invalid_argument("narrow_phase: bad argument");
+        record(ctx, EV_TMPA);
+        narrow_run(
+            ctx, kind, mesh_input(ctx, d_pairs, n), ms, max_iter, tol, allow_zero_toi != 0,
+            toi_inout, d_toi_per_query);
+        ctx->stats.n_launches = ctx->lc.n;
+        return SCCD_OK;
+    });
+}
+
+int sccd_narrow_phase_queries(
+    sccd_ctx* ctx, int kind, const double* queries, int64_t n, int on_device, double ms,
+    int max_iter, double tol, int allow_zero_toi, double* toi_inout, double* d_toi_per_query)
+{
+    return guarded(ctx, [&] {
+        if (!toi_inout || (n > 0 && !queries) || n < 0 || (kind != SCCD_VF && kind != SCCD_EE))
+            throw std::invalid_argument("narrow_phase_queries: bad argument");
+        NarrowInput in;
+        in.n = n;
+        if (on_device || n == 0) {
+            in.queries = queries;
+        } else {
+            double* d = (double*)ctx->b_queries.reserve((size_t)n * 24 * 8);
+            SCCD_CUDA(cudaMemcpyAsync(
+                d, queries, (size_t)n * 24 * 8, cudaMemcpyHostToDevice, ctx->stream));
+            in.queries = d;
+        }
+        record(ctx, EV_TMPA);
+        narrow_run(ctx, kind, in, ms, max_iter, tol, allow_zero_toi != 0, toi_inout, d_toi_per_query);
+        record(ctx, EV_TMPB);
+        SCCD_CUDA(cudaEventSynchronize(ctx->ev[EV_TMPB]));
+        ctx->stats.ms_narrow[kind] = elapsed(ctx, EV_TMPA, EV_TMPB);
+        ctx->stats.n_launches = ctx->lc.n;
+        return SCCD_OK;
+    });
+}
+
+int sccd_ccd(
+    sccd_ctx* ctx, double min_distance, int max_iter, double tol, int allow_zero_toi, double* toi)
+{
+    return guarded(ctx, [&] {
+        if (!toi)
+            throw std::invalid_argument("ccd: null toi");
+        run_pipeline(
+            ctx, min_distance, max_iter, tol, allow_zero_toi != 0, false, toi, false, nullptr,
+            nullptr, nullptr);
+        return SCCD_OK;
+    });
+}
+
+int sccd_ccd_collisions(
+    sccd_ctx* ctx, double min_distance, int max_iter, double tol, int allow_zero_toi,
+    double* toi, sccd_pair* ids, double* tois, int64_t cap, int64_t* n_vf, int64_t* n_ee)
+{
+    return guarded(ctx, [&] {
+        if (!toi)
+            throw std::invalid_argument("ccd_collisions: null toi");
+        std::vector<sccd_pair> cid;
+        std::vector<double> ct;
+        int64_t nc[2] = { 0, 0 };
+        run_pipeline(
+            ctx, min_distance, max_iter, tol, allow_zero_toi != 0, false, toi, true, &cid, &ct, nc);
+        const int64_t k = std::min<int64_t>(cap, (int64_t)cid.size());
+        if (ids && k > 0)
+            std::memcpy(ids, cid.data(), (size_t)k * sizeof(sccd_pair));
+        if (tois && k > 0)
+            std::memcpy(tois, ct.data(), (size_t)k * 8);
+        if (n_vf)
+            *n_vf = nc[0];
+        if (n_ee)
+            *n_ee = nc[1];
+        return SCCD_OK;
+    });
+}
+
+int sccd_ccd_host(
+    sccd_ctx* ctx, const double* V0, const double* V1, int64_t nV, const int32_t* E, int64_t nE,
+    const int32_t* F, int64_t nF, double min_distance, int max_iter, double tol,
+    int allow_zero_toi, double* toi)
+{
+    return guarded(ctx, [&] {
+        if (!toi)
+            throw std::invalid_argument("ccd: null toi");
+        upload_mesh(ctx, V0, V1, nV, E, nE, F, nF, false);
+        run_pipeline(
+            ctx, min_distance, max_iter, tol, allow_zero_toi != 0, false, toi, false, nullptr,
+            nullptr, nullptr);
+        return SCCD_OK;
+    });
+}
+
+int sccd_ipc_ccd_strategy(
+    sccd_ctx* ctx, double min_distance, int max_iter, double tol, double* toi)
+{
+    return guarded(ctx, [&] {
+        if (!toi)
+            throw std::invalid_argument("ipc_ccd_strategy: null toi");
+        run_pipeline(
+            ctx, min_distance, max_iter, tol, true, true, toi, false, nullptr, nullptr, nullptr);
+        return SCCD_OK;
+    });
+}
+
+int sccd_get_stats(const sccd_ctx* ctx, sccd_stats* out)
+{
+    if (!ctx || !out)
+        return SCCD_ERR_ARG;
+    *out = ctx->stats;
+    return SCCD_OK;
+}
+
+int sccd_synchronize(sccd_ctx* ctx)
+{
+    return guarded(ctx, [&] {
+        SCCD_CUDA(cudaStreamSynchronize(ctx->stream));
+        return SCCD_OK;
+    });
+}
+
+} // extern "C"

@@ -1,0 +1,145 @@
+// AABB construction on the device (north-star item 1).
+//
+// Replaces the reference's host/TBB box builders + 64 B/box AoS upload + split_boxes
+// kernel (cuda/broad_phase/aabb.cu:26-35, 40-72, 115-229) with two coalesced kernels that
+// read the two-frame vertex / edge / face buffers directly and emit, per box, the exact
+// 64-byte record (x interval, yz mini-box, ids) plus the 32-bit radix key of min.x.
+// Results are bit-identical to the reference's boxes: nextafter() in double is exact on
+// the device and min/max/add are correctly rounded.
+#include "common.cuh"
+
+#include <cfloat>
+
+namespace sccd {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ double next_down(double x) { return nextafter(x, -DBL_MAX); }
+__device__ __forceinline__ double next_up(double x) { return nextafter(x, DBL_MAX); }
+
+__device__ __forceinline__ void store_record(
+    const BoxArrays& out, uint32_t* keys, int k, const double lo[3], const double hi[3],
+    int4 id)
+{
+    out.x[k] = make_double2(lo[0], hi[0]);
+    out.yz[k] = make_double4(lo[1], lo[2], hi[1], hi[2]);
+    out.id[k] = id;
+    // sort key: min.x rounded DOWN to f32 (conservative for the f32 prefilter sweep)
+    keys[k] = float_to_key(__double2float_rd(lo[0]));
+}
+
+// aabb.cu:146-184 build_vertex_boxes(V0, V1, r) + from_point + conservative_inflation.
+__global__ void __launch_bounds__(kThreads) vertex_boxes_kernel(
+    const double* __restrict__ V0, const double* __restrict__ V1, int nV, double radius_up,
+    VertexRec* __restrict__ vtab, double* __restrict__ vbox, BoxArrays vf, uint32_t* vf_keys)
+{
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= nV)
+        return;
+    double p0[3], p1[3], lo[3], hi[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        p0[k] = V0[i + (size_t)k * nV];
+        p1[k] = V1[i + (size_t)k * nV];
+        // aabb.cu:29-34 on each end point, then AABB(a, b) = componentwise min / max
+        const double a_lo = __dsub_rn(next_down(p0[k]), radius_up);
+        const double b_lo = __dsub_rn(next_down(p1[k]), radius_up);
+        const double a_hi = __dadd_rn(next_up(p0[k]), radius_up);
+        const double b_hi = __dadd_rn(next_up(p1[k]), radius_up);
+        lo[k] = fmin(a_lo, b_lo);
+        hi[k] = fmax(a_hi, b_hi);
+    }
+    VertexRec r;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        r.p0[k] = p0[k];
+        r.p1[k] = p1[k];
+    }
+    vtab[i] = r;
+    double2* vb = reinterpret_cast<double2*>(vbox + (size_t)6 * i);
+    vb[0] = make_double2(lo[0], lo[1]);
+    vb[1] = make_double2(lo[2], hi[0]);
+    vb[2] = make_double2(hi[1], hi[2]);
+    // aabb.cu:180-181 ids; element id flipped because vertices are list A of the
+    // vertex-face sweep (broad_phase.cu:20-26).
+    store_record(vf, vf_keys, i, lo, hi, make_int4(i, -i - 1, -i - 1, -i - 1));
+}
+
+__device__ __forceinline__ void load_vbox(
+    const double* __restrict__ vbox, int v, double lo[3], double hi[3])
+{
+    const double2* vb = reinterpret_cast<const double2*>(vbox + (size_t)6 * v);
+    const double2 a = __ldg(vb), b = __ldg(vb + 1), c = __ldg(vb + 2);
+    lo[0] = a.x;
+    lo[1] = a.y;
+    lo[2] = b.x;
+    hi[0] = b.y;
+    hi[1] = c.x;
+    hi[2] = c.y;
+}
+
+// aabb.cu:186-229 build_edge_boxes / build_face_boxes (union of vertex boxes).
+__global__ void __launch_bounds__(kThreads) element_boxes_kernel(
+    const double* __restrict__ vbox, const int32_t* __restrict__ E, int nE,
+    const int32_t* __restrict__ F, int nF, int nV, BoxArrays eb, uint32_t* e_keys,
+    BoxArrays vf, uint32_t* vf_keys)
+{
+    const int t = blockIdx.x * kThreads + threadIdx.x;
+    if (t < nE) {
+        const int e0 = E[t], e1 = E[t + (size_t)nE];
+        double lo[3], hi[3], lo1[3], hi1[3];
+        load_vbox(vbox, e0, lo, hi);
+        load_vbox(vbox, e1, lo1, hi1);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            lo[k] = fmin(lo[k], lo1[k]);
+            hi[k] = fmax(hi[k], hi1[k]);
+        }
+        store_record(eb, e_keys, t, lo, hi, make_int4(e0, e1, -e0 - 1, t));
+    } else if (t < nE + nF) {
+        const int f = t - nE;
+        const int f0 = F[f], f1 = F[f + (size_t)nF], f2 = F[f + (size_t)2 * nF];
+        double lo[3], hi[3], lo1[3], hi1[3], lo2[3], hi2[3];
+        load_vbox(vbox, f0, lo, hi);
+        load_vbox(vbox, f1, lo1, hi1);
+        load_vbox(vbox, f2, lo2, hi2);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            lo[k] = fmin(fmin(lo[k], lo1[k]), lo2[k]);
+            hi[k] = fmax(fmax(hi[k], hi1[k]), hi2[k]);
+        }
+        store_record(vf, vf_keys, nV + f, lo, hi, make_int4(f0, f1, f2, f));
+    }
+}
+
+} // namespace
+
+void launch_vertex_boxes(
+    const double* V0, const double* V1, int nV, double radius_up, VertexRec* vtab,
+    double* vbox, BoxArrays vf_unsorted, uint32_t* vf_keys, cudaStream_t s, LaunchCounter& lc)
+{
+    if (nV <= 0)
+        return;
+    vertex_boxes_kernel<<<(nV + kThreads - 1) / kThreads, kThreads, 0, s>>>(
+        V0, V1, nV, radius_up, vtab, vbox, vf_unsorted, vf_keys);
+    SCCD_CUDA(cudaGetLastError());
+    lc.n++;
+}
+
+void launch_element_boxes(
+    const double* vbox, const int32_t* E, int nE, const int32_t* F, int nF, int nV,
+    BoxArrays e_unsorted, uint32_t* e_keys, BoxArrays vf_unsorted, uint32_t* vf_keys,
+    cudaStream_t s, LaunchCounter& lc)
+{
+    const int n = nE + nF;
+    if (n <= 0)
+        return;
+    element_boxes_kernel<<<(n + kThreads - 1) / kThreads, kThreads, 0, s>>>(
+        vbox, E, nE, F, nF, nV, e_unsorted, e_keys, vf_unsorted, vf_keys);
+    SCCD_CUDA(cudaGetLastError());
+    lc.n++;
+}
+
+} // namespace sccd

@@ -1,0 +1,235 @@
+// Shared declarations of the B200 CCD hot path (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/sccd.h"
+
+namespace sccd {
+
+// ---- errors ---------------------------------------------------------------------
+struct CudaError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+inline void check(cudaError_t e, const char* what, const char* file, int line)
+{
+    if (e != cudaSuccess) {
+        char buf[512];
+        snprintf(
+            buf, sizeof(buf), "%s: %s (%s) at %s:%d", what, cudaGetErrorName(e),
+            cudaGetErrorString(e), file, line);
+        throw CudaError(buf);
+    }
+}
+#define SCCD_CUDA(expr) ::sccd::check((expr), #expr, __FILE__, __LINE__)
+
+// ---- grow-only device buffer (kept across calls: frame-to-frame reuse) -----------
+struct DevBuf {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    ~DevBuf() { release(); }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    void release()
+    {
+        if (ptr)
+            cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+    // Contents are NOT preserved when the buffer grows.
+    void* reserve(size_t bytes)
+    {
+        if (bytes > cap) {
+            release();
+            size_t want = bytes + bytes / 8 + 256;
+            if (cudaMalloc(&ptr, want) != cudaSuccess) {
+                (void)cudaGetLastError();
+                want = bytes;
+                SCCD_CUDA(cudaMalloc(&ptr, want));
+            }
+            cap = want;
+        }
+        return ptr;
+    }
+    template <typename T> T* as() const { return static_cast<T*>(ptr); }
+};
+
+// ---- HBM layouts -------------------------------------------------------------------
+// Per-vertex two-frame record gathered by the narrow phase: (x0 y0 z0 x1 y1 z1).
+struct __align__(16) VertexRec {
+    double p0[3];
+    double p1[3];
+};
+static_assert(sizeof(VertexRec) == 48, "VertexRec");
+
+// Exact box record, 64 bytes split in three arrays so every access is one aligned
+// vector load: X = (xmin, xmax), YZ = (ymin, zmin, ymax, zmax), ID = (v0, v1, v2, elem).
+// elem is the element id, flipped (-id-1) for list A of a two-list sweep exactly as the
+// reference does (cuda/broad_phase/broad_phase.cu:20-26).
+struct BoxArrays {
+    double2* x = nullptr;
+    double4* yz = nullptr;
+    int4* id = nullptr;
+};
+
+// f32 conservative prefilter view of the SORTED boxes (min rounded down, max rounded
+// up): xmin / xmax separate, yz = (ymin, ymax, zmin, zmax).
+struct PrefilterArrays {
+    float* xmin = nullptr;
+    float* xmax = nullptr;
+    float4* yz = nullptr;
+};
+
+// One sorted list ready for sweeping.
+struct SortedList {
+    int n = 0;
+    bool two_lists = false;
+    BoxArrays box;      // sorted, exact
+    PrefilterArrays pf; // sorted, f32
+};
+
+#ifdef __CUDACC__
+// read-only 32-byte load (there is no __ldg overload for double4)
+__device__ __forceinline__ double4 ldg_d4(const double4* p)
+{
+    const double2* q = reinterpret_cast<const double2*>(p);
+    const double2 a = __ldg(q), b = __ldg(q + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+#endif
+
+// order-preserving float <-> uint32 key
+__host__ __device__ inline uint32_t float_to_key(float f)
+{
+#ifdef __CUDA_ARCH__
+    uint32_t u = __float_as_uint(f);
+#else
+    union {
+        float f;
+        uint32_t u;
+    } c;
+    c.f = f;
+    uint32_t u = c.u;
+#endif
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ inline float key_to_float(uint32_t k)
+{
+    uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    union {
+        float f;
+        uint32_t u;
+    } c;
+    c.u = u;
+    return c.f;
+#endif
+}
+
+// ---- narrow-phase parameters -----------------------------------------------------------
+struct NarrowParams {
+    double ms;
+    double tol;     // co-domain tolerance
+    int max_iter;   // < 0: unlimited
+    int allow_zero_toi;
+    int use_ms;     // ms > 0 (selects the error filter, root_finder.cu:95-122)
+};
+
+// Bounded global work queue of sub-boxes handed between lanes (56-byte payload, the size
+// of the reference's CCDDomain, plus a ready ticket).
+struct __align__(16) WorkItem {
+    double lo[3];
+    double w[3];
+    unsigned long long ready; // ticket + 1 once the payload is visible
+    uint32_t query;
+    uint32_t pad;
+};
+static_assert(sizeof(WorkItem) == 64, "WorkItem");
+
+struct NarrowCounters {
+    unsigned long long next_query;  // next unclaimed query index
+    unsigned long long q_tail;      // tickets reserved by producers
+    unsigned long long q_head;      // tickets reserved by consumers
+    long long outstanding;          // sub-trees alive (claimed or queued)
+    int hungry;                     // lanes with nothing to do
+    int overflow;                   // a donation was refused because the queue was full
+    unsigned long long box_checks;
+    unsigned long long donated;
+    unsigned long long capped;
+    double toi;                     // shared earliest toi
+};
+
+// ---- kernel launchers (defined in the .cu files) -----------------------------------
+struct LaunchCounter {
+    int64_t n = 0;
+};
+
+void launch_vertex_boxes(
+    const double* V0, const double* V1, int nV, double radius_up, VertexRec* vtab,
+    double* vbox /* 6*nV: min xyz, max xyz */, BoxArrays vf_unsorted, uint32_t* vf_keys,
+    cudaStream_t s, LaunchCounter& lc);
+void launch_element_boxes(
+    const double* vbox, const int32_t* E, int nE, const int32_t* F, int nF, int nV,
+    BoxArrays e_unsorted, uint32_t* e_keys, BoxArrays vf_unsorted, uint32_t* vf_keys,
+    cudaStream_t s, LaunchCounter& lc);
+
+size_t sort_temp_bytes(int n);
+void launch_sort_and_gather(
+    int n, uint32_t* keys_in, uint32_t* keys_tmp, uint32_t* idx_in, uint32_t* idx_out,
+    void* temp, size_t temp_bytes, BoxArrays unsorted, SortedList out, cudaStream_t s,
+    LaunchCounter& lc);
+
+// window[i] = number of candidates after owner i whose f32 xmin <= owner's f32 xmax
+void launch_sweep_windows(
+    const SortedList& L, uint32_t* window, cudaStream_t s, LaunchCounter& lc);
+void launch_sweep_count(
+    const SortedList& L, int owner_lo, int owner_hi, uint32_t* counts,
+    unsigned long long* n_candidates, cudaStream_t s, LaunchCounter& lc);
+// counts / offsets are indexed relative to the first owner of the count pass (shard_lo);
+// the fill of owner range [owner_lo, owner_hi) writes pairs[offsets[i] - offsets[owner_lo]..).
+void launch_sweep_fill(
+    const SortedList& L, int shard_lo, int owner_lo, int owner_hi,
+    const unsigned long long* offsets, sccd_pair* pairs, cudaStream_t s, LaunchCounter& lc);
+size_t scan_temp_bytes(int n);
+// offsets[0..n] = exclusive prefix sum of counts[0..n) (offsets[n] = total)
+void launch_scan_u32_to_u64(
+    const uint32_t* counts, unsigned long long* offsets, int n, void* temp,
+    size_t temp_bytes, cudaStream_t s, LaunchCounter& lc);
+// first index e in (lo, hi] with offsets[e] - offsets[lo] > budget, minus one (>= lo+1 if
+// the first owner alone fits); result written to *d_out
+void launch_find_chunk_end(
+    const unsigned long long* offsets, int lo, int hi, unsigned long long budget,
+    int* d_out, cudaStream_t s, LaunchCounter& lc);
+
+struct NarrowInput {
+    // mesh mode
+    const VertexRec* vtab = nullptr;
+    const int32_t* E = nullptr;
+    const int32_t* F = nullptr;
+    int nE = 0, nF = 0;
+    const sccd_pair* pairs = nullptr;
+    // direct mode (n x 24 doubles)
+    const double* queries = nullptr;
+    long long n = 0;
+};
+void launch_narrow_phase(
+    bool is_vf, const NarrowInput& in, const NarrowParams& p, NarrowCounters* counters,
+    WorkItem* queue, long long queue_cap, double* toi_per_query, unsigned int* checks_per_query,
+    int num_sms, cudaStream_t s, LaunchCounter& lc);
+void launch_fill_f64(double* p, long long n, double v, cudaStream_t s, LaunchCounter& lc);
+// compacts (pair, toi) of queries with toi < 1 ; *d_count receives the number
+void launch_compact_collisions(
+    const sccd_pair* pairs, const double* toi_q, long long n, sccd_pair* out_ids,
+    double* out_toi, unsigned long long* d_count, cudaStream_t s, LaunchCounter& lc);
+
+} // namespace sccd

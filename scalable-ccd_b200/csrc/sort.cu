@@ -1,0 +1,108 @@
+// Major-axis sort (north-star item 2a).
+//
+// Replaces thrust::sort_by_key with a comparator on 16 B keys / 48 B values, the D2D copy,
+// flip_element_ids and thrust::merge_by_key of the reference
+// (cuda/broad_phase/aabb.cu:107-109, broad_phase.cu:57-101) by:
+//   1. a 4-pass LSD radix sort of (u32 key = order-preserving f32(min.x rounded down),
+//      u32 box index)  -- 8 B per box per pass instead of 64 B;
+//   2. ONE gather that moves each 64 B exact record to its sorted position and emits the
+//      24 B f32 prefilter view (min rounded down / max rounded up) the sweep streams.
+// The radix sort is stable, so ties keep element order and the result is deterministic.
+// The vertex-face list is sorted as one tagged list (vertex element ids are already
+// flipped at build time), so no merge is needed.
+#include "common.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+
+namespace sccd {
+
+namespace {
+constexpr int kThreads = 256;
+
+__global__ void __launch_bounds__(kThreads) iota_kernel(uint32_t* idx, int n)
+{
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i < n)
+        idx[i] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(kThreads) gather_sorted_kernel(
+    int n, const uint32_t* __restrict__ sorted_keys, const uint32_t* __restrict__ sorted_idx,
+    BoxArrays in, BoxArrays out, PrefilterArrays pf)
+{
+    const int j = blockIdx.x * kThreads + threadIdx.x;
+    if (j >= n)
+        return;
+    const uint32_t src = sorted_idx[j];
+    const double2 x = __ldg(&in.x[src]);
+    const double4 yz = ldg_d4(&in.yz[src]);
+    const int4 id = __ldg(&in.id[src]);
+    out.x[j] = x;
+    out.yz[j] = yz;
+    out.id[j] = id;
+    pf.xmin[j] = key_to_float(sorted_keys[j]); // == __double2float_rd(x.x)
+    pf.xmax[j] = __double2float_ru(x.y);
+    pf.yz[j] = make_float4(
+        __double2float_rd(yz.x), __double2float_ru(yz.z), __double2float_rd(yz.y),
+        __double2float_ru(yz.w));
+}
+
+struct U32ToU64 {
+    __host__ __device__ unsigned long long operator()(uint32_t v) const { return v; }
+};
+} // namespace
+
+size_t sort_temp_bytes(int n)
+{
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(
+        nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+        (const uint32_t*)nullptr, (uint32_t*)nullptr, n > 0 ? n : 1, 0, 32);
+    return bytes;
+}
+
+void launch_sort_and_gather(
+    int n, uint32_t* keys_in, uint32_t* keys_tmp, uint32_t* idx_in, uint32_t* idx_out,
+    void* temp, size_t temp_bytes, BoxArrays unsorted, SortedList out, cudaStream_t s,
+    LaunchCounter& lc)
+{
+    if (n <= 0)
+        return;
+    const int grid = (n + kThreads - 1) / kThreads;
+    iota_kernel<<<grid, kThreads, 0, s>>>(idx_in, n);
+    SCCD_CUDA(cudaGetLastError());
+    lc.n++;
+    SCCD_CUDA(cub::DeviceRadixSort::SortPairs(
+        temp, temp_bytes, (const uint32_t*)keys_in, keys_tmp, (const uint32_t*)idx_in,
+        idx_out, n, 0, 32, s));
+    lc.n += 6; // histogram + exclusive sum + 4 onesweep passes (CUB's sm_100 policy)
+    gather_sorted_kernel<<<grid, kThreads, 0, s>>>(
+        n, keys_tmp, idx_out, unsorted, out.box, out.pf);
+    SCCD_CUDA(cudaGetLastError());
+    lc.n++;
+}
+
+size_t scan_temp_bytes(int n)
+{
+    size_t bytes = 0;
+    cub::TransformInputIterator<unsigned long long, U32ToU64, const uint32_t*> it(
+        nullptr, U32ToU64());
+    cub::DeviceScan::ExclusiveSum(
+        nullptr, bytes, it, (unsigned long long*)nullptr, n > 0 ? n + 1 : 1);
+    return bytes;
+}
+
+void launch_scan_u32_to_u64(
+    const uint32_t* counts, unsigned long long* offsets, int n, void* temp,
+    size_t temp_bytes, cudaStream_t s, LaunchCounter& lc)
+{
+    // counts has n+1 readable entries (the last one is zero) so that offsets[n] = total.
+    cub::TransformInputIterator<unsigned long long, U32ToU64, const uint32_t*> it(
+        counts, U32ToU64());
+    SCCD_CUDA(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, it, offsets, n + 1, s));
+    lc.n += 2;
+}
+
+} // namespace sccd

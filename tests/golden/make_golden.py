@@ -1,0 +1,125 @@
+"""Freeze golden vectors from the UNMODIFIED reference (oracle/_ref, see oracle/Makefile).
+
+  python tests/golden/make_golden.py cpu  [outdir]   # reference CPU broad phase (no GPU)
+  python tests/golden/make_golden.py cuda [outdir]   # reference CUDA path (needs a GPU)
+
+Inputs are the deterministic generators in scalable-ccd_b200/scenes.py; each fixture
+stores a hash of its inputs so generator drift is detected.  Outputs committed under
+tests/golden/ are what tests/test_oracle.py and tests/test_gpu_parity.py check against.
+"""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from _pkg import load_package  # noqa: E402
+from oracle import orc  # noqa: E402
+
+sccd = load_package()
+scenes = sccd.scenes
+
+
+def sha(*arrays):
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def scene_hash(s):
+    return sha(s["V0"], s["V1"], s["E"], s["F"])
+
+
+def small_scene():
+    return scenes.cloth_on_sphere(31, seed=7, sphere="uv")
+
+
+def c5_small(n=3000):
+    return scenes.queries_c5(n, seed=4)
+
+
+NARROW_CASES = [  # (name, ms, max_iter, tol, allow_zero_toi)
+    ("default", 0.0, -1, 1e-6, True),
+    ("tight", 0.0, -1, 1e-9, True),
+    ("ms", 1e-8, -1, 1e-6, True),
+    ("nozero", 0.0, -1, 1e-6, False),
+]
+
+
+def make_cpu(out):
+    fix = {}
+    for name, s in (("c1", scenes.scene_c1()), ("small", small_scene())):
+        r = orc.ref_cpu_broad_phase(s)
+        vf, ee = orc.canonical(r["vf"]), orc.canonical(r["ee"])
+        assert len(vf) == r["n_vf"] and len(ee) == r["n_ee"], "reference emitted duplicates"
+        fix[name] = {
+            "scene_sha256": scene_hash(s), "n_vf": int(r["n_vf"]), "n_ee": int(r["n_ee"]),
+            "next_axes": list(r["axes"]), "vf_sha256": sha(vf), "ee_sha256": sha(ee),
+            "sizes": [int(s["V0"].shape[0]), int(s["E"].shape[0]), int(s["F"].shape[0])],
+        }
+        vb, eb, fb = orc.ref_cpu_build_boxes(s)
+        fix[name]["boxes_sha256"] = sha(vb, eb, fb)
+        if name == "small":
+            np.savez_compressed(os.path.join(out, "broad_small_ref_cpu.npz"), vf=vf, ee=ee)
+    with open(os.path.join(out, "broad_ref_cpu.json"), "w") as f:
+        json.dump(fix, f, indent=1, sort_keys=True)
+    print("wrote", out, json.dumps(fix)[:300])
+
+
+def make_cuda(out):
+    meta = {}
+    # 1. whole pipeline, TOI_PER_QUERY build: toi + collisions
+    for name, s in (("small", small_scene()), ("c1", scenes.scene_c1())):
+        r = orc.ref_cuda_ccd(s, per_query=True, coll_cap=1 << 22)
+        r0 = orc.ref_cuda_ccd(s, per_query=False)
+        order = np.lexsort((r["coll_ids"][:, 1], r["coll_ids"][:, 0]))
+        meta[f"ccd_{name}"] = {"scene_sha256": scene_hash(s), "toi_pq": r["toi"],
+                               "toi": r0["toi"], "n_coll": int(r["n_coll"])}
+        np.savez_compressed(os.path.join(out, f"ccd_{name}_ref_cuda.npz"),
+                            coll_ids=r["coll_ids"][order], coll_toi=r["coll_toi"][order],
+                            toi=np.float64(r0["toi"]), toi_pq=np.float64(r["toi"]))
+        b = orc.ref_cuda_broad_phase(s)
+        vf, ee = orc.canonical(b["vf"]), orc.canonical(b["ee"])
+        meta[f"broad_{name}"] = {"n_vf": int(b["n_vf"]), "n_ee": int(b["n_ee"]),
+                                 "n_vf_unique": len(vf), "n_ee_unique": len(ee),
+                                 "vf_sha256": sha(vf), "ee_sha256": sha(ee)}
+        # IPC strategy
+        meta[f"ipc_{name}"] = {}
+        L = orc.ref_cuda(False)
+        import ctypes as C
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        for md, mi in ((0.0, -1), (1e-4, 200)):
+            el = C.c_double(0)
+            t = L.ref_cuda_ipc_ccd_strategy(
+                p(s["V0"]), p(s["V1"]), C.c_int64(s["V0"].shape[0]), p(s["E"]),
+                C.c_int64(s["E"].shape[0]), p(s["F"]), C.c_int64(s["F"].shape[0]),
+                C.c_double(md), C.c_int(mi), C.c_double(1e-6), C.byref(el))
+            meta[f"ipc_{name}"][f"md{md}_mi{mi}"] = t
+    # 2. root finder on adversarial query arrays
+    ee_q, vf_q = c5_small()
+    arrays = {}
+    for cname, ms, mi, tol, az in NARROW_CASES:
+        for kind, q in (("vf", vf_q), ("ee", ee_q)):
+            r = orc.ref_cuda_narrow_queries(q, kind == "vf", ms, mi, tol, az, 1.0, True)
+            g = orc.ref_cuda_narrow_queries(q, kind == "vf", ms, mi, tol, az, 1.0, False)
+            arrays[f"{cname}_{kind}_tpq"] = r["toi_per_query"]
+            arrays[f"{cname}_{kind}_toi"] = np.float64(g["toi"])
+            meta[f"narrow_{cname}_{kind}"] = {
+                "toi_pq_build": r["toi"], "toi": g["toi"], "reruns": [r["reruns"], g["reruns"]],
+                "hits": int((r["toi_per_query"] < 1).sum())}
+    meta["c5_sha256"] = sha(ee_q, vf_q)
+    np.savez_compressed(os.path.join(out, "narrow_c5_ref_cuda.npz"), **arrays)
+    with open(os.path.join(out, "ref_cuda_meta.json"), "w") as f:
+        json.dump(meta, f, indent=1, sort_keys=True)
+    print(json.dumps(meta, indent=1)[:3000])
+
+
+if __name__ == "__main__":
+    mode = sys.argv[1]
+    out = sys.argv[2] if len(sys.argv) > 2 else os.path.dirname(os.path.abspath(__file__))
+    os.makedirs(out, exist_ok=True)
+    {"cpu": make_cpu, "cuda": make_cuda}[mode](out)

@@ -1,0 +1,54 @@
+"""The C-ABI library loads and exports every symbol include/sccd.h declares (no compute)."""
+import ctypes as C
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "sccd.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sccd_[a-z_]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree(sccd):
+    assert header_symbols() == sorted(sccd.capi.SYMBOLS)
+
+
+def test_library_exports_all_symbols(sccd):
+    L = sccd.capi.load()
+    for name in header_symbols():
+        assert hasattr(L, name), f"{name} not exported by libsccd_b200.so"
+    assert b"sm_100a" in L.sccd_version()
+
+
+def test_stats_struct_layout_matches_header(sccd):
+    # 7 int64[2] + 2 int64 + 7 floats (+ padding to 8)
+    assert C.sizeof(sccd.capi.Stats) == 7 * 16 + 16 + 32
+
+
+def test_no_cpu_fallback(sccd):
+    """Without a usable sm_100 device the product fails loudly instead of falling back."""
+    import torch
+    if torch.cuda.is_available():
+        c = sccd.Context(0)
+        c.close()
+        return
+    try:
+        sccd.Context(0)
+    except sccd.SccdError as e:
+        assert e.code == sccd.capi.ERR_CUDA
+    else:
+        raise AssertionError("Context() must fail without a GPU")
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "scalable-ccd_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("oracle/", "").lower() or f == "__init__.py" \
+                    or "import oracle" not in text and "from oracle" not in text, f
+                assert "from oracle" not in text and "import oracle" not in text, f

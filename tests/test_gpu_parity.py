@@ -1,0 +1,266 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs, and against golden vectors frozen from the unmodified reference.
+
+Bar: boxes bit-exact, overlap sets bit-exact after canonical sort, per-query hit/miss equal,
+per-query and global TOI bit-equal for max_iter < 0 (tolerance 0.0: the arithmetic contract
+reproduces the reference's rounding), conservative (<=) for capped queries."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    return torch
+
+
+def run_broad(ctx, scene, r=0.0):
+    ctx.upload_mesh(scene["V0"], scene["V1"], scene["E"], scene["F"])
+    ctx.build_boxes(r)
+    return ctx.broad_phase(0), ctx.broad_phase(1)
+
+
+@pytest.mark.parametrize("r", [0.0, 1e-3])
+def test_boxes_bit_exact(ctx, orc, scene_c1, r):
+    ctx.upload_mesh(scene_c1["V0"], scene_c1["V1"], scene_c1["E"], scene_c1["F"])
+    ctx.build_boxes(r)
+    got = ctx.get_boxes()
+    want = orc.build_boxes(scene_c1, r)
+    for g, w in zip(got, want):
+        assert g.tobytes() == w.tobytes()
+
+
+@pytest.mark.parametrize("which", ["small", "c1"])
+def test_overlap_sets_bit_exact(ctx, orc, scene_c1, scene_small, which):
+    s = {"small": scene_small, "c1": scene_c1}[which]
+    vf, ee = run_broad(ctx, s)
+    vb, eb, fb = orc.build_boxes(s)
+    ovf, _ = orc.sort_and_sweep_two_lists(vb, fb, 0)
+    oee, _ = orc.sort_and_sweep(eb, 0)
+    assert len(vf) == len(ovf) and len(ee) == len(oee)           # no duplicates
+    assert np.array_equal(orc.canonical(vf), orc.canonical(ovf))
+    assert np.array_equal(orc.canonical(ee), orc.canonical(oee))
+    gold = json.load(open(os.path.join(GOLD, "broad_ref_cpu.json")))[which]
+    assert (len(vf), len(ee)) == (gold["n_vf"], gold["n_ee"])      # reference CPU golden
+
+
+def test_overlap_list_is_deterministic_and_chunking_is_lossless(ctx, sccd, scene_c1):
+    vf1, ee1 = run_broad(ctx, scene_c1)
+    vf2, ee2 = run_broad(ctx, scene_c1)
+    assert np.array_equal(vf1, vf2) and np.array_equal(ee1, ee2)   # same ORDER, not just set
+    ctx.set_max_pairs_per_chunk(5000)                               # force ~15 chunks
+    try:
+        vf3, ee3 = run_broad(ctx, scene_c1)
+    finally:
+        ctx.set_max_pairs_per_chunk(0)
+    assert np.array_equal(vf1, vf3) and np.array_equal(ee1, ee3)
+
+
+def test_inflated_boxes_and_brute_force(ctx, orc, scene_small):
+    vf, ee = run_broad(ctx, scene_small, r=5e-3)
+    vb, eb, fb = orc.build_boxes(scene_small, 5e-3)
+    assert np.array_equal(orc.canonical(vf), orc.canonical(orc.brute_force(vb, fb)))
+    assert np.array_equal(orc.canonical(ee), orc.canonical(orc.brute_force(eb)))
+
+
+def test_ragged_and_empty_inputs(ctx, orc, sccd):
+    # a single triangle: 3 V / 3 E / 1 F -> no admissible pairs at all
+    V = np.asfortranarray(np.array([[0., 0, 0], [1, 0, 0], [0, 1, 0]]))
+    F = np.asfortranarray(np.array([[0, 1, 2]], dtype=np.int32))
+    E = np.asfortranarray(sccd.scenes.edges_from_faces(F))
+    ctx.upload_mesh(V, V.copy(order="F"), E, F)
+    assert ctx.ccd() == 1.0
+    assert len(ctx.broad_phase(0)) == 0 and len(ctx.broad_phase(1)) == 0
+    # no faces / no edges at all
+    E0 = np.zeros((0, 2), np.int32, order="F")
+    F0 = np.zeros((0, 3), np.int32, order="F")
+    ctx.upload_mesh(V, V.copy(order="F"), E0, F0)
+    assert ctx.ccd() == 1.0
+    # identical boxes (all ties on the sort key): 64 coincident, disconnected edges
+    n = 64
+    Vt = np.asfortranarray(np.tile(np.array([[0., 0, 0], [1, 1, 1]]), (n, 1)))
+    Et = np.asfortranarray(np.arange(2 * n, dtype=np.int32).reshape(n, 2))
+    ctx.upload_mesh(Vt, Vt.copy(order="F"), Et, F0)
+    ctx.build_boxes(0.0)
+    assert len(ctx.broad_phase(1)) == n * (n - 1) // 2
+
+
+def test_broad_phase_before_build_is_an_error(sccd):
+    c = sccd.Context(0)
+    with pytest.raises(sccd.SccdError) as e:
+        c.broad_phase_begin(0)
+    assert e.value.code == sccd.capi.ERR_STATE
+    c.close()
+
+
+def _narrow_gpu(ctx, torch, kind, q, **kw):
+    tq = torch.empty(len(q), dtype=torch.float64, device="cuda")
+    toi = ctx.narrow_phase_queries(kind, q, d_toi_per_query=tq.data_ptr(), **kw)
+    return toi, tq.cpu().numpy()
+
+
+CASES = {"default": dict(ms=0.0, max_iter=-1, tol=1e-6, allow_zero_toi=True),
+         "tight": dict(ms=0.0, max_iter=-1, tol=1e-9, allow_zero_toi=True),
+         "ms": dict(ms=1e-8, max_iter=-1, tol=1e-6, allow_zero_toi=True),
+         "nozero": dict(ms=0.0, max_iter=-1, tol=1e-6, allow_zero_toi=False)}
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_adversarial_queries_match_oracle(ctx, orc, sccd, torch_cuda, case):
+    ee, vf = sccd.scenes.queries_c5(3000, seed=4)
+    kw = CASES[case]
+    for kind, q in ((0, vf), (1, ee)):
+        toi, tpq = _narrow_gpu(ctx, torch_cuda, kind, q, **kw)
+        otoi, otpq, _ = orc.narrow_phase(q, kind == 0, kw["ms"], kw["max_iter"], kw["tol"],
+                                         kw["allow_zero_toi"])
+        assert np.array_equal(tpq < 1, otpq < 1)      # hit / miss
+        assert np.array_equal(tpq, otpq)              # bit-exact per-query toi (tolerance 0)
+        assert toi == otoi
+        # shared-bound mode (default reference build) returns the same minimum
+        assert ctx.narrow_phase_queries(kind, q, **kw) == otoi
+
+
+def test_adversarial_queries_match_reference_cuda_golden(ctx, sccd, torch_cuda):
+    path = os.path.join(GOLD, "narrow_c5_ref_cuda.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden not generated yet")
+    z = np.load(path)
+    ee, vf = sccd.scenes.queries_c5(3000, seed=4)
+    for case, kw in CASES.items():
+        for kind, name, q in ((0, "vf", vf), (1, "ee", ee)):
+            toi, tpq = _narrow_gpu(ctx, torch_cuda, kind, q, **kw)
+            assert np.array_equal(tpq, z[f"{case}_{name}_tpq"]), (case, name)
+            assert toi == float(z[f"{case}_{name}_toi"])
+
+
+def test_iteration_cap_is_conservative(ctx, orc, sccd, torch_cuda):
+    ee, vf = sccd.scenes.queries_c5(2000, seed=12)
+    for kind, q in ((0, vf), (1, ee)):
+        _, full, _ = orc.narrow_phase(q, kind == 0, max_iter=-1)
+        toi, capped = _narrow_gpu(ctx, torch_cuda, kind, q, max_iter=60)
+        assert ctx.stats()["n_capped"][kind] > 0
+        assert np.all(capped <= full)                  # never later than the exact answer
+        under = ~(capped < full)                       # queries the cap did not touch
+        assert np.array_equal(capped[under], full[under])
+        assert toi <= min(1.0, full.min())
+
+
+def test_bounded_queue_and_donation(sccd, orc, torch_cuda):
+    """A handful of very deep queries: the tail must be spread through the work queue and the
+    answer must not depend on it."""
+    c = sccd.Context(0)
+    c.set_queue_capacity(1)            # clamped to the minimum the kernel accepts
+    ee, vf = sccd.scenes.queries_c5(64, seed=5)
+    for kind, q in ((0, vf), (1, ee)):
+        toi, tpq = _narrow_gpu(c, torch_cuda, kind, q, tol=1e-9)
+        otoi, otpq, _ = orc.narrow_phase(q, kind == 0, tol=1e-9)
+        assert np.array_equal(tpq, otpq) and toi == otoi
+    c.close()
+
+
+@pytest.mark.parametrize("which", ["small", "c1"])
+def test_full_pipeline_matches_oracle(ctx, orc, scene_c1, scene_small, which):
+    s = {"small": scene_small, "c1": scene_c1}[which]
+    ctx.upload_mesh(s["V0"], s["V1"], s["E"], s["F"])
+    want = orc.ccd(s)
+    assert ctx.ccd() == want["toi"]
+    st = ctx.stats()
+    assert st["n_pairs"] == [len(want["vf"]), len(want["ee"])]
+    toi, (vf_ids, vf_t), (ee_ids, ee_t) = ctx.ccd_collisions()
+    assert toi == want["toi"]
+    for ids, t, pairs, tq in ((vf_ids, vf_t, want["vf"], want["toi_vf"]),
+                              (ee_ids, ee_t, want["ee"], want["toi_ee"])):
+        order = np.lexsort((ids[:, 1], ids[:, 0]))
+        hit = tq < 1
+        assert np.array_equal(ids[order], pairs[hit])      # per-query hit / miss
+        assert np.array_equal(t[order], tq[hit])           # per-query toi
+    # host-pointer entry point (upload inside the call)
+    assert ctx.ccd_host(s["V0"], s["V1"], s["E"], s["F"]) == want["toi"]
+
+
+def test_pipeline_with_min_distance_and_chunks(ctx, orc, scene_small):
+    s = scene_small
+    ctx.upload_mesh(s["V0"], s["V1"], s["E"], s["F"])
+    want = orc.ccd(s, ms=1e-4, tol=1e-5)
+    ctx.set_max_pairs_per_chunk(1000)
+    try:
+        assert ctx.ccd(ms=1e-4, tol=1e-5) == want["toi"]
+    finally:
+        ctx.set_max_pairs_per_chunk(0)
+
+
+def test_pipeline_matches_reference_cuda_golden(ctx, scene_small, scene_c1):
+    for name, s in (("small", scene_small), ("c1", scene_c1)):
+        path = os.path.join(GOLD, f"ccd_{name}_ref_cuda.npz")
+        if not os.path.exists(path):
+            pytest.skip("golden not generated yet")
+        z = np.load(path)
+        ctx.upload_mesh(s["V0"], s["V1"], s["E"], s["F"])
+        toi, (vf_ids, vf_t), (ee_ids, ee_t) = ctx.ccd_collisions()
+        assert toi == float(z["toi"])
+        ids = np.concatenate([vf_ids, ee_ids])
+        t = np.concatenate([vf_t, ee_t])
+        order = np.lexsort((ids[:, 1], ids[:, 0]))
+        assert np.array_equal(ids[order], z["coll_ids"])
+        assert np.array_equal(t[order], z["coll_toi"])
+
+
+def test_ipc_ccd_strategy(ctx, orc, scene_small):
+    """ipc_ccd_strategy.cu:54-92 composed from oracle pieces."""
+    s = scene_small
+    ctx.upload_mesh(s["V0"], s["V1"], s["E"], s["F"])
+    for md, mi in ((0.0, -1), (1e-4, 200)):
+        vb, eb, fb = orc.build_boxes(s, md)
+        vf = orc.canonical(orc.sort_and_sweep_two_lists(vb, fb, 0)[0])
+        ee = orc.canonical(orc.sort_and_sweep(eb, 0)[0])
+        toi = 1.0
+        for pairs, is_vf in ((vf, True), (ee, False)):
+            q = orc.gather_queries(s, pairs, is_vf)
+            before = toi
+            toi, _, _ = orc.narrow_phase(q, is_vf, md, mi, 1e-6, True, toi, per_query=False)
+            if toi < 1e-6:
+                toi, _, _ = orc.narrow_phase(q, is_vf, 0.0, -1, 1e-6, False, before,
+                                             per_query=False)
+                toi *= 0.8
+        got = ctx.ipc_ccd_strategy(md, mi, 1e-6)
+        if mi < 0:
+            assert got == toi
+        else:
+            assert got <= toi      # capped: conservative
+
+
+def test_device_pointer_inputs(ctx, orc, scene_small, torch_cuda):
+    torch = torch_cuda
+    s = scene_small
+    t = {k: torch.from_numpy(np.ascontiguousarray(v.T)).cuda() for k, v in s.items()}
+    ctx.upload_mesh(t["V0"].data_ptr(), t["V1"].data_ptr(), t["E"].data_ptr(), t["F"].data_ptr(),
+                    sizes=(s["V0"].shape[0], s["E"].shape[0], s["F"].shape[0]))
+    assert ctx.ccd() == orc.ccd(s)["toi"]
+
+
+def test_sharded_broad_phase_is_a_partition(sccd, orc, scene_c1):
+    """world=3 owner slices: disjoint, and their union is the single-GPU list."""
+    s = scene_c1
+    c = sccd.Context(0)
+    c.upload_mesh(s["V0"], s["V1"], s["E"], s["F"])
+    c.build_boxes(0.0)
+    full = [c.broad_phase(0), c.broad_phase(1)]
+    parts = [[], []]
+    for r in range(3):
+        c.set_shard(r, 3)
+        for k in (0, 1):
+            parts[k].append(c.broad_phase(k))
+    c.close()
+    for k in (0, 1):
+        cat = np.concatenate(parts[k])
+        assert np.array_equal(cat, full[k])          # rank order == global deterministic order
+        assert min(len(p) for p in parts[k]) > 0
