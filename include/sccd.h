@@ -77,6 +77,13 @@ typedef struct {
     float ms_sweep[2];       /* sweep count + scan + fill                               */
     float ms_narrow[2];      /* narrow phase                                            */
     float ms_total;          /* whole call, device time                                 */
+    /* single-kernel device times (summed over chunks), for roofline arithmetic */
+    float ms_k_sweep_count[2];
+    float ms_k_sweep_fill[2];
+    float ms_k_narrow[2];
+    float ms_k_boxes;        /* vertex + element box kernels                            */
+    float ms_k_gather;       /* both record gathers                                     */
+    float pad_;
 } sccd_stats;
 
 /* ---- context ------------------------------------------------------------------ */

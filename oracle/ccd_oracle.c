@@ -472,7 +472,7 @@ typedef struct {
  *   cap_mode 1 is the conservative rule the B200 path uses: a box popped after
  *   the cap is ACCEPTED at its t_lo, which can only make the answer earlier.
  */
-static void solve_query(
+static int64_t solve_query(
     const orc_query* q, int is_vf, double ms, int max_iter, double co_tol,
     int allow_zero_toi, int cap_mode, double* prune_toi, double* global_toi,
     orc_np_stats* st)
@@ -560,6 +560,7 @@ static void solve_query(
     }
     if (capped)
         st->capped_queries++;
+    return checks;
 }
 
 /*
@@ -575,7 +576,7 @@ static void solve_query(
 void orc_narrow_phase(
     const orc_query* queries, int64_t n, int is_vf, double ms, int max_iter,
     double tol, int allow_zero_toi, int cap_mode, double* toi, double* toi_per_query,
-    orc_np_stats* stats)
+    orc_np_stats* stats, int64_t* checks_per_query)
 {
     orc_np_stats total = { 0, 0, 0 };
     if (toi_per_query) {
@@ -587,10 +588,12 @@ void orc_narrow_phase(
 #pragma omp for schedule(dynamic, 256)
             for (int64_t i = 0; i < n; i++) {
                 double tq = INFINITY;
-                solve_query(
+                const int64_t nc = solve_query(
                     &queries[i], is_vf, ms, max_iter, tol, allow_zero_toi, cap_mode,
                     &tq, &lg, &st);
                 toi_per_query[i] = tq;
+                if (checks_per_query)
+                    checks_per_query[i] = nc;
             }
 #pragma omp critical
             {
@@ -609,9 +612,11 @@ void orc_narrow_phase(
         double g = *toi;
         for (int64_t i = 0; i < n && g > 0; i++) { /* narrow_phase.cu:136 */
             double dummy = g;
-            solve_query(
+            const int64_t nc = solve_query(
                 &queries[i], is_vf, ms, max_iter, tol, allow_zero_toi, cap_mode, &g,
                 &dummy, &total);
+            if (checks_per_query)
+                checks_per_query[i] = nc;
         }
         *toi = g;
     }

@@ -143,17 +143,27 @@ def narrow_phase(queries, is_vf: bool, ms: float = 0.0, max_iter: int = -1, tol:
                  allow_zero_toi: bool = True, toi: float = 1.0, per_query: bool = True,
                  cap_mode: int = 1):
     """Tight-Inclusion over (n, 24) query arrays.  Returns (toi, toi_per_query | None,
-    stats dict)."""
+    stats dict); stats["checks"] holds the per-query box counts."""
     q = np.ascontiguousarray(queries, dtype=np.float64).reshape(-1, 24)
     t = C.c_double(toi)
     tpq = np.empty(len(q), np.float64) if per_query else None
     st = NpStats()
+    checks = np.zeros(len(q), np.int64)
     lib().orc_narrow_phase(
         _p(q), C.c_int64(len(q)), C.c_int(int(is_vf)), C.c_double(ms), C.c_int(max_iter),
         C.c_double(tol), C.c_int(int(allow_zero_toi)), C.c_int(cap_mode), C.byref(t),
-        _p(tpq) if per_query else None, C.byref(st))
+        _p(tpq) if per_query else None, C.byref(st), _p(checks))
     return t.value, tpq, {"box_checks": st.box_checks, "max_stack": st.max_stack,
-                          "capped_queries": st.capped_queries}
+                          "capped_queries": st.capped_queries, "checks": checks}
+
+
+def tractable(queries, is_vf: bool, ms: float, tol: float, allow_zero_toi: bool = True,
+              limit: int = 20000) -> np.ndarray:
+    """Mask of the queries the solver finishes within `limit` box checks.  Grazing
+    queries with ms > 0 can need >1e8 boxes (for the reference as well); uncapped parity
+    runs use this mask, capped runs use everything."""
+    _, _, st = narrow_phase(queries, is_vf, ms, limit, tol, allow_zero_toi, cap_mode=1)
+    return st["checks"] <= limit
 
 
 def ccd(scene, ms: float = 0.0, max_iter: int = -1, tol: float = 1e-6,
@@ -226,11 +236,18 @@ def ref_cuda(per_query: bool = False):
     path = os.path.join(REF_DIR, "libref_sccd_cuda_pq.so" if per_query else "libref_sccd_cuda.so")
     if not os.path.exists(path):
         return None
-    L = C.CDLL(path)
+    if path in _ref_cuda_libs:
+        return _ref_cuda_libs[path]
+    # RTLD_DEEPBIND: each variant binds its own copies of the inline spdlog / thrust symbols
+    L = C.CDLL(path, mode=os.RTLD_NOW | os.RTLD_LOCAL | os.RTLD_DEEPBIND)
     L.ref_cuda_ccd.restype = C.c_double
     L.ref_cuda_ipc_ccd_strategy.restype = C.c_double
     L.ref_cuda_quiet()
+    _ref_cuda_libs[path] = L
     return L
+
+
+_ref_cuda_libs = {}
 
 
 def ref_cuda_ccd(scene, ms=0.0, max_iter=-1, tol=1e-6, allow_zero_toi=True, per_query=False,

@@ -39,6 +39,9 @@ class Stats(C.Structure):
         ("n_donated", C.c_int64 * 2), ("n_capped", C.c_int64 * 2), ("n_launches", C.c_int64),
         ("queue_overflow", C.c_int64), ("ms_build", C.c_float), ("ms_sort", C.c_float),
         ("ms_sweep", C.c_float * 2), ("ms_narrow", C.c_float * 2), ("ms_total", C.c_float),
+        ("ms_k_sweep_count", C.c_float * 2), ("ms_k_sweep_fill", C.c_float * 2),
+        ("ms_k_narrow", C.c_float * 2), ("ms_k_boxes", C.c_float), ("ms_k_gather", C.c_float),
+        ("pad_", C.c_float),
     ]
 
     def as_dict(self):
@@ -217,13 +220,16 @@ class Context:
             C.c_int(int(allow_zero_toi)), C.byref(t)))
         return t.value
 
-    def ccd_host(self, V0, V1, E, F, ms=0.0, max_iter=-1, tol=1e-6, allow_zero_toi=True) -> float:
+    def ccd_host(self, V0, V1, E, F, ms=0.0, max_iter=-1, tol=1e-6, allow_zero_toi=True,
+                 sizes=None) -> float:
+        """ccd() with HOST buffers (numpy arrays, or raw host pointers + sizes=(nV,nE,nF))."""
+        nV, nE, nF = sizes if sizes is not None else (V0.shape[0], E.shape[0], F.shape[0])
         t = C.c_double(1.0)
         self._chk(self.L.sccd_ccd_host(
-            self._h, _ptr(V0), _ptr(V1), C.c_int64(V0.shape[0]), _ptr(E), C.c_int64(E.shape[0]),
-            _ptr(F), C.c_int64(F.shape[0]), C.c_double(ms), C.c_int(max_iter), C.c_double(tol),
+            self._h, _ptr(V0), _ptr(V1), C.c_int64(nV), _ptr(E), C.c_int64(nE),
+            _ptr(F), C.c_int64(nF), C.c_double(ms), C.c_int(max_iter), C.c_double(tol),
             C.c_int(int(allow_zero_toi)), C.byref(t)))
-        self.nV, self.nE, self.nF = V0.shape[0], E.shape[0], F.shape[0]
+        self.nV, self.nE, self.nF = nV, nE, nF
         return t.value
 
     def ccd_collisions(self, ms=0.0, max_iter=-1, tol=1e-6, allow_zero_toi=True):

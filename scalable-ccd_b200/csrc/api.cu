@@ -93,7 +93,15 @@ struct sccd_ctx {
 
     sccd_stats stats {};
     LaunchCounter lc;
-    cudaEvent_t ev[16] {};
+    cudaEvent_t ev[20] {};
+    bool gather_timed = false;
+    // pooled event pairs timing single kernels; resolved into stats at the end of a call
+    struct KTimer {
+        cudaEvent_t a = nullptr, b = nullptr;
+        float* dst = nullptr;
+    };
+    std::vector<KTimer> ktimers;
+    size_t kt_used = 0;
 
     ~sccd_ctx()
     {
@@ -104,13 +112,17 @@ struct sccd_ctx {
         for (auto& e : ev)
             if (e)
                 cudaEventDestroy(e);
+        for (auto& k : ktimers) {
+            cudaEventDestroy(k.a);
+            cudaEventDestroy(k.b);
+        }
     }
 };
 
 namespace {
 
 enum { EV_T0, EV_BUILD, EV_SORT, EV_SW0A, EV_SW0B, EV_NP0A, EV_NP0B, EV_SW1A, EV_SW1B,
-       EV_NP1A, EV_NP1B, EV_T1, EV_TMPA, EV_TMPB };
+       EV_NP1A, EV_NP1B, EV_T1, EV_TMPA, EV_TMPB, EV_GA0, EV_GB0, EV_GA1, EV_GB1, EV_COUNT };
 
 void use_device(sccd_ctx* c) { SCCD_CUDA(cudaSetDevice(c->device)); }
 
@@ -149,6 +161,34 @@ float elapsed(sccd_ctx* c, int a, int b)
         return 0.f;
     }
     return ms;
+}
+
+size_t kt_begin(sccd_ctx* c, float* dst)
+{
+    if (c->kt_used == c->ktimers.size()) {
+        sccd_ctx::KTimer k;
+        SCCD_CUDA(cudaEventCreate(&k.a));
+        SCCD_CUDA(cudaEventCreate(&k.b));
+        c->ktimers.push_back(k);
+    }
+    sccd_ctx::KTimer& k = c->ktimers[c->kt_used];
+    k.dst = dst;
+    SCCD_CUDA(cudaEventRecord(k.a, c->stream));
+    return c->kt_used++;
+}
+void kt_end(sccd_ctx* c, size_t id) { SCCD_CUDA(cudaEventRecord(c->ktimers[id].b, c->stream)); }
+void kt_resolve(sccd_ctx* c)
+{
+    for (size_t i = 0; i < c->kt_used; i++) {
+        sccd_ctx::KTimer& k = c->ktimers[i];
+        float ms = 0.f;
+        if (cudaEventSynchronize(k.b) == cudaSuccess
+            && cudaEventElapsedTime(&ms, k.a, k.b) == cudaSuccess)
+            *k.dst += ms;
+        else
+            (void)cudaGetLastError();
+    }
+    c->kt_used = 0;
 }
 
 size_t budget_bytes(sccd_ctx* c)
@@ -243,21 +283,24 @@ void build_boxes(sccd_ctx* c, double inflation_radius)
     const double radius_up = std::nextafter(inflation_radius, DBL_MAX);
     auto& LV = c->lists[0];
     auto& LE = c->lists[1];
+    const size_t kt_boxes = kt_begin(c, &c->stats.ms_k_boxes);
     launch_vertex_boxes(
         c->dV0, c->dV1, nV, radius_up, c->b_vtab.as<VertexRec>(), c->b_vbox.as<double>(),
         LV.unsorted, LV.keys.as<uint32_t>(), c->stream, c->lc);
     launch_element_boxes(
         c->b_vbox.as<double>(), c->dE, nE, c->dF, nF, nV, LE.unsorted, LE.keys.as<uint32_t>(),
         LV.unsorted, LV.keys.as<uint32_t>(), c->stream, c->lc);
+    kt_end(c, kt_boxes);
     record(c, EV_BUILD);
     launch_sort_and_gather(
         (int)nVF, LV.keys.as<uint32_t>(), LV.keys_tmp.as<uint32_t>(), LV.idx.as<uint32_t>(),
         LV.idx_out.as<uint32_t>(), c->b_sort_temp.ptr, c->b_sort_temp.cap, LV.unsorted,
-        LV.sorted, c->stream, c->lc);
+        LV.sorted, c->stream, c->lc, c->ev[EV_GA0], c->ev[EV_GB0]);
     launch_sort_and_gather(
         nE, LE.keys.as<uint32_t>(), LE.keys_tmp.as<uint32_t>(), LE.idx.as<uint32_t>(),
         LE.idx_out.as<uint32_t>(), c->b_sort_temp.ptr, c->b_sort_temp.cap, LE.unsorted,
-        LE.sorted, c->stream, c->lc);
+        LE.sorted, c->stream, c->lc, c->ev[EV_GA1], c->ev[EV_GB1]);
+    c->gather_timed = true;
     record(c, EV_SORT);
     c->have_boxes = true;
     c->bp_kind = -1;
@@ -323,8 +366,10 @@ void broad_phase_begin(sccd_ctx* c, int kind)
     SCCD_CUDA(cudaMemsetAsync(c->b_counts.as<uint32_t>() + m, 0, 4, c->stream));
     unsigned long long* d_cand = reinterpret_cast<unsigned long long*>(c->b_small.as<char>() + 128);
     SCCD_CUDA(cudaMemsetAsync(d_cand, 0, 8, c->stream));
+    const size_t kt = kt_begin(c, &c->stats.ms_k_sweep_count[kind]);
     launch_sweep_count(
         L, c->shard_lo, c->shard_hi, c->b_counts.as<uint32_t>(), d_cand, c->stream, c->lc);
+    kt_end(c, kt);
     launch_scan_u32_to_u64(
         c->b_counts.as<uint32_t>(), c->b_offsets.as<unsigned long long>(), m,
         c->b_scan_temp.ptr, c->b_scan_temp.cap, c->stream, c->lc);
@@ -384,9 +429,11 @@ void broad_phase_partial(sccd_ctx* c, const sccd_pair** d_pairs, int64_t* n_pair
     }
     if (n_chunk > 0) {
         c->b_pairs.reserve((size_t)n_chunk * sizeof(sccd_pair));
+        const size_t kt = kt_begin(c, &c->stats.ms_k_sweep_fill[kind]);
         launch_sweep_fill(
             L, c->shard_lo, c->bp_cursor, end, c->b_offsets.as<unsigned long long>(),
             c->b_pairs.as<sccd_pair>(), c->stream, c->lc);
+        kt_end(c, kt);
     }
     c->bp_cursor = end;
     c->bp_emitted += n_chunk;
@@ -449,9 +496,11 @@ void narrow_run(
         checks = (unsigned int*)c->b_checks_q.reserve((size_t)in.n * 4);
         SCCD_CUDA(cudaMemsetAsync(checks, 0, (size_t)in.n * 4, c->stream));
     }
+    const size_t kt = kt_begin(c, &c->stats.ms_k_narrow[kind]);
     launch_narrow_phase(
         kind == SCCD_VF, in, P, c->b_counters.as<NarrowCounters>(), c->b_queue.as<WorkItem>(),
         c->queue_items, d_toi_per_query, checks, c->num_sms, c->stream, c->lc);
+    kt_end(c, kt);
     SCCD_CUDA(cudaMemcpyAsync(
         c->h_counters, c->b_counters.ptr, sizeof(NarrowCounters), cudaMemcpyDeviceToHost,
         c->stream));
@@ -495,6 +544,12 @@ void reset_stats(sccd_ctx* c)
 void finish_stats(sccd_ctx* c, bool pipeline)
 {
     c->stats.n_launches = c->lc.n;
+    kt_resolve(c);
+    if (c->gather_timed) {
+        SCCD_CUDA(cudaEventSynchronize(c->ev[EV_GB1]));
+        c->stats.ms_k_gather = elapsed(c, EV_GA0, EV_GB0) + elapsed(c, EV_GA1, EV_GB1);
+        c->gather_timed = false;
+    }
     if (!pipeline)
         return;
     SCCD_CUDA(cudaEventSynchronize(c->ev[EV_T1]));
@@ -680,6 +735,7 @@ int sccd_build_boxes(sccd_ctx* ctx, double inflation_radius)
     return guarded(ctx, [&] {
         record(ctx, EV_T0);
         build_boxes(ctx, inflation_radius);
+        finish_stats(ctx, false);
         return SCCD_OK;
     });
 }
@@ -768,7 +824,7 @@ int sccd_broad_phase(sccd_ctx* ctx, int kind, sccd_pair* out, int64_t cap, int64
         }
         if (n_total)
             *n_total = total;
-        ctx->stats.n_launches = ctx->lc.n;
+        finish_stats(ctx, false);
         return SCCD_OK;
     });
 }
@@ -784,7 +840,7 @@ int sccd_narrow_phase(
         narrow_run(
             ctx, kind, mesh_input(ctx, d_pairs, n), ms, max_iter, tol, allow_zero_toi != 0,
             toi_inout, d_toi_per_query);
-        ctx->stats.n_launches = ctx->lc.n;
+        finish_stats(ctx, false);
         return SCCD_OK;
     });
 }
@@ -811,7 +867,7 @@ int sccd_narrow_phase_queries(
         record(ctx, EV_TMPB);
         SCCD_CUDA(cudaEventSynchronize(ctx->ev[EV_TMPB]));
         ctx->stats.ms_narrow[kind] = elapsed(ctx, EV_TMPA, EV_TMPB);
-        ctx->stats.n_launches = ctx->lc.n;
+        finish_stats(ctx, false);
         return SCCD_OK;
     });
 }

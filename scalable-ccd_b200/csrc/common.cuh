@@ -187,7 +187,7 @@ size_t sort_temp_bytes(int n);
 void launch_sort_and_gather(
     int n, uint32_t* keys_in, uint32_t* keys_tmp, uint32_t* idx_in, uint32_t* idx_out,
     void* temp, size_t temp_bytes, BoxArrays unsorted, SortedList out, cudaStream_t s,
-    LaunchCounter& lc);
+    LaunchCounter& lc, cudaEvent_t gather_begin = nullptr, cudaEvent_t gather_end = nullptr);
 
 // window[i] = number of candidates after owner i whose f32 xmin <= owner's f32 xmax
 void launch_sweep_windows(

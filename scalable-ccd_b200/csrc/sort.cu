@@ -66,10 +66,15 @@ size_t sort_temp_bytes(int n)
 void launch_sort_and_gather(
     int n, uint32_t* keys_in, uint32_t* keys_tmp, uint32_t* idx_in, uint32_t* idx_out,
     void* temp, size_t temp_bytes, BoxArrays unsorted, SortedList out, cudaStream_t s,
-    LaunchCounter& lc)
+    LaunchCounter& lc, cudaEvent_t gather_begin, cudaEvent_t gather_end)
 {
-    if (n <= 0)
+    if (n <= 0) {
+        if (gather_begin)
+            SCCD_CUDA(cudaEventRecord(gather_begin, s));
+        if (gather_end)
+            SCCD_CUDA(cudaEventRecord(gather_end, s));
         return;
+    }
     const int grid = (n + kThreads - 1) / kThreads;
     iota_kernel<<<grid, kThreads, 0, s>>>(idx_in, n);
     SCCD_CUDA(cudaGetLastError());
@@ -78,10 +83,14 @@ void launch_sort_and_gather(
         temp, temp_bytes, (const uint32_t*)keys_in, keys_tmp, (const uint32_t*)idx_in,
         idx_out, n, 0, 32, s));
     lc.n += 6; // histogram + exclusive sum + 4 onesweep passes (CUB's sm_100 policy)
+    if (gather_begin)
+        SCCD_CUDA(cudaEventRecord(gather_begin, s));
     gather_sorted_kernel<<<grid, kThreads, 0, s>>>(
         n, keys_tmp, idx_out, unsorted, out.box, out.pf);
     SCCD_CUDA(cudaGetLastError());
     lc.n++;
+    if (gather_end)
+        SCCD_CUDA(cudaEventRecord(gather_end, s));
 }
 
 size_t scan_temp_bytes(int n)

@@ -210,20 +210,27 @@ def scene_c4(seed: int = 3, n_inst: int = 83_000):
     return blob_pile(n_inst, seed, slab=True)
 
 
-def queries_c5(n: int, seed: int = 4):
+def queries_c5(n: int, seed: int = 4, parallel: bool = True):
     """Config 5: adversarial narrow-phase queries given directly as vertex arrays.
 
     Returns (ee, vf): float64 arrays of shape (n, 24) laid out like the first 192
     bytes of the reference's CCDData (cuda/narrow_phase/ccd_data.cuh:8-18):
     v0s v1s v2s v3s v0e v1e v2e v3e.  EE: parallel / near-parallel edges sliding past
     each other at offsets 10^U(-12,-6); VF: vertex trajectories grazing the face
-    plane / face edges within 10^U(-12,-6)."""
+    plane / face edges within 10^U(-12,-6).
+
+    parallel=False keeps the edges skew (tilt 10^U(-3,-1)): with a minimum separation
+    ms > 0, exactly parallel overlapping edges have a whole contact LINE that the solver
+    must resolve at tolerance (>1e8 boxes per query, for the reference as well), which is
+    only usable together with max_iter."""
     rng = np.random.default_rng(seed)
     off = 10.0 ** rng.uniform(-12, -6, n)
     sign = rng.choice([-1.0, 1.0], n)
     # ---- edge-edge: edge A along x at height +-off above edge B (near parallel)
     ee = np.zeros((n, 8, 3))
     tilt = 10.0 ** rng.uniform(-10, -3, n) * rng.choice([0.0, 1.0], n)
+    if not parallel:
+        tilt = 10.0 ** rng.uniform(-3, -1, n)
     shift = rng.uniform(-0.3, 0.3, (n, 3))
     a0 = np.stack([-0.5 + 0 * off, 0 * off, off * sign], 1)
     a1 = np.stack([0.5 + 0 * off, tilt, off * sign], 1)

@@ -104,6 +104,10 @@ def make_cuda(out):
     arrays = {}
     for cname, ms, mi, tol, az in NARROW_CASES:
         for kind, q in (("vf", vf_q), ("ee", ee_q)):
+            # uncapped runs only on queries the solver finishes (see orc.tractable)
+            mask = orc.tractable(q, kind == "vf", ms, tol, az)
+            arrays[f"{cname}_{kind}_idx"] = np.flatnonzero(mask).astype(np.int32)
+            q = q[mask]
             r = orc.ref_cuda_narrow_queries(q, kind == "vf", ms, mi, tol, az, 1.0, True)
             g = orc.ref_cuda_narrow_queries(q, kind == "vf", ms, mi, tol, az, 1.0, False)
             arrays[f"{cname}_{kind}_tpq"] = r["toi_per_query"]

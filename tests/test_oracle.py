@@ -168,7 +168,9 @@ def test_golden_reference_cuda_narrow(orc, sccd):
              "ms": (1e-8, -1, 1e-6, True), "nozero": (0.0, -1, 1e-6, False)}
     for cname, (ms, mi, tol, az) in cases.items():
         for kind, q in (("vf", vf), ("ee", ee)):
-            toi, tpq, _ = orc.narrow_phase(q, kind == "vf", ms, mi, tol, az)
+            idx = z[f"{cname}_{kind}_idx"]
+            assert np.array_equal(idx, np.flatnonzero(orc.tractable(q, kind == "vf", ms, tol, az)))
+            toi, tpq, _ = orc.narrow_phase(q[idx], kind == "vf", ms, mi, tol, az)
             ref = z[f"{cname}_{kind}_tpq"]
             assert np.array_equal(tpq < 1, ref < 1), (cname, kind)        # hit/miss
             assert np.array_equal(tpq, ref), (cname, kind)                 # bit-exact toi
