@@ -292,7 +292,7 @@ def ref_cuda_broad_phase(scene, r=0.0, want_pairs=True):
 
 
 def ref_cuda_narrow_queries(queries, is_vf, ms=0.0, max_iter=-1, tol=1e-6, allow_zero_toi=True,
-                            toi=1.0, per_query=True):
+                            toi=1.0, per_query=True, min_queue_units=1 << 26):
     L = ref_cuda(per_query)
     q = np.ascontiguousarray(queries, dtype=np.float64).reshape(-1, 24)
     t = C.c_double(toi)
@@ -301,5 +301,5 @@ def ref_cuda_narrow_queries(queries, is_vf, ms=0.0, max_iter=-1, tol=1e-6, allow
     reruns = L.ref_cuda_narrow_queries(
         _p(q), C.c_int64(len(q)), C.c_int(int(is_vf)), C.c_double(ms), C.c_int(max_iter),
         C.c_double(tol), C.c_int(int(allow_zero_toi)), C.byref(t),
-        _p(tpq) if per_query else None, C.byref(ms_el))
+        _p(tpq) if per_query else None, C.byref(ms_el), C.c_int64(min_queue_units))
     return {"toi": t.value, "toi_per_query": tpq, "ms": ms_el.value, "reruns": reruns}

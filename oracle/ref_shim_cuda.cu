@@ -163,7 +163,7 @@ void ref_cuda_broad_phase(
 int ref_cuda_narrow_queries(
     const double* queries, int64_t n, int is_vf, double ms, int max_iter,
     double tol, int allow_zero_toi, double* toi_inout, double* toi_per_query,
-    double* elapsed_ms)
+    double* elapsed_ms, int64_t min_queue_units)
 {
     thrust::host_vector<CCDData> h(n);
     for (int64_t i = 0; i < n; i++) {
@@ -201,6 +201,14 @@ int ref_cuda_narrow_queries(
             mh->handleNarrowPhase(nq);
         else
             mh->handleOverflow(nq);
+        // The reference sizes its ring queue at 2x the query count
+        // (memory_handler.cpp:116) and its full-check is not atomic with the push
+        // (ccd_buffer.cuh:25-34): when almost every query is deep, as in these
+        // adversarial sets, whole BFS levels wrap over unprocessed entries WITHOUT raising
+        // the overflow flag and hits are silently lost.  Give it the queue a realistic
+        // (mostly shallow) batch would have had.
+        if ((int64_t)mh->MAX_UNIT_SIZE < min_queue_units)
+            mh->MAX_UNIT_SIZE = (size_t)min_queue_units;
         d_data = h;
         if (is_vf)
             overflowed = ccd<true>(

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -479,6 +480,10 @@ void narrow_run(
     P.max_iter = max_iter;
     P.allow_zero_toi = allow_zero_toi ? 1 : 0;
     P.use_ms = ms > 0 ? 1 : 0;
+    {
+        const char* f = getenv("SCCD_NP_FLAGS");
+        P.flags = f ? atoi(f) : 0;
+    }
 
     NarrowCounters init {};
     init.next_query = 0;

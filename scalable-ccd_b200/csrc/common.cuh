@@ -143,6 +143,7 @@ struct NarrowParams {
     int max_iter;   // < 0: unlimited
     int allow_zero_toi;
     int use_ms;     // ms > 0 (selects the error filter, root_finder.cu:95-122)
+    int flags;      // debug knobs (SCCD_NP_FLAGS env): 1 = never donate
 };
 
 // Bounded global work queue of sub-boxes handed between lanes (56-byte payload, the size
@@ -156,17 +157,20 @@ struct __align__(16) WorkItem {
 };
 static_assert(sizeof(WorkItem) == 64, "WorkItem");
 
-struct NarrowCounters {
-    unsigned long long next_query;  // next unclaimed query index
-    unsigned long long q_tail;      // tickets reserved by producers
-    unsigned long long q_head;      // tickets reserved by consumers
-    long long outstanding;          // sub-trees alive (claimed or queued)
-    int hungry;                     // lanes with nothing to do
-    int overflow;                   // a donation was refused because the queue was full
+// Every hot word sits in its own 128-byte line: idle warps poll q_tail / q_head /
+// outstanding while busy lanes read toi / hungry, and sharing a line made every busy-lane
+// read queue behind thousands of polls.
+struct alignas(128) NarrowCounters {
+    alignas(128) unsigned long long next_query; // next unclaimed query index
+    alignas(128) unsigned long long q_tail;     // tickets reserved by producers
+    alignas(128) unsigned long long q_head;     // tickets reserved by consumers
+    alignas(128) long long outstanding;         // sub-trees alive (claimed or queued)
+    alignas(128) int hungry;                    // lanes with nothing to do
+    alignas(128) double toi;                    // shared earliest toi
+    alignas(128) int overflow;                  // a donation was refused (queue full)
     unsigned long long box_checks;
     unsigned long long donated;
     unsigned long long capped;
-    double toi;                     // shared earliest toi
 };
 
 // ---- kernel launchers (defined in the .cu files) -----------------------------------

@@ -225,9 +225,13 @@ def test_pipeline_matches_reference_cuda_golden(ctx, scene_small, scene_c1):
 
 
 def test_ipc_ccd_strategy(ctx, orc, scene_small):
-    """ipc_ccd_strategy.cu:54-92 composed from oracle pieces."""
+    """ipc_ccd_strategy.cu:54-92 composed from oracle pieces.  With an iteration cap the
+    result must be conservative w.r.t. the uncapped composition; the reference-CUDA value
+    for the same call is frozen in tests/golden/ref_cuda_meta.json."""
     s = scene_small
     ctx.upload_mesh(s["V0"], s["V1"], s["E"], s["F"])
+    meta_path = os.path.join(GOLD, "ref_cuda_meta.json")
+    gold = json.load(open(meta_path))["ipc_small"] if os.path.exists(meta_path) else None
     for md, mi in ((0.0, -1), (1e-4, 200)):
         vb, eb, fb = orc.build_boxes(s, md)
         vf = orc.canonical(orc.sort_and_sweep_two_lists(vb, fb, 0)[0])
@@ -236,7 +240,7 @@ def test_ipc_ccd_strategy(ctx, orc, scene_small):
         for pairs, is_vf in ((vf, True), (ee, False)):
             q = orc.gather_queries(s, pairs, is_vf)
             before = toi
-            toi, _, _ = orc.narrow_phase(q, is_vf, md, mi, 1e-6, True, toi, per_query=False)
+            toi, _, _ = orc.narrow_phase(q, is_vf, md, -1, 1e-6, True, toi, per_query=False)
             if toi < 1e-6:
                 toi, _, _ = orc.narrow_phase(q, is_vf, 0.0, -1, 1e-6, False, before,
                                              per_query=False)
@@ -244,8 +248,12 @@ def test_ipc_ccd_strategy(ctx, orc, scene_small):
         got = ctx.ipc_ccd_strategy(md, mi, 1e-6)
         if mi < 0:
             assert got == toi
+            if gold:
+                assert got == gold[f"md{md}_mi{mi}"]
         else:
-            assert got <= toi      # capped: conservative
+            assert got <= toi      # capped: never later than the exact answer
+            if gold:               # ... nor than the reference's (which drops boxes)
+                assert got <= gold[f"md{md}_mi{mi}"]
 
 
 def test_device_pointer_inputs(ctx, orc, scene_small, torch_cuda):
