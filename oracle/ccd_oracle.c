@@ -663,3 +663,122 @@ int orc_num_threads(void)
     return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------- */
+/* Level-synchronous BFS over ALL queries at once, exactly the traversal of the
+ * reference's host loop (root_finder.cu:431-447: one ccd_kernel launch per level over
+ * the ring buffer).  Same accepted minimum as the DFS above; what differs is the WORK:
+ * BFS cannot prune by toi until some box reaches an accepting depth, so whole fronts are
+ * expanded.  Used to size the reference's queue when freezing goldens and to report the
+ * reference's box-check count next to ours.  Returns the number of levels; *max_level
+ * receives the widest level (= ring-buffer entries the reference needs). */
+typedef struct {
+    orc_box box;
+    int32_t query;
+} orc_bfs_item;
+
+int64_t orc_narrow_phase_bfs(
+    const orc_query* queries, int64_t n, int is_vf, double ms, double tol,
+    int allow_zero_toi, double* toi_per_query, int64_t* total_checks, int64_t* max_level,
+    int64_t cap_items)
+{
+    orc_bounds* bd = (orc_bounds*)malloc(sizeof(orc_bounds) * (size_t)(n > 0 ? n : 1));
+    for (int64_t i = 0; i < n; i++) {
+        orc_compute_bounds(&queries[i], is_vf, tol, ms > 0, &bd[i]);
+        toi_per_query[i] = INFINITY;
+    }
+    int64_t cap = n > 1024 ? 2 * n : 2048, cur_n = n, levels = 0;
+    orc_bfs_item* cur = (orc_bfs_item*)malloc(sizeof(orc_bfs_item) * (size_t)cap);
+    orc_bfs_item* nxt = (orc_bfs_item*)malloc(sizeof(orc_bfs_item) * (size_t)cap);
+    int64_t nxt_cap = cap;
+    for (int64_t i = 0; i < n; i++) {
+        for (int k = 0; k < 3; k++) {
+            cur[i].box.lo[k] = 0.0;
+            cur[i].box.hi[k] = 1.0;
+        }
+        cur[i].query = (int32_t)i;
+    }
+    const double one_plus = 1 / (1 - DBL_EPSILON);
+    *total_checks = 0;
+    *max_level = n;
+    while (cur_n > 0) {
+        levels++;
+        int64_t nn = 0;
+        for (int64_t b = 0; b < cur_n; b++) {
+            const orc_box box = cur[b].box;
+            const int32_t q = cur[b].query;
+            const double min_t = box.lo[0];
+            if (min_t >= toi_per_query[q])
+                continue;
+            (*total_checks)++;
+            double true_tol;
+            int box_in;
+            if (!origin_in_inclusion(&queries[q], &bd[q], is_vf, ms, &box, &true_tol, &box_in))
+                continue;
+            const double w[3] = { box.hi[0] - box.lo[0], box.hi[1] - box.lo[1],
+                                  box.hi[2] - box.lo[2] };
+            int accept = 0;
+            if (w[0] <= bd[q].tol[0] && w[1] <= bd[q].tol[1] && w[2] <= bd[q].tol[2])
+                accept = 1;
+            else if (box_in && (allow_zero_toi || min_t > 0))
+                accept = 1;
+            else if (true_tol <= tol && (allow_zero_toi || min_t > 0))
+                accept = 1;
+            if (!accept) {
+                const int split = split_dimension(&bd[q], w);
+                const double mid = (box.lo[split] + box.hi[split]) / 2;
+                if (box.lo[split] >= mid || mid >= box.hi[split]) {
+                    accept = 1;
+                } else {
+                    if (nn + 2 > nxt_cap) {
+                        nxt_cap *= 2;
+                        if (cap_items > 0 && nxt_cap > 4 * cap_items) {
+                            free(bd);
+                            free(cur);
+                            free(nxt);
+                            *max_level = nxt_cap;
+                            return -1; /* gave up: the front exceeds the caller's bound */
+                        }
+                        nxt = (orc_bfs_item*)realloc(nxt, sizeof(orc_bfs_item) * (size_t)nxt_cap);
+                    }
+                    nxt[nn].box = box;
+                    nxt[nn].box.hi[split] = mid;
+                    nxt[nn].query = q;
+                    nn++;
+                    int push_second;
+                    if (split == 0)
+                        push_second = mid <= toi_per_query[q];
+                    else if (is_vf)
+                        push_second = (mid + box.lo[split == 1 ? 2 : 1]) <= one_plus;
+                    else
+                        push_second = 1;
+                    if (push_second) {
+                        nxt[nn].box = box;
+                        nxt[nn].box.lo[split] = mid;
+                        nxt[nn].query = q;
+                        nn++;
+                    }
+                }
+            }
+            if (accept && min_t < toi_per_query[q])
+                toi_per_query[q] = min_t;
+        }
+        if (nn > *max_level)
+            *max_level = nn;
+        if (cap < nxt_cap) {
+            cap = nxt_cap;
+            cur = (orc_bfs_item*)realloc(cur, sizeof(orc_bfs_item) * (size_t)cap);
+        }
+        orc_bfs_item* t = cur;
+        cur = nxt;
+        nxt = t;
+        const int64_t tc = cap;
+        cap = nxt_cap;
+        nxt_cap = tc;
+        cur_n = nn;
+    }
+    free(bd);
+    free(cur);
+    free(nxt);
+    return levels;
+}

@@ -166,6 +166,37 @@ def tractable(queries, is_vf: bool, ms: float, tol: float, allow_zero_toi: bool 
     return st["checks"] <= limit
 
 
+def narrow_phase_bfs(queries, is_vf: bool, ms: float = 0.0, tol: float = 1e-6,
+                     allow_zero_toi: bool = True, cap_items: int = 0):
+    """The reference's level-synchronous traversal (root_finder.cu:431-447).  Returns
+    (toi_per_query, levels, total_checks, widest_level); levels == -1 if the front outgrew
+    4 * cap_items and the run was abandoned."""
+    q = np.ascontiguousarray(queries, dtype=np.float64).reshape(-1, 24)
+    L = lib()
+    L.orc_narrow_phase_bfs.restype = C.c_int64
+    tpq = np.empty(len(q), np.float64)
+    tc, ml = C.c_int64(0), C.c_int64(0)
+    lv = L.orc_narrow_phase_bfs(
+        _p(q), C.c_int64(len(q)), C.c_int(int(is_vf)), C.c_double(ms), C.c_double(tol),
+        C.c_int(int(allow_zero_toi)), _p(tpq), C.byref(tc), C.byref(ml), C.c_int64(cap_items))
+    return tpq, lv, tc.value, ml.value
+
+
+def tractable_bfs(queries, is_vf: bool, ms: float, tol: float, allow_zero_toi: bool = True,
+                  front_limit: int = 4096) -> np.ndarray:
+    """Mask of the queries whose BREADTH-first front stays below front_limit entries.  The
+    reference's ring queue silently wraps over unprocessed boxes when a front outgrows it
+    (the full-check is not atomic with the push, ccd_buffer.cuh:25-34), so goldens frozen
+    from it are only meaningful on such queries."""
+    q = np.ascontiguousarray(queries, dtype=np.float64).reshape(-1, 24)
+    mask = np.zeros(len(q), bool)
+    for i in range(len(q)):
+        _, lv, _, ml = narrow_phase_bfs(q[i:i + 1], is_vf, ms, tol, allow_zero_toi,
+                                        cap_items=front_limit)
+        mask[i] = lv > 0 and ml <= front_limit
+    return mask
+
+
 def ccd(scene, ms: float = 0.0, max_iter: int = -1, tol: float = 1e-6,
         allow_zero_toi: bool = True, per_query: bool = True):
     """Whole pipeline on the CPU, as cuda/ccd.cu:80-146 composes it."""

@@ -106,6 +106,9 @@ def make_cuda(out):
         for kind, q in (("vf", vf_q), ("ee", ee_q)):
             # uncapped runs only on queries the solver finishes (see orc.tractable)
             mask = orc.tractable(q, kind == "vf", ms, tol, az)
+            # ... and whose breadth-first front fits the reference's ring queue (it wraps
+            # silently otherwise and loses hits, see orc.tractable_bfs)
+            mask &= orc.tractable_bfs(q, kind == "vf", ms, tol, az)
             arrays[f"{cname}_{kind}_idx"] = np.flatnonzero(mask).astype(np.int32)
             q = q[mask]
             r = orc.ref_cuda_narrow_queries(q, kind == "vf", ms, mi, tol, az, 1.0, True)
