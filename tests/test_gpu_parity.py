@@ -209,7 +209,9 @@ def test_pipeline_with_min_distance_and_chunks(ctx, orc, scene_small):
 
 
 def test_pipeline_matches_reference_cuda_golden(ctx, scene_small, scene_c1):
-    for name, s in (("small", scene_small), ("c1", scene_c1)):
+    # (the 31x31 scene is not frozen: the reference's ring queue wraps on it, see
+    # tests/golden/make_golden.py)
+    for name, s in (("c1", scene_c1),):
         path = os.path.join(GOLD, f"ccd_{name}_ref_cuda.npz")
         if not os.path.exists(path):
             pytest.skip("golden not generated yet")
@@ -231,7 +233,7 @@ def test_ipc_ccd_strategy(ctx, orc, scene_small):
     s = scene_small
     ctx.upload_mesh(s["V0"], s["V1"], s["E"], s["F"])
     meta_path = os.path.join(GOLD, "ref_cuda_meta.json")
-    gold = json.load(open(meta_path))["ipc_small"] if os.path.exists(meta_path) else None
+    gold = None   # reference values are frozen for config 1 only (see below)
     for md, mi in ((0.0, -1), (1e-4, 200)):
         vb, eb, fb = orc.build_boxes(s, md)
         vf = orc.canonical(orc.sort_and_sweep_two_lists(vb, fb, 0)[0])
@@ -254,6 +256,18 @@ def test_ipc_ccd_strategy(ctx, orc, scene_small):
             assert got <= toi      # capped: never later than the exact answer
             if gold:               # ... nor than the reference's (which drops boxes)
                 assert got <= gold[f"md{md}_mi{mi}"]
+
+
+def test_ipc_ccd_strategy_matches_reference_cuda_golden(ctx, scene_c1):
+    meta_path = os.path.join(GOLD, "ref_cuda_meta.json")
+    if not os.path.exists(meta_path):
+        pytest.skip("golden not generated yet")
+    gold = json.load(open(meta_path))["ipc_c1"]
+    s = scene_c1
+    ctx.upload_mesh(s["V0"], s["V1"], s["E"], s["F"])
+    assert ctx.ipc_ccd_strategy(0.0, -1, 1e-6) == gold["md0.0_mi-1"]
+    # capped: the reference drops boxes (later or equal), we accept them (earlier or equal)
+    assert ctx.ipc_ccd_strategy(1e-4, 200, 1e-6) <= gold["md0.0001_mi200"]
 
 
 def test_device_pointer_inputs(ctx, orc, scene_small, torch_cuda):

@@ -179,8 +179,9 @@ def test_golden_reference_cuda_narrow(orc, sccd):
             assert toi == float(z[f"{cname}_{kind}_toi"])
 
 
-def test_golden_reference_cuda_ccd(orc, scene_small):
-    path = os.path.join(GOLD, "ccd_small_ref_cuda.npz")
+def test_golden_reference_cuda_ccd(orc, scene_c1):
+    scene_small = scene_c1   # the smallest scene whose BFS front fits the reference's queue
+    path = os.path.join(GOLD, "ccd_c1_ref_cuda.npz")
     if not os.path.exists(path):
         pytest.skip("golden not generated yet (tests/golden/make_golden.py cuda)")
     z = np.load(path)
