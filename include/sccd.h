@@ -133,6 +133,20 @@ int sccd_build_boxes(sccd_ctx* ctx, double inflation_radius);
  * which: 0 vertices, 1 edges, 2 faces.  out: host array of nV / nE / nF boxes. */
 int sccd_get_boxes(sccd_ctx* ctx, int which, sccd_aabb* out);
 
+/* DeviceAABBs(boxes) + BroadPhase::build(boxes) / build(boxesA, boxesB) for caller-made
+ * boxes (cuda/broad_phase/aabb.cu:75-111, broad_phase.cu:29-101; this is how
+ * tests/test_broad_phase.cu:88-104 drives the broad phase), and the box-list half of the
+ * CPU entry points sort_and_sweep(boxes, axis, overlaps) / sort_and_sweep(boxesA, boxesB,
+ * axis, overlaps) (broad_phase/sort_and_sweep.hpp:24-42).  Host arrays in the reference's
+ * AABB layout; b == NULL / nb == 0 selects the single-list form.  sort_axis (0, 1, 2) is the
+ * axis to sweep along -- the overlap set does not depend on it.  *next_axis (may be NULL)
+ * receives the axis sort_and_sweep would return: argmax of the variance of the box centres
+ * (sort_and_sweep.cpp:176-195).  The list is then swept with kind = SCCD_BOXES. */
+#define SCCD_BOXES 2
+int sccd_set_boxes(
+    sccd_ctx* ctx, const sccd_aabb* a, int64_t na, const sccd_aabb* b, int64_t nb,
+    int sort_axis, int* next_axis);
+
 /* ---- broad phase ---------------------------------------------------------------- */
 
 /* BroadPhase::build (cuda/broad_phase/broad_phase.cu:29-101) for kind = SCCD_VF

@@ -14,7 +14,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsccd_b200.so")
 
-VF, EE = 0, 1
+VF, EE, BOXES = 0, 1, 2
 OK, ERR_CUDA, ERR_ARG, ERR_STATE, ERR_MEMORY = 0, -1, -2, -3, -4
 
 AABB_DTYPE = np.dtype(
@@ -24,7 +24,8 @@ AABB_DTYPE = np.dtype(
 SYMBOLS = [
     "sccd_create", "sccd_destroy", "sccd_last_error", "sccd_set_memory_limit",
     "sccd_set_max_pairs_per_chunk", "sccd_set_queue_capacity", "sccd_set_shard",
-    "sccd_upload_mesh", "sccd_build_boxes", "sccd_get_boxes", "sccd_broad_phase_begin",
+    "sccd_upload_mesh", "sccd_build_boxes", "sccd_get_boxes", "sccd_set_boxes",
+    "sccd_broad_phase_begin",
     "sccd_broad_phase_partial", "sccd_broad_phase_is_complete", "sccd_broad_phase",
     "sccd_narrow_phase", "sccd_narrow_phase_queries", "sccd_ccd", "sccd_ccd_collisions",
     "sccd_ccd_host", "sccd_ipc_ccd_strategy", "sccd_get_stats", "sccd_synchronize",
@@ -162,6 +163,22 @@ class Context:
             self._chk(self.L.sccd_get_boxes(self._h, C.c_int(which), _ptr(a)))
             out.append(a[:n])
         return tuple(out)
+
+    def set_boxes(self, a, b=None, sort_axis: int = 0) -> int:
+        """Caller-made boxes (AABB_DTYPE arrays): BroadPhase::build(boxes[, boxesB]) /
+        sort_and_sweep(boxes..., axis).  Sweep them with kind=BOXES.  Returns the next sort
+        axis the reference's sort_and_sweep would report."""
+        a = np.ascontiguousarray(a)
+        assert a.dtype == AABB_DTYPE
+        if b is not None:
+            b = np.ascontiguousarray(b)
+            assert b.dtype == AABB_DTYPE
+        nxt = C.c_int(0)
+        self._chk(self.L.sccd_set_boxes(
+            self._h, _ptr(a), C.c_int64(len(a)), _ptr(b), C.c_int64(len(b) if b is not None else 0),
+            C.c_int(sort_axis), C.byref(nxt)))
+        self._keep_boxes = (a, b)
+        return nxt.value
 
     # ---- broad phase
     def broad_phase(self, kind: int, want_pairs: bool = True):

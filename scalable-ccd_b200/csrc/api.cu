@@ -76,7 +76,8 @@ struct sccd_ctx {
         DevBuf pxmin, pxmax, pyz; // sorted f32 prefilter
         SortedList sorted;
         BoxArrays unsorted;
-    } lists[2];
+    } lists[3]; // [2] = caller-made boxes (sccd_set_boxes)
+    bool have_custom = false;
     DevBuf b_sort_temp;
 
     // broad-phase state
@@ -309,6 +310,77 @@ void build_boxes(sccd_ctx* c, double inflation_radius)
     c->stats.n_boxes[1] = nE;
 }
 
+// stats are kept per reference pass (VF, EE); caller-made box lists report in slot 0
+inline int stat_slot(int kind) { return kind == SCCD_EE ? 1 : 0; }
+
+// sccd_set_boxes: caller-made AABBs -> exact records + keys (host, O(n)) -> device sort.
+void set_boxes(
+    sccd_ctx* c, const sccd_aabb* a, int64_t na, const sccd_aabb* b, int64_t nb, int sort_axis,
+    int* next_axis)
+{
+    if (na < 0 || nb < 0 || (na && !a) || (nb && !b) || sort_axis < 0 || sort_axis > 2)
+        throw std::invalid_argument("set_boxes: bad argument");
+    const bool two = b != nullptr && nb > 0;
+    const int64_t n = na + (two ? nb : 0);
+    if (n >= (1ll << 27))
+        throw std::invalid_argument("set_boxes: more than 2^27 boxes in one list");
+    // the sweep always runs along the first coordinate of the record: rotate the axes
+    const int ax = sort_axis, ay = (sort_axis + 1) % 3, az = (sort_axis + 2) % 3;
+    std::vector<double2> hx((size_t)std::max<int64_t>(n, 1));
+    std::vector<double4> hyz(hx.size());
+    std::vector<int4> hid(hx.size());
+    std::vector<uint32_t> hkey(hx.size());
+    double s1[3] = { 0, 0, 0 }, s2[3] = { 0, 0, 0 };
+    // variance accumulation in the reference's order: the boxes as swept, i.e. sorted on
+    // min[axis] (sort_and_sweep.cpp:176-186); summation order only matters in the last ulp,
+    // so the argmax is taken over the same quantities computed in input order.
+    for (int64_t i = 0; i < n; i++) {
+        const sccd_aabb& bx = i < na ? a[i] : b[i - na];
+        hx[i] = make_double2(bx.min[ax], bx.max[ax]);
+        hyz[i] = make_double4(bx.min[ay], bx.min[az], bx.max[ay], bx.max[az]);
+        const int elem = (two && i < na) ? -bx.element_id - 1 : bx.element_id;
+        hid[i] = make_int4(bx.vertex_ids[0], bx.vertex_ids[1], bx.vertex_ids[2], elem);
+        // round toward -inf: nearest, then step down if it landed above
+        float f = (float)bx.min[ax];
+        if ((double)f > bx.min[ax])
+            f = std::nextafterf(f, -INFINITY);
+        hkey[i] = float_to_key(f);
+        for (int k = 0; k < 3; k++) {
+            const double ctr = (bx.min[k] + bx.max[k]) / 2;
+            s1[k] += ctr;
+            s2[k] += ctr * ctr;
+        }
+    }
+    if (next_axis) {
+        double var[3];
+        for (int k = 0; k < 3; k++)
+            var[k] = n > 0 ? s2[k] - s1[k] * s1[k] / (double)n : 0.0;
+        int best = 0;
+        if (var[1] > var[0])
+            best = 1;
+        if (var[2] > var[best])
+            best = 2;
+        *next_axis = best;
+    }
+    prepare_list(c, 2, (int)n, two);
+    auto& L = c->lists[2];
+    c->b_sort_temp.reserve(sort_temp_bytes((int)n));
+    if (n > 0) {
+        SCCD_CUDA(cudaMemcpyAsync(L.unsorted.x, hx.data(), sizeof(double2) * n, cudaMemcpyHostToDevice, c->stream));
+        SCCD_CUDA(cudaMemcpyAsync(L.unsorted.yz, hyz.data(), sizeof(double4) * n, cudaMemcpyHostToDevice, c->stream));
+        SCCD_CUDA(cudaMemcpyAsync(L.unsorted.id, hid.data(), sizeof(int4) * n, cudaMemcpyHostToDevice, c->stream));
+        SCCD_CUDA(cudaMemcpyAsync(L.keys.ptr, hkey.data(), 4 * n, cudaMemcpyHostToDevice, c->stream));
+    }
+    launch_sort_and_gather(
+        (int)n, L.keys.as<uint32_t>(), L.keys_tmp.as<uint32_t>(), L.idx.as<uint32_t>(),
+        L.idx_out.as<uint32_t>(), c->b_sort_temp.ptr, c->b_sort_temp.cap, L.unsorted, L.sorted,
+        c->stream, c->lc);
+    SCCD_CUDA(cudaStreamSynchronize(c->stream)); // host staging vectors go out of scope
+    c->have_custom = true;
+    c->bp_kind = -1;
+    c->stats.n_boxes[0] = n;
+}
+
 void small_scratch(sccd_ctx* c)
 {
     c->b_small.reserve(256);
@@ -320,18 +392,19 @@ void small_scratch(sccd_ctx* c)
 // the scan.  One host sync (the total).
 void broad_phase_begin(sccd_ctx* c, int kind)
 {
-    if (!c->have_boxes)
+    if (kind != SCCD_VF && kind != SCCD_EE && kind != SCCD_BOXES)
+        throw std::invalid_argument("broad_phase: kind must be SCCD_VF, SCCD_EE or SCCD_BOXES");
+    if (kind == SCCD_BOXES ? !c->have_custom : !c->have_boxes)
         throw std::logic_error("Must initialize build broad phase before detecting overlaps!");
-    if (kind != SCCD_VF && kind != SCCD_EE)
-        throw std::invalid_argument("broad_phase: kind must be SCCD_VF or SCCD_EE");
     const SortedList& L = c->lists[kind].sorted;
+    const int sk = stat_slot(kind);
     small_scratch(c);
     c->bp_kind = kind;
     c->shard_lo = 0;
     c->shard_hi = L.n;
-    c->stats.n_pairs[kind] = 0;
-    c->stats.n_candidates[kind] = 0;
-    record(c, kind == SCCD_VF ? EV_SW0A : EV_SW1A);
+    c->stats.n_pairs[sk] = 0;
+    c->stats.n_candidates[sk] = 0;
+    record(c, sk == 0 ? EV_SW0A : EV_SW1A);
     if (c->world > 1 && L.n > 0) {
         // balance owner slices by sweep-window length
         c->b_counts.reserve(((size_t)L.n + 1) * 4);
@@ -367,7 +440,7 @@ void broad_phase_begin(sccd_ctx* c, int kind)
     SCCD_CUDA(cudaMemsetAsync(c->b_counts.as<uint32_t>() + m, 0, 4, c->stream));
     unsigned long long* d_cand = reinterpret_cast<unsigned long long*>(c->b_small.as<char>() + 128);
     SCCD_CUDA(cudaMemsetAsync(d_cand, 0, 8, c->stream));
-    const size_t kt = kt_begin(c, &c->stats.ms_k_sweep_count[kind]);
+    const size_t kt = kt_begin(c, &c->stats.ms_k_sweep_count[sk]);
     launch_sweep_count(
         L, c->shard_lo, c->shard_hi, c->b_counts.as<uint32_t>(), d_cand, c->stream, c->lc);
     kt_end(c, kt);
@@ -380,7 +453,7 @@ void broad_phase_begin(sccd_ctx* c, int kind)
     SCCD_CUDA(cudaMemcpyAsync(&h[1], d_cand, 8, cudaMemcpyDeviceToHost, c->stream));
     SCCD_CUDA(cudaStreamSynchronize(c->stream));
     c->bp_total = h[0];
-    c->stats.n_candidates[kind] = (int64_t)h[1];
+    c->stats.n_candidates[sk] = (int64_t)h[1];
 }
 
 bool broad_phase_complete(sccd_ctx* c) { return c->bp_cursor >= c->shard_hi; }
@@ -395,6 +468,7 @@ void broad_phase_partial(sccd_ctx* c, const sccd_pair** d_pairs, int64_t* n_pair
     if (broad_phase_complete(c))
         return;
     const int kind = c->bp_kind;
+    const int sk = stat_slot(kind);
     const SortedList& L = c->lists[kind].sorted;
     const unsigned long long remaining = c->bp_total - c->bp_emitted;
     unsigned long long budget;
@@ -430,7 +504,7 @@ void broad_phase_partial(sccd_ctx* c, const sccd_pair** d_pairs, int64_t* n_pair
     }
     if (n_chunk > 0) {
         c->b_pairs.reserve((size_t)n_chunk * sizeof(sccd_pair));
-        const size_t kt = kt_begin(c, &c->stats.ms_k_sweep_fill[kind]);
+        const size_t kt = kt_begin(c, &c->stats.ms_k_sweep_fill[sk]);
         launch_sweep_fill(
             L, c->shard_lo, c->bp_cursor, end, c->b_offsets.as<unsigned long long>(),
             c->b_pairs.as<sccd_pair>(), c->stream, c->lc);
@@ -438,8 +512,8 @@ void broad_phase_partial(sccd_ctx* c, const sccd_pair** d_pairs, int64_t* n_pair
     }
     c->bp_cursor = end;
     c->bp_emitted += n_chunk;
-    c->stats.n_pairs[kind] += (int64_t)n_chunk;
-    record(c, kind == SCCD_VF ? EV_SW0B : EV_SW1B);
+    c->stats.n_pairs[sk] += (int64_t)n_chunk;
+    record(c, sk == 0 ? EV_SW0B : EV_SW1B);
     *d_pairs = c->b_pairs.as<sccd_pair>();
     *n_pairs = (int64_t)n_chunk;
 }
@@ -775,6 +849,16 @@ int sccd_get_boxes(sccd_ctx* ctx, int which, sccd_aabb* out)
             // vertices carry the flipped id on the device; the reference's host boxes do not
             out[i].element_id = which == 0 ? -id[i].w - 1 : id[i].w;
         }
+        return SCCD_OK;
+    });
+}
+
+int sccd_set_boxes(
+    sccd_ctx* ctx, const sccd_aabb* a, int64_t na, const sccd_aabb* b, int64_t nb,
+    int sort_axis, int* next_axis)
+{
+    return guarded(ctx, [&] {
+        set_boxes(ctx, a, na, b, nb, sort_axis, next_axis);
         return SCCD_OK;
     });
 }

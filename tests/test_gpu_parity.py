@@ -296,3 +296,25 @@ def test_sharded_broad_phase_is_a_partition(sccd, orc, scene_c1):
         cat = np.concatenate(parts[k])
         assert np.array_equal(cat, full[k])          # rank order == global deterministic order
         assert min(len(p) for p in parts[k]) > 0
+
+
+@pytest.mark.parametrize("axis", [0, 1, 2])
+def test_caller_made_boxes_any_axis(ctx, sccd, orc, scene_small, axis):
+    """BroadPhase::build(boxes[, boxesB]) / sort_and_sweep(boxes..., axis): the overlap set does
+    not depend on the sweep axis and the next-axis report matches the reference CPU path."""
+    vb, eb, fb = orc.build_boxes(scene_small, 1e-3)
+    B = sccd.capi.BOXES
+    nxt = ctx.set_boxes(eb, None, axis)
+    ee = ctx.broad_phase(B)
+    oee, oax = orc.sort_and_sweep(eb, axis)
+    assert nxt == oax and len(ee) == len(oee)
+    assert np.array_equal(orc.canonical(ee), orc.canonical(oee))
+    nxt = ctx.set_boxes(vb, fb, axis)
+    vf = ctx.broad_phase(B)
+    ovf, oax = orc.sort_and_sweep_two_lists(vb, fb, axis)
+    assert nxt == oax and len(vf) == len(ovf)
+    assert np.array_equal(orc.canonical(vf), orc.canonical(ovf))
+    if orc.ref_cpu() is not None and axis == 0:   # live unmodified reference, when it travels
+        ref = orc.ref_cpu_broad_phase(scene_small, r=1e-3, axis=axis)
+        assert np.array_equal(orc.canonical(vf), orc.canonical(ref["vf"]))
+        assert np.array_equal(orc.canonical(ee), orc.canonical(ref["ee"]))
