@@ -216,8 +216,8 @@ def main():
 
     stream = torch.cuda.current_stream().cuda_stream
     ctx = sccd.Context(local, stream)
-    ctx.set_shard(rank, world)
     ctx.upload_mesh(scene["V0"], scene["V1"], scene["E"], scene["F"])
+    sharded = sccd.multigpu.ShardedCCD(ctx) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     toi_t = torch.zeros(1, dtype=torch.float64, device="cuda")
 
@@ -227,24 +227,22 @@ def main():
         torch.cuda.synchronize()
 
     def step_resident():
-        toi = ctx.ccd(**PARAMS)
-        if world > 1:
-            toi_t.fill_(toi)
-            dist.all_reduce(toi_t, op=dist.ReduceOp.MIN)
-            toi = float(toi_t.item())
-        return toi
+        if world > 1:   # sharded sweep, pair rebalancing, NCCL min-TOI (multigpu.py)
+            ctx.reset_stats()
+            return sharded.ccd(**PARAMS)
+        return ctx.ccd(**PARAMS)
 
     # pinned host copies for the end-to-end arm
     pinned = {k: torch.from_numpy(np.ascontiguousarray(v.T)).pin_memory() for k, v in scene.items()}
 
     def step_e2e():
-        toi = ctx.ccd_host(pinned["V0"].data_ptr(), pinned["V1"].data_ptr(), pinned["E"].data_ptr(),
-                           pinned["F"].data_ptr(), sizes=(nV, nE, nF), **PARAMS)
         if world > 1:
-            toi_t.fill_(toi)
-            dist.all_reduce(toi_t, op=dist.ReduceOp.MIN)
-            toi = float(toi_t.item())
-        return toi
+            ctx.reset_stats()
+            ctx.upload_mesh(pinned["V0"].data_ptr(), pinned["V1"].data_ptr(), pinned["E"].data_ptr(),
+                            pinned["F"].data_ptr(), sizes=(nV, nE, nF), host=True)
+            return sharded.ccd(**PARAMS)
+        return ctx.ccd_host(pinned["V0"].data_ptr(), pinned["V1"].data_ptr(), pinned["E"].data_ptr(),
+                            pinned["F"].data_ptr(), sizes=(nV, nE, nF), **PARAMS)
 
     def timed(fn, steps, warmup, sampler=False):
         for _ in range(warmup):
@@ -345,7 +343,8 @@ def main():
                 "h2d_bytes_per_step": 2 * 24 * nV + 8 * nE + 12 * nF, "d2h_bytes_per_step": 8},
         "gpu_launches": int(avg("n_launches")) * args.steps,
         "roofline": roofline,
-        "toi": toi, "n_pairs": n_pairs, "n_prefilter_survivors": n_cand, "n_box_checks": n_checks,
+        "toi": toi, "n_pairs": n_pairs,
+        "pairs_per_rank": (sharded.last if sharded else None), "n_prefilter_survivors": n_cand, "n_box_checks": n_checks,
         "narrow_queries_per_s": (sum(n_pairs) / (narrow_ms * 1e-3)) if narrow_ms > 0 else None,
         "narrow_box_checks_per_s": (sum(n_checks) / (narrow_ms * 1e-3)) if narrow_ms > 0 else None,
         "narrow_fp64_instr_per_s": (fp64_instr / (narrow_ms * 1e-3)) if narrow_ms > 0 else None,

@@ -220,6 +220,9 @@ int sccd_ipc_ccd_strategy(
 
 /* ---- introspection -------------------------------------------------------------- */
 int sccd_get_stats(const sccd_ctx* ctx, sccd_stats* out);
+/* Pipeline calls (sccd_ccd*, sccd_ipc_ccd_strategy) start from zeroed stats by themselves;
+ * callers that compose the phase-level entry points reset them here. */
+int sccd_reset_stats(sccd_ctx* ctx);
 int sccd_synchronize(sccd_ctx* ctx);
 /* "major.minor.patch sm_100a" */
 const char* sccd_version(void);

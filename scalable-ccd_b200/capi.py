@@ -28,7 +28,8 @@ SYMBOLS = [
     "sccd_broad_phase_begin",
     "sccd_broad_phase_partial", "sccd_broad_phase_is_complete", "sccd_broad_phase",
     "sccd_narrow_phase", "sccd_narrow_phase_queries", "sccd_ccd", "sccd_ccd_collisions",
-    "sccd_ccd_host", "sccd_ipc_ccd_strategy", "sccd_get_stats", "sccd_synchronize",
+    "sccd_ccd_host", "sccd_ipc_ccd_strategy", "sccd_get_stats", "sccd_reset_stats",
+    "sccd_synchronize",
     "sccd_version",
 ]
 
@@ -129,8 +130,9 @@ class Context:
         self._chk(self.L.sccd_set_shard(self._h, C.c_int(rank), C.c_int(world)))
 
     # ---- mesh + boxes
-    def upload_mesh(self, V0, V1, E, F, sizes=None):
-        """Host numpy arrays (column-major) or device pointers with sizes=(nV, nE, nF)."""
+    def upload_mesh(self, V0, V1, E, F, sizes=None, host=False):
+        """Host numpy arrays (column-major), or raw pointers with sizes=(nV, nE, nF): device
+        pointers by default, host pointers (e.g. pinned buffers) with host=True."""
         if sizes is None:
             for a, cols in ((V0, 3), (V1, 3), (E, 2), (F, 3)):
                 if a.ndim != 2 or a.shape[1] != cols or not a.flags.f_contiguous:
@@ -146,7 +148,7 @@ class Context:
             on_dev = 0
         else:
             nV, nE, nF = sizes
-            on_dev = 1
+            on_dev = 0 if host else 1
         self._chk(self.L.sccd_upload_mesh(
             self._h, _ptr(V0), _ptr(V1), C.c_int64(nV), _ptr(E), C.c_int64(nE), _ptr(F),
             C.c_int64(nF), C.c_int(on_dev)))
@@ -277,6 +279,9 @@ class Context:
         s = Stats()
         self._chk(self.L.sccd_get_stats(self._h, C.byref(s)))
         return s.as_dict()
+
+    def reset_stats(self):
+        self._chk(self.L.sccd_reset_stats(self._h))
 
     def synchronize(self):
         self._chk(self.L.sccd_synchronize(self._h))

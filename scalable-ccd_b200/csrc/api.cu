@@ -1035,6 +1035,15 @@ int sccd_get_stats(const sccd_ctx* ctx, sccd_stats* out)
     return SCCD_OK;
 }
 
+int sccd_reset_stats(sccd_ctx* ctx)
+{
+    return guarded(ctx, [&] {
+        kt_resolve(ctx);
+        reset_stats(ctx);
+        return SCCD_OK;
+    });
+}
+
 int sccd_synchronize(sccd_ctx* ctx)
 {
     return guarded(ctx, [&] {
