@@ -84,6 +84,8 @@ typedef struct {
     float ms_k_boxes;        /* vertex + element box kernels                            */
     float ms_k_gather;       /* both record gathers                                     */
     float pad_;
+    int64_t n_records[2];    /* sweep records = boxes replicated into the (y,z) cells   */
+    int32_t grid_cells[2][2]; /* (sy, sz) cell grid chosen for each list                */
 } sccd_stats;
 
 /* ---- context ------------------------------------------------------------------ */
@@ -107,6 +109,11 @@ int sccd_set_max_pairs_per_chunk(sccd_ctx* ctx, int64_t max_pairs);
 /* Capacity (items) of the bounded narrow-phase work queue (0 = default).  Replaces
  * MemoryHandler::MAX_UNIT_SIZE (cuda/memory_handler.cpp:81-122). */
 int sccd_set_queue_capacity(sccd_ctx* ctx, int64_t items);
+
+/* Upper bound on the number of (y, z) sweep cells per list: 0 = automatic (about twice the
+ * mean box extent per cell, <= 2^20 cells), 1 = plain one-axis sweep.  The overlap set does
+ * not depend on it; it only changes how many candidates the sweep has to test. */
+int sccd_set_grid_cells(sccd_ctx* ctx, int max_cells);
 
 /* Multi-GPU sharding: this context sweeps only the rank-th of `world` owner slices
  * of each sorted list (slices balanced by sweep-window length) and therefore emits

@@ -23,7 +23,8 @@ AABB_DTYPE = np.dtype(
 # every symbol include/sccd.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "sccd_create", "sccd_destroy", "sccd_last_error", "sccd_set_memory_limit",
-    "sccd_set_max_pairs_per_chunk", "sccd_set_queue_capacity", "sccd_set_shard",
+    "sccd_set_max_pairs_per_chunk", "sccd_set_queue_capacity", "sccd_set_grid_cells",
+    "sccd_set_shard",
     "sccd_upload_mesh", "sccd_build_boxes", "sccd_get_boxes", "sccd_set_boxes",
     "sccd_broad_phase_begin",
     "sccd_broad_phase_partial", "sccd_broad_phase_is_complete", "sccd_broad_phase",
@@ -43,14 +44,16 @@ class Stats(C.Structure):
         ("ms_sweep", C.c_float * 2), ("ms_narrow", C.c_float * 2), ("ms_total", C.c_float),
         ("ms_k_sweep_count", C.c_float * 2), ("ms_k_sweep_fill", C.c_float * 2),
         ("ms_k_narrow", C.c_float * 2), ("ms_k_boxes", C.c_float), ("ms_k_gather", C.c_float),
-        ("pad_", C.c_float),
+        ("pad_", C.c_float), ("n_records", C.c_int64 * 2), ("grid_cells", (C.c_int32 * 2) * 2),
     ]
 
     def as_dict(self):
         out = {}
         for name, _ in self._fields_:
             v = getattr(self, name)
-            out[name] = list(v) if hasattr(v, "__len__") else v
+            if hasattr(v, "__len__"):
+                v = [list(x) if hasattr(x, "__len__") else x for x in v]
+            out[name] = v
         return out
 
 
@@ -125,6 +128,10 @@ class Context:
 
     def set_queue_capacity(self, n: int):
         self._chk(self.L.sccd_set_queue_capacity(self._h, C.c_int64(n)))
+
+    def set_grid_cells(self, max_cells: int):
+        """0 = automatic (y, z) cell grid, 1 = plain one-axis sweep."""
+        self._chk(self.L.sccd_set_grid_cells(self._h, C.c_int(max_cells)))
 
     def set_shard(self, rank: int, world: int):
         self._chk(self.L.sccd_set_shard(self._h, C.c_int(rank), C.c_int(world)))

@@ -70,15 +70,19 @@ struct sccd_ctx {
 
     // box lists: [0] = vertex+face (two lists), [1] = edges
     struct ListBufs {
-        DevBuf ux, uyz, uid;     // unsorted exact records
-        DevBuf keys, keys_tmp, idx, idx_out;
-        DevBuf sx, syz, sid;     // sorted exact
-        DevBuf pxmin, pxmax, pyz; // sorted f32 prefilter
+        DevBuf ux, uyz, uid;     // unsorted exact records (one per box)
+        DevBuf copies, offs;     // cells touched per box, and their exclusive scan
+        DevBuf keys, keys_tmp, idx, idx_out; // (key, box index) records, one per (box, cell)
+        DevBuf sx, syz, sid;     // sorted exact records
+        DevBuf pkey, preach, pyz; // sorted prefilter view
         SortedList sorted;
         BoxArrays unsorted;
+        int n_boxes = 0;
     } lists[3]; // [2] = caller-made boxes (sccd_set_boxes)
     bool have_custom = false;
-    DevBuf b_sort_temp;
+    DevBuf b_sort_temp, b_stats;
+    double* h_stats = nullptr; // pinned
+    int grid_max_cells = -1;   // < 0: choose automatically; 1 forces the plain 1-axis sweep
 
     // broad-phase state
     int bp_kind = -1;
@@ -109,6 +113,8 @@ struct sccd_ctx {
     {
         if (h_small)
             cudaFreeHost(h_small);
+        if (h_stats)
+            cudaFreeHost(h_stats);
         if (h_counters)
             cudaFreeHost(h_counters);
         for (auto& e : ev)
@@ -252,18 +258,135 @@ void prepare_list(sccd_ctx* c, int which, int n, bool two_lists)
     L.unsorted.x = (double2*)L.ux.reserve(m * sizeof(double2));
     L.unsorted.yz = (double4*)L.uyz.reserve(m * sizeof(double4));
     L.unsorted.id = (int4*)L.uid.reserve(m * sizeof(int4));
-    L.keys.reserve(m * 4);
-    L.keys_tmp.reserve(m * 4);
-    L.idx.reserve(m * 4);
-    L.idx_out.reserve(m * 4);
-    L.sorted.n = n;
+    L.n_boxes = n;
+    L.sorted.n = 0;
     L.sorted.two_lists = two_lists;
-    L.sorted.box.x = (double2*)L.sx.reserve(m * sizeof(double2));
-    L.sorted.box.yz = (double4*)L.syz.reserve(m * sizeof(double4));
-    L.sorted.box.id = (int4*)L.sid.reserve(m * sizeof(int4));
-    L.sorted.pf.xmin = (float*)L.pxmin.reserve(m * 4);
-    L.sorted.pf.xmax = (float*)L.pxmax.reserve(m * 4);
-    L.sorted.pf.yz = (float4*)L.pyz.reserve(m * sizeof(float4));
+}
+
+// Choose the (y, z) cell grid of a list from its box statistics: cells about twice the mean
+// box extent (so a box touches ~1.5 cells per axis), at most 1024 per axis / 2^20 in total.
+GridParams choose_grid(const double st[6], int n, int max_cells)
+{
+    GridParams g;
+    if (n <= 0 || max_cells == 1)
+        return g;
+    const double ext[2] = { st[1] - st[0], st[3] - st[2] };
+    const double mean[2] = { st[4] / n, st[5] / n };
+    int s[2] = { 1, 1 };
+    for (int a = 0; a < 2; a++) {
+        if (!(ext[a] > 0) || !(mean[a] >= 0) || !std::isfinite(ext[a]))
+            continue;
+        const double cell = std::max(2.0 * mean[a], ext[a] / 1024.0);
+        const double k = cell > 0 ? std::floor(ext[a] / cell) : 1.0;
+        s[a] = (int)std::min(1024.0, std::max(1.0, k));
+    }
+    const long long cap = max_cells > 0 ? max_cells : (1ll << 20);
+    while ((long long)s[0] * s[1] > cap) {
+        if (s[0] >= s[1])
+            s[0] = (s[0] + 1) / 2;
+        else
+            s[1] = (s[1] + 1) / 2;
+    }
+    g.sy = s[0];
+    g.sz = s[1];
+    g.y0 = st[0];
+    g.z0 = st[2];
+    g.inv_hy = g.sy > 1 ? g.sy / ext[0] : 0.0;
+    g.inv_hz = g.sz > 1 ? g.sz / ext[1] : 0.0;
+    return g;
+}
+
+// DeviceAABBs constructor + BroadPhase::build of the reference, for one list whose unsorted
+// exact records are on the device: grid choice, replication into cells, radix sort, gather.
+// Two small host syncs (statistics, record total).
+void sort_list(sccd_ctx* c, int which, cudaEvent_t ga, cudaEvent_t gb)
+{
+    auto& L = c->lists[which];
+    const int n = L.n_boxes;
+    if (n <= 0) {
+        L.sorted.n = 0;
+        L.sorted.grid = GridParams();
+        if (ga)
+            SCCD_CUDA(cudaEventRecord(ga, c->stream));
+        if (gb)
+            SCCD_CUDA(cudaEventRecord(gb, c->stream));
+        return;
+    }
+    if (!c->h_stats)
+        SCCD_CUDA(cudaMallocHost((void**)&c->h_stats, 64));
+    c->b_stats.reserve((size_t)(kStatsBlocks * 6 + 8) * sizeof(double));
+    double* d_stats = c->b_stats.as<double>() + kStatsBlocks * 6;
+    launch_box_stats(L.unsorted, n, c->b_stats.as<double>(), d_stats, c->stream, c->lc);
+    SCCD_CUDA(cudaMemcpyAsync(c->h_stats, d_stats, 48, cudaMemcpyDeviceToHost, c->stream));
+    SCCD_CUDA(cudaStreamSynchronize(c->stream));
+    GridParams g = choose_grid(c->h_stats, n, c->grid_max_cells);
+
+    L.copies.reserve(((size_t)n + 1) * 4);
+    L.offs.reserve(((size_t)n + 1) * 8);
+    c->b_scan_temp.reserve(scan_temp_bytes(n));
+    unsigned long long m = (unsigned long long)n;
+    for (int attempt = 0;; attempt++) {
+        if (g.sy * g.sz == 1) {
+            m = (unsigned long long)n;
+            break;
+        }
+        SCCD_CUDA(cudaMemsetAsync(L.copies.as<uint32_t>() + n, 0, 4, c->stream));
+        launch_expand_count(L.unsorted, n, g, L.copies.as<uint32_t>(), c->stream, c->lc);
+        launch_scan_u32_to_u64(
+            L.copies.as<uint32_t>(), L.offs.as<unsigned long long>(), n, c->b_scan_temp.ptr,
+            c->b_scan_temp.cap, c->stream, c->lc);
+        SCCD_CUDA(cudaMemcpyAsync(
+            c->h_stats + 6, L.offs.as<unsigned long long>() + n, 8, cudaMemcpyDeviceToHost,
+            c->stream));
+        SCCD_CUDA(cudaStreamSynchronize(c->stream));
+        m = *reinterpret_cast<unsigned long long*>(c->h_stats + 6);
+        // a few huge boxes can touch every cell: coarsen until replication is modest
+        if (m <= 2ull * n + 1024 || attempt >= 12)
+            break;
+        if (g.sy >= g.sz)
+            g.sy = (g.sy + 1) / 2;
+        else
+            g.sz = (g.sz + 1) / 2;
+        g.inv_hy = g.sy > 1 ? g.sy / (c->h_stats[1] - c->h_stats[0]) : 0.0;
+        g.inv_hz = g.sz > 1 ? g.sz / (c->h_stats[3] - c->h_stats[2]) : 0.0;
+    }
+    if (m > 2ull * n + 1024) { // give up on the grid rather than explode memory
+        g = GridParams();
+        m = (unsigned long long)n;
+    }
+    if (m >= (1ull << 27))
+        throw std::invalid_argument("more than 2^27 sweep records in one list");
+    if (g.sy * g.sz == 1) { // plain 1-axis sweep: identity expansion
+        SCCD_CUDA(cudaMemsetAsync(L.copies.as<uint32_t>() + n, 0, 4, c->stream));
+        launch_expand_count(L.unsorted, n, g, L.copies.as<uint32_t>(), c->stream, c->lc);
+        launch_scan_u32_to_u64(
+            L.copies.as<uint32_t>(), L.offs.as<unsigned long long>(), n, c->b_scan_temp.ptr,
+            c->b_scan_temp.cap, c->stream, c->lc);
+    }
+    const size_t mm = (size_t)m;
+    L.keys.reserve(mm * 8);
+    L.keys_tmp.reserve(mm * 8);
+    L.idx.reserve(mm * 4);
+    L.idx_out.reserve(mm * 4);
+    L.sorted.n = (int)m;
+    L.sorted.grid = g;
+    L.sorted.box.x = (double2*)L.sx.reserve(mm * sizeof(double2));
+    L.sorted.box.yz = (double4*)L.syz.reserve(mm * sizeof(double4));
+    L.sorted.box.id = (int4*)L.sid.reserve(mm * sizeof(int4));
+    L.sorted.pf.key = (unsigned long long*)L.pkey.reserve(mm * 8);
+    L.sorted.pf.reach = (unsigned long long*)L.preach.reserve(mm * 8);
+    L.sorted.pf.yz = (float4*)L.pyz.reserve(mm * sizeof(float4));
+    c->b_sort_temp.reserve(sort_temp_bytes((int)m));
+    launch_expand_fill(
+        L.unsorted, n, g, L.offs.as<unsigned long long>(), L.keys.as<unsigned long long>(),
+        L.idx.as<uint32_t>(), c->stream, c->lc);
+    int cell_bits = 0;
+    while ((1ll << cell_bits) < (long long)g.sy * g.sz)
+        cell_bits++;
+    launch_sort_and_gather(
+        (int)m, 32 + cell_bits, L.keys.as<unsigned long long>(),
+        L.keys_tmp.as<unsigned long long>(), L.idx.as<uint32_t>(), L.idx_out.as<uint32_t>(),
+        c->b_sort_temp.ptr, c->b_sort_temp.cap, L.unsorted, L.sorted, c->stream, c->lc, ga, gb);
 }
 
 void build_boxes(sccd_ctx* c, double inflation_radius)
@@ -278,8 +401,6 @@ void build_boxes(sccd_ctx* c, double inflation_radius)
     c->b_vbox.reserve(sizeof(double) * 6 * (size_t)std::max(nV, 1));
     prepare_list(c, 0, (int)nVF, true);
     prepare_list(c, 1, nE, false);
-    const size_t temp = std::max(sort_temp_bytes((int)nVF), sort_temp_bytes(nE));
-    c->b_sort_temp.reserve(temp);
 
     // aabb.cu:31-34: the radius itself is rounded up once
     const double radius_up = std::nextafter(inflation_radius, DBL_MAX);
@@ -288,26 +409,26 @@ void build_boxes(sccd_ctx* c, double inflation_radius)
     const size_t kt_boxes = kt_begin(c, &c->stats.ms_k_boxes);
     launch_vertex_boxes(
         c->dV0, c->dV1, nV, radius_up, c->b_vtab.as<VertexRec>(), c->b_vbox.as<double>(),
-        LV.unsorted, LV.keys.as<uint32_t>(), c->stream, c->lc);
+        LV.unsorted, c->stream, c->lc);
     launch_element_boxes(
-        c->b_vbox.as<double>(), c->dE, nE, c->dF, nF, nV, LE.unsorted, LE.keys.as<uint32_t>(),
-        LV.unsorted, LV.keys.as<uint32_t>(), c->stream, c->lc);
+        c->b_vbox.as<double>(), c->dE, nE, c->dF, nF, nV, LE.unsorted, LV.unsorted, c->stream,
+        c->lc);
     kt_end(c, kt_boxes);
     record(c, EV_BUILD);
-    launch_sort_and_gather(
-        (int)nVF, LV.keys.as<uint32_t>(), LV.keys_tmp.as<uint32_t>(), LV.idx.as<uint32_t>(),
-        LV.idx_out.as<uint32_t>(), c->b_sort_temp.ptr, c->b_sort_temp.cap, LV.unsorted,
-        LV.sorted, c->stream, c->lc, c->ev[EV_GA0], c->ev[EV_GB0]);
-    launch_sort_and_gather(
-        nE, LE.keys.as<uint32_t>(), LE.keys_tmp.as<uint32_t>(), LE.idx.as<uint32_t>(),
-        LE.idx_out.as<uint32_t>(), c->b_sort_temp.ptr, c->b_sort_temp.cap, LE.unsorted,
-        LE.sorted, c->stream, c->lc, c->ev[EV_GA1], c->ev[EV_GB1]);
+    sort_list(c, 0, c->ev[EV_GA0], c->ev[EV_GB0]);
+    sort_list(c, 1, c->ev[EV_GA1], c->ev[EV_GB1]);
     c->gather_timed = true;
     record(c, EV_SORT);
     c->have_boxes = true;
     c->bp_kind = -1;
     c->stats.n_boxes[0] = nVF;
     c->stats.n_boxes[1] = nE;
+    c->stats.n_records[0] = LV.sorted.n;
+    c->stats.n_records[1] = LE.sorted.n;
+    c->stats.grid_cells[0][0] = LV.sorted.grid.sy;
+    c->stats.grid_cells[0][1] = LV.sorted.grid.sz;
+    c->stats.grid_cells[1][0] = LE.sorted.grid.sy;
+    c->stats.grid_cells[1][1] = LE.sorted.grid.sz;
 }
 
 // stats are kept per reference pass (VF, EE); caller-made box lists report in slot 0
@@ -329,7 +450,6 @@ void set_boxes(
     std::vector<double2> hx((size_t)std::max<int64_t>(n, 1));
     std::vector<double4> hyz(hx.size());
     std::vector<int4> hid(hx.size());
-    std::vector<uint32_t> hkey(hx.size());
     double s1[3] = { 0, 0, 0 }, s2[3] = { 0, 0, 0 };
     // variance accumulation in the reference's order: the boxes as swept, i.e. sorted on
     // min[axis] (sort_and_sweep.cpp:176-186); summation order only matters in the last ulp,
@@ -340,11 +460,6 @@ void set_boxes(
         hyz[i] = make_double4(bx.min[ay], bx.min[az], bx.max[ay], bx.max[az]);
         const int elem = (two && i < na) ? -bx.element_id - 1 : bx.element_id;
         hid[i] = make_int4(bx.vertex_ids[0], bx.vertex_ids[1], bx.vertex_ids[2], elem);
-        // round toward -inf: nearest, then step down if it landed above
-        float f = (float)bx.min[ax];
-        if ((double)f > bx.min[ax])
-            f = std::nextafterf(f, -INFINITY);
-        hkey[i] = float_to_key(f);
         for (int k = 0; k < 3; k++) {
             const double ctr = (bx.min[k] + bx.max[k]) / 2;
             s1[k] += ctr;
@@ -364,21 +479,17 @@ void set_boxes(
     }
     prepare_list(c, 2, (int)n, two);
     auto& L = c->lists[2];
-    c->b_sort_temp.reserve(sort_temp_bytes((int)n));
     if (n > 0) {
         SCCD_CUDA(cudaMemcpyAsync(L.unsorted.x, hx.data(), sizeof(double2) * n, cudaMemcpyHostToDevice, c->stream));
         SCCD_CUDA(cudaMemcpyAsync(L.unsorted.yz, hyz.data(), sizeof(double4) * n, cudaMemcpyHostToDevice, c->stream));
         SCCD_CUDA(cudaMemcpyAsync(L.unsorted.id, hid.data(), sizeof(int4) * n, cudaMemcpyHostToDevice, c->stream));
-        SCCD_CUDA(cudaMemcpyAsync(L.keys.ptr, hkey.data(), 4 * n, cudaMemcpyHostToDevice, c->stream));
     }
-    launch_sort_and_gather(
-        (int)n, L.keys.as<uint32_t>(), L.keys_tmp.as<uint32_t>(), L.idx.as<uint32_t>(),
-        L.idx_out.as<uint32_t>(), c->b_sort_temp.ptr, c->b_sort_temp.cap, L.unsorted, L.sorted,
-        c->stream, c->lc);
+    sort_list(c, 2, nullptr, nullptr);
     SCCD_CUDA(cudaStreamSynchronize(c->stream)); // host staging vectors go out of scope
     c->have_custom = true;
     c->bp_kind = -1;
     c->stats.n_boxes[0] = n;
+    c->stats.n_records[0] = L.sorted.n;
 }
 
 void small_scratch(sccd_ctx* c)
@@ -786,6 +897,14 @@ int sccd_set_queue_capacity(sccd_ctx* ctx, int64_t items)
     if (!ctx || items < 0)
         return SCCD_ERR_ARG;
     ctx->queue_cap = items;
+    return SCCD_OK;
+}
+
+int sccd_set_grid_cells(sccd_ctx* ctx, int max_cells)
+{
+    if (!ctx || max_cells < 0)
+        return SCCD_ERR_ARG;
+    ctx->grid_max_cells = max_cells == 0 ? -1 : max_cells;
     return SCCD_OK;
 }
 

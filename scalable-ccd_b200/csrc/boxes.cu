@@ -3,7 +3,7 @@
 // Replaces the reference's host/TBB box builders + 64 B/box AoS upload + split_boxes
 // kernel (cuda/broad_phase/aabb.cu:26-35, 40-72, 115-229) with two coalesced kernels that
 // read the two-frame vertex / edge / face buffers directly and emit, per box, the exact
-// 64-byte record (x interval, yz mini-box, ids) plus the 32-bit radix key of min.x.
+// 64-byte record (x interval, yz mini-box, ids); the sort keys are made by csrc/grid.cu.
 // Results are bit-identical to the reference's boxes: nextafter() in double is exact on
 // the device and min/max/add are correctly rounded.
 #include "common.cuh"
@@ -20,20 +20,17 @@ __device__ __forceinline__ double next_down(double x) { return nextafter(x, -DBL
 __device__ __forceinline__ double next_up(double x) { return nextafter(x, DBL_MAX); }
 
 __device__ __forceinline__ void store_record(
-    const BoxArrays& out, uint32_t* keys, int k, const double lo[3], const double hi[3],
-    int4 id)
+    const BoxArrays& out, int k, const double lo[3], const double hi[3], int4 id)
 {
     out.x[k] = make_double2(lo[0], hi[0]);
     out.yz[k] = make_double4(lo[1], lo[2], hi[1], hi[2]);
     out.id[k] = id;
-    // sort key: min.x rounded DOWN to f32 (conservative for the f32 prefilter sweep)
-    keys[k] = float_to_key(__double2float_rd(lo[0]));
 }
 
 // aabb.cu:146-184 build_vertex_boxes(V0, V1, r) + from_point + conservative_inflation.
 __global__ void __launch_bounds__(kThreads) vertex_boxes_kernel(
     const double* __restrict__ V0, const double* __restrict__ V1, int nV, double radius_up,
-    VertexRec* __restrict__ vtab, double* __restrict__ vbox, BoxArrays vf, uint32_t* vf_keys)
+    VertexRec* __restrict__ vtab, double* __restrict__ vbox, BoxArrays vf)
 {
     const int i = blockIdx.x * kThreads + threadIdx.x;
     if (i >= nV)
@@ -64,7 +61,7 @@ __global__ void __launch_bounds__(kThreads) vertex_boxes_kernel(
     vb[2] = make_double2(hi[1], hi[2]);
     // aabb.cu:180-181 ids; element id flipped because vertices are list A of the
     // vertex-face sweep (broad_phase.cu:20-26).
-    store_record(vf, vf_keys, i, lo, hi, make_int4(i, -i - 1, -i - 1, -i - 1));
+    store_record(vf, i, lo, hi, make_int4(i, -i - 1, -i - 1, -i - 1));
 }
 
 __device__ __forceinline__ void load_vbox(
@@ -83,8 +80,7 @@ __device__ __forceinline__ void load_vbox(
 // aabb.cu:186-229 build_edge_boxes / build_face_boxes (union of vertex boxes).
 __global__ void __launch_bounds__(kThreads) element_boxes_kernel(
     const double* __restrict__ vbox, const int32_t* __restrict__ E, int nE,
-    const int32_t* __restrict__ F, int nF, int nV, BoxArrays eb, uint32_t* e_keys,
-    BoxArrays vf, uint32_t* vf_keys)
+    const int32_t* __restrict__ F, int nF, int nV, BoxArrays eb, BoxArrays vf)
 {
     const int t = blockIdx.x * kThreads + threadIdx.x;
     if (t < nE) {
@@ -97,7 +93,7 @@ __global__ void __launch_bounds__(kThreads) element_boxes_kernel(
             lo[k] = fmin(lo[k], lo1[k]);
             hi[k] = fmax(hi[k], hi1[k]);
         }
-        store_record(eb, e_keys, t, lo, hi, make_int4(e0, e1, -e0 - 1, t));
+        store_record(eb, t, lo, hi, make_int4(e0, e1, -e0 - 1, t));
     } else if (t < nE + nF) {
         const int f = t - nE;
         const int f0 = F[f], f1 = F[f + (size_t)nF], f2 = F[f + (size_t)2 * nF];
@@ -110,7 +106,7 @@ __global__ void __launch_bounds__(kThreads) element_boxes_kernel(
             lo[k] = fmin(fmin(lo[k], lo1[k]), lo2[k]);
             hi[k] = fmax(fmax(hi[k], hi1[k]), hi2[k]);
         }
-        store_record(vf, vf_keys, nV + f, lo, hi, make_int4(f0, f1, f2, f));
+        store_record(vf, nV + f, lo, hi, make_int4(f0, f1, f2, f));
     }
 }
 
@@ -118,26 +114,25 @@ __global__ void __launch_bounds__(kThreads) element_boxes_kernel(
 
 void launch_vertex_boxes(
     const double* V0, const double* V1, int nV, double radius_up, VertexRec* vtab,
-    double* vbox, BoxArrays vf_unsorted, uint32_t* vf_keys, cudaStream_t s, LaunchCounter& lc)
+    double* vbox, BoxArrays vf_unsorted, cudaStream_t s, LaunchCounter& lc)
 {
     if (nV <= 0)
         return;
     vertex_boxes_kernel<<<(nV + kThreads - 1) / kThreads, kThreads, 0, s>>>(
-        V0, V1, nV, radius_up, vtab, vbox, vf_unsorted, vf_keys);
+        V0, V1, nV, radius_up, vtab, vbox, vf_unsorted);
     SCCD_CUDA(cudaGetLastError());
     lc.n++;
 }
 
 void launch_element_boxes(
     const double* vbox, const int32_t* E, int nE, const int32_t* F, int nF, int nV,
-    BoxArrays e_unsorted, uint32_t* e_keys, BoxArrays vf_unsorted, uint32_t* vf_keys,
-    cudaStream_t s, LaunchCounter& lc)
+    BoxArrays e_unsorted, BoxArrays vf_unsorted, cudaStream_t s, LaunchCounter& lc)
 {
     const int n = nE + nF;
     if (n <= 0)
         return;
     element_boxes_kernel<<<(n + kThreads - 1) / kThreads, kThreads, 0, s>>>(
-        vbox, E, nE, F, nF, nV, e_unsorted, e_keys, vf_unsorted, vf_keys);
+        vbox, E, nE, F, nF, nV, e_unsorted, vf_unsorted);
     SCCD_CUDA(cudaGetLastError());
     lc.n++;
 }

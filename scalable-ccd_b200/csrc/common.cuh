@@ -80,20 +80,44 @@ struct BoxArrays {
     int4* id = nullptr;
 };
 
-// f32 conservative prefilter view of the SORTED boxes (min rounded down, max rounded
-// up): xmin / xmax separate, yz = (ymin, ymax, zmin, zmax).
+// Uniform (y, z) cell grid laid over a list.  Every box is replicated into each cell its
+// closed [ymin,ymax] x [zmin,zmax] range touches and the list is sorted on (cell, xmin), so
+// the sweep window of a box only holds boxes of the same cell.  A pair is reported in ONE
+// cell only: the cell of (max(ymin_a, ymin_b), max(zmin_a, zmin_b)), which both boxes touch
+// whenever they overlap (cell_index() is monotone).  sy = sz = 1 is the plain 1-axis sweep.
+struct GridParams {
+    double y0 = 0, z0 = 0, inv_hy = 0, inv_hz = 0;
+    int sy = 1, sz = 1;
+};
+
+__host__ __device__ inline int cell_index(double v, double v0, double inv_h, int s)
+{
+    // monotone non-decreasing in v (subtraction, multiplication by a non-negative constant,
+    // truncation and clamping all are); NaN-free inputs assumed
+    if (s <= 1)
+        return 0;
+    const double f = (v - v0) * inv_h;
+    int i = f <= 0.0 ? 0 : (f >= (double)(s - 1) ? s - 1 : (int)f);
+    return i;
+}
+
+// Prefilter view of the SORTED records: 64-bit sort key = (cell << 32) | key32(f32(xmin)
+// rounded down), reach = (cell << 32) | key32(f32(xmax) rounded up), and the f32 conservative
+// yz = (ymin dn, ymax up, zmin dn, zmax up).  For j after i in sorted order,
+// key[j] <= reach[i]  <=>  same cell and f32(xmin_j) <= f32(xmax_i).
 struct PrefilterArrays {
-    float* xmin = nullptr;
-    float* xmax = nullptr;
+    unsigned long long* key = nullptr;
+    unsigned long long* reach = nullptr;
     float4* yz = nullptr;
 };
 
-// One sorted list ready for sweeping.
+// One sorted list ready for sweeping (n = number of RECORDS, >= number of boxes).
 struct SortedList {
     int n = 0;
     bool two_lists = false;
+    GridParams grid;
     BoxArrays box;      // sorted, exact
-    PrefilterArrays pf; // sorted, f32
+    PrefilterArrays pf; // sorted prefilter view
 };
 
 #ifdef __CUDACC__
@@ -180,18 +204,34 @@ struct LaunchCounter {
 
 void launch_vertex_boxes(
     const double* V0, const double* V1, int nV, double radius_up, VertexRec* vtab,
-    double* vbox /* 6*nV: min xyz, max xyz */, BoxArrays vf_unsorted, uint32_t* vf_keys,
-    cudaStream_t s, LaunchCounter& lc);
+    double* vbox /* 6*nV: min xyz, max xyz */, BoxArrays vf_unsorted, cudaStream_t s,
+    LaunchCounter& lc);
 void launch_element_boxes(
     const double* vbox, const int32_t* E, int nE, const int32_t* F, int nF, int nV,
-    BoxArrays e_unsorted, uint32_t* e_keys, BoxArrays vf_unsorted, uint32_t* vf_keys,
+    BoxArrays e_unsorted, BoxArrays vf_unsorted, cudaStream_t s, LaunchCounter& lc);
+
+// ---- grid (csrc/grid.cu)
+// stats[6] = {min ymin, max ymax, min zmin, max zmax, sum (ymax-ymin), sum (zmax-zmin)}
+constexpr int kStatsBlocks = 296;
+void launch_box_stats(
+    const BoxArrays& unsorted, int n, double* partials /* kStatsBlocks*6 */, double* stats,
     cudaStream_t s, LaunchCounter& lc);
+// copies[i] = number of cells box i touches
+void launch_expand_count(
+    const BoxArrays& unsorted, int n, GridParams g, uint32_t* copies, cudaStream_t s,
+    LaunchCounter& lc);
+// one (key, box index) record per touched cell, at offsets[i] ...
+void launch_expand_fill(
+    const BoxArrays& unsorted, int n, GridParams g, const unsigned long long* offsets,
+    unsigned long long* keys, uint32_t* idx, cudaStream_t s, LaunchCounter& lc);
 
 size_t sort_temp_bytes(int n);
+// sorts m (key, box index) records on the low key_bits bits and gathers the sorted views
 void launch_sort_and_gather(
-    int n, uint32_t* keys_in, uint32_t* keys_tmp, uint32_t* idx_in, uint32_t* idx_out,
-    void* temp, size_t temp_bytes, BoxArrays unsorted, SortedList out, cudaStream_t s,
-    LaunchCounter& lc, cudaEvent_t gather_begin = nullptr, cudaEvent_t gather_end = nullptr);
+    int m, int key_bits, unsigned long long* keys_in, unsigned long long* keys_out,
+    uint32_t* idx_in, uint32_t* idx_out, void* temp, size_t temp_bytes, BoxArrays unsorted,
+    SortedList out, cudaStream_t s, LaunchCounter& lc, cudaEvent_t gather_begin = nullptr,
+    cudaEvent_t gather_end = nullptr);
 
 // window[i] = number of candidates after owner i whose f32 xmin <= owner's f32 xmax
 void launch_sweep_windows(

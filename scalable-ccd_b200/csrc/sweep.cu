@@ -1,14 +1,16 @@
-// Sweep over the major-axis-sorted boxes (north-star item 2b).
+// Sweep over the (cell, major-axis)-sorted records (north-star item 2b).
 //
 // Replaces sweep_and_tiniest_queue (cuda/broad_phase/sweep.cu:101-182: one warp per CTA,
 // a 64-slot shared ring rebalanced with shared atomics every round, uncoalesced 48 B
 // MiniBox loads per candidate, one global atomicAdd per emitted pair into a buffer that is
 // value-initialised on every call) with a tiled sweep:
 //
-//   * a CTA owns a tile of 256 consecutive sorted boxes ("owners", one per lane);
+//   * a CTA owns a tile of 256 consecutive sorted records ("owners", one per lane);
 //   * the candidate window to the right of the tile is streamed through shared memory in
-//     256-box chunks of the 20-byte f32 prefilter view (register double-buffered), every
-//     lane testing its owner against each staged candidate by shared-memory broadcast;
+//     256-record chunks of the 24-byte prefilter view (register double-buffered), every
+//     lane testing its owner against each staged candidate by shared-memory broadcast:
+//     one 64-bit compare key_j <= reach_i (same cell AND f32 xmin_j <= f32 xmax_i, see
+//     common.cuh) plus four f32 compares on y / z;
 //   * prefilter survivors (a conservative superset: min rounded down / max rounded up to
 //     f32) are ballot/scan-compacted into a per-warp shared queue -- the "tiniest queue" --
 //     and drained 32 at a time with ALL lanes running the exact double test + id tests,
@@ -17,12 +19,14 @@
 //     (owner position, candidate position) and therefore deterministic; no global atomics
 //     and no giant memset; 64-bit offsets.
 //
-// The emitted SET equals the reference's: every pair (i < j in sorted order) with closed
-// overlap on x, y, z (cuda/broad_phase/aabb.cuh:100-104, sweep.cu:131,173), valid list
-// membership (collision.cuh:27-35) and no shared vertex (collision.cuh:17-21).  Sorting on
-// the f32 key instead of the double changes only the ORDER in which ties are visited: the
-// window test uses f32(min_j) <= f32up(max_i), a superset of min_j <= max_i, and the exact
-// test checks both x directions, so no pair is lost or duplicated.
+// The emitted SET equals the reference's: every pair with closed overlap on x, y, z
+// (cuda/broad_phase/aabb.cuh:100-104, sweep.cu:131,173), valid list membership
+// (collision.cuh:27-35) and no shared vertex (collision.cuh:17-21).  Why nothing is lost or
+// duplicated: (1) sorting on the f32 key instead of the double only changes the ORDER in
+// which ties are visited -- the window test on rounded values is a superset of
+// min_j <= max_i and the exact test checks both x directions; (2) two overlapping boxes both
+// own a record in the cell of (max(ymin_a,ymin_b), max(zmin_a,zmin_b)) because cell_index()
+// is monotone, and the pair is accepted in that cell only.
 #include "common.cuh"
 
 #include <cfloat>
@@ -37,23 +41,25 @@ constexpr int kChunk = 256; // candidates staged per step
 constexpr int kQueueCap = 32 * 32 + 32;
 constexpr int kRelBits = 27; // candidate position relative to the tile start
 constexpr unsigned kFull = 0xffffffffu;
+constexpr unsigned long long kKeyInf = ~0ull;
 
 struct SweepSmem {
-    float c_xmin[kChunk];
+    unsigned long long c_key[kChunk];
     float4 c_yz[kChunk];
     double2 o_x[kTile];
     double4 o_yz[kTile];
     int4 o_id[kTile];
     unsigned long long o_off[kTile];
+    uint32_t o_cell[kTile];
     uint32_t o_cnt[kTile];
     uint32_t q[kWarps][kQueueCap];
-    float red[kWarps];
+    unsigned long long red[kWarps];
 };
 
 template <bool FILL, bool TWO_LISTS>
 __device__ __forceinline__ void drain32(
-    SweepSmem& sm, const BoxArrays& box, int tile0, int warp, int lane, uint32_t entry,
-    bool active, sccd_pair* __restrict__ pairs)
+    SweepSmem& sm, const BoxArrays& box, const GridParams& g, int tile0, int warp, int lane,
+    uint32_t entry, bool active, sccd_pair* __restrict__ pairs)
 {
     const int ol = active ? (int)(entry >> kRelBits) : 0;
     const int t = warp * 32 + ol;
@@ -77,6 +83,12 @@ __device__ __forceinline__ void drain32(
             || aid.y == bid.x || aid.y == bid.y || aid.y == bid.z || aid.z == bid.x
             || aid.z == bid.y || aid.z == bid.z;
         hit = hit && !share;
+        if (g.sy * g.sz > 1) {
+            // report the pair only in its home cell (both boxes own a record there)
+            const int cy = cell_index(fmax(ayz.x, byz.x), g.y0, g.inv_hy, g.sy);
+            const int cz = cell_index(fmax(ayz.y, byz.y), g.z0, g.inv_hz, g.sz);
+            hit = hit && (uint32_t)(cy * g.sz + cz) == sm.o_cell[t];
+        }
         ea = aid.w;
         eb = bid.w;
     }
@@ -110,8 +122,8 @@ __device__ __forceinline__ void drain32(
 
 template <bool FILL, bool TWO_LISTS>
 __global__ void __launch_bounds__(kTile) sweep_kernel(
-    PrefilterArrays pf, BoxArrays box, int n, int shard_lo, int owner_lo, int owner_hi,
-    uint32_t* __restrict__ counts, const unsigned long long* __restrict__ offsets,
+    PrefilterArrays pf, BoxArrays box, GridParams g, int n, int shard_lo, int owner_lo,
+    int owner_hi, uint32_t* __restrict__ counts, const unsigned long long* __restrict__ offsets,
     sccd_pair* __restrict__ pairs, unsigned long long* __restrict__ n_candidates)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -124,70 +136,73 @@ __global__ void __launch_bounds__(kTile) sweep_kernel(
     const int i = tile0 + tid;
     const bool valid = i < owner_hi;
 
-    float my_xmax = __uint_as_float(0xff800000u); // -inf: an invalid owner matches nothing
+    unsigned long long my_reach = 0; // an invalid owner reaches nothing (keys are > 0)
     float4 my = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid) {
-        my_xmax = pf.xmax[i];
+        my_reach = pf.reach[i];
         my = pf.yz[i];
         sm.o_x[tid] = box.x[i];
         sm.o_yz[tid] = box.yz[i];
         sm.o_id[tid] = box.id[i];
+        sm.o_cell[tid] = (uint32_t)(my_reach >> 32);
         if (FILL) // position of this owner's first pair inside the chunk being filled
             sm.o_off[tid] = offsets[i - shard_lo] - offsets[owner_lo - shard_lo];
     }
     sm.o_cnt[tid] = 0;
 
-    // reach of the warp / of the tile along the sorted axis
-    float wmax = my_xmax;
+    // reach of the warp / of the tile in sorted-key order
+    unsigned long long wmax = my_reach;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-        wmax = fmaxf(wmax, __shfl_xor_sync(kFull, wmax, o));
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long v = __shfl_xor_sync(kFull, wmax, o);
+        wmax = v > wmax ? v : wmax;
+    }
     if (lane == 0)
         sm.red[warp] = wmax;
     __syncthreads();
-    float tile_xmax = sm.red[0];
+    unsigned long long tile_max = sm.red[0];
 #pragma unroll
     for (int w = 1; w < kWarps; w++)
-        tile_xmax = fmaxf(tile_xmax, sm.red[w]);
+        tile_max = sm.red[w] > tile_max ? sm.red[w] : tile_max;
 
     uint32_t* q = sm.q[warp];
-    int qn = 0;                       // entries waiting in this warp's queue (warp-uniform)
-    unsigned long long tested = 0;    // exact tests run by this warp (lane 0's copy is used)
+    int qn = 0;                    // entries waiting in this warp's queue (warp-uniform)
+    unsigned long long tested = 0; // exact tests run by this warp (lane 0's copy is used)
 
     // register double buffer for the next chunk
     int cs = tile0 + 1;
-    float nx = __uint_as_float(0x7f800000u); // +inf pads the list
+    unsigned long long nk = kKeyInf; // +inf pads the list
     float4 nyz = make_float4(0.f, 0.f, 0.f, 0.f);
     if (cs + tid < n) {
-        nx = pf.xmin[cs + tid];
+        nk = pf.key[cs + tid];
         nyz = pf.yz[cs + tid];
     }
     for (; cs < n; cs += kChunk) {
         __syncthreads(); // previous chunk fully consumed
-        sm.c_xmin[tid] = nx;
+        sm.c_key[tid] = nk;
         sm.c_yz[tid] = nyz;
         __syncthreads();
-        if (sm.c_xmin[0] > tile_xmax)
+        if (sm.c_key[0] > tile_max)
             break; // block-uniform: the sorted list has left the tile's reach
         {
             const int jn = cs + kChunk + tid;
-            nx = __uint_as_float(0x7f800000u);
+            nk = kKeyInf;
             if (jn < n) {
-                nx = pf.xmin[jn];
+                nk = pf.key[jn];
                 nyz = pf.yz[jn];
             }
         }
-        if (sm.c_xmin[0] > wmax)
+        if (sm.c_key[0] > wmax)
             continue; // warp-uniform
         for (int k0 = 0; k0 < kChunk; k0 += 32) {
-            if (sm.c_xmin[k0] > wmax)
+            if (sm.c_key[k0] > wmax)
                 break; // warp-uniform
             uint32_t mask = 0;
 #pragma unroll
             for (int kk = 0; kk < 32; kk++) {
-                const float xm = sm.c_xmin[k0 + kk];
+                const unsigned long long kj = sm.c_key[k0 + kk];
                 const float4 b = sm.c_yz[k0 + kk];
-                const bool p = (xm <= my_xmax) && (b.x <= my.y) && (my.x <= b.y)
+                const bool p = (kj <= my_reach) && (b.x <= my.y) && (my.x <= b.y)
                     && (b.z <= my.w) && (my.z <= b.w);
                 mask |= (p ? 1u : 0u) << kk;
             }
@@ -223,7 +238,8 @@ __global__ void __launch_bounds__(kTile) sweep_kernel(
             if (qn >= 32) {
                 const int nfull = qn & ~31;
                 for (int h = 0; h < nfull; h += 32)
-                    drain32<FILL, TWO_LISTS>(sm, box, tile0, warp, lane, q[h + lane], true, pairs);
+                    drain32<FILL, TWO_LISTS>(
+                        sm, box, g, tile0, warp, lane, q[h + lane], true, pairs);
                 tested += nfull;
                 const int r = qn - nfull;
                 const uint32_t v = (lane < r) ? q[nfull + lane] : 0u;
@@ -237,7 +253,7 @@ __global__ void __launch_bounds__(kTile) sweep_kernel(
     }
     if (qn > 0) {
         drain32<FILL, TWO_LISTS>(
-            sm, box, tile0, warp, lane, lane < qn ? q[lane] : 0u, lane < qn, pairs);
+            sm, box, g, tile0, warp, lane, lane < qn ? q[lane] : 0u, lane < qn, pairs);
         tested += qn;
     }
     if (!FILL) {
@@ -249,19 +265,19 @@ __global__ void __launch_bounds__(kTile) sweep_kernel(
     }
 }
 
-// window[i] = #candidates j > i with f32 xmin_j <= f32 xmax_i (sweep work estimate used to
-// balance owner ranges across GPUs).
+// window[i] = #records j > i with key_j <= reach_i (sweep work estimate used to balance
+// owner ranges across GPUs).
 __global__ void __launch_bounds__(256)
     sweep_window_kernel(PrefilterArrays pf, int n, uint32_t* __restrict__ window)
 {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n)
         return;
-    const float xmax = pf.xmax[i];
-    int lo = i + 1, hi = n; // first j in (i, n) with xmin[j] > xmax
+    const unsigned long long reach = pf.reach[i];
+    int lo = i + 1, hi = n; // first j in (i, n) with key[j] > reach
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (pf.xmin[mid] <= xmax)
+        if (pf.key[mid] <= reach)
             lo = mid + 1;
         else
             hi = mid;
@@ -304,7 +320,8 @@ void launch_sweep(
     }
     const int grid = (owners + kTile - 1) / kTile;
     kern<<<grid, kTile, sizeof(SweepSmem), s>>>(
-        L.pf, L.box, L.n, shard_lo, owner_lo, owner_hi, counts, offsets, pairs, n_candidates);
+        L.pf, L.box, L.grid, L.n, shard_lo, owner_lo, owner_hi, counts, offsets, pairs,
+        n_candidates);
     SCCD_CUDA(cudaGetLastError());
     lc.n++;
 }
@@ -326,7 +343,7 @@ void launch_sweep_count(
     unsigned long long* n_candidates, cudaStream_t s, LaunchCounter& lc)
 {
     if (L.n >= (1 << kRelBits))
-        throw std::runtime_error("sweep: more than 2^27 boxes in one list is not supported");
+        throw std::runtime_error("sweep: more than 2^27 records in one list is not supported");
     if (L.two_lists)
         launch_sweep<false, true>(
             L, owner_lo, owner_lo, owner_hi, counts, nullptr, nullptr, n_candidates, s, lc);

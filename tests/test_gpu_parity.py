@@ -318,3 +318,30 @@ def test_caller_made_boxes_any_axis(ctx, sccd, orc, scene_small, axis):
         ref = orc.ref_cpu_broad_phase(scene_small, r=1e-3, axis=axis)
         assert np.array_equal(orc.canonical(vf), orc.canonical(ref["vf"]))
         assert np.array_equal(orc.canonical(ee), orc.canonical(ref["ee"]))
+
+
+@pytest.mark.parametrize("max_cells", [1, 2, 7, 64, 0])
+def test_cell_grid_does_not_change_the_overlap_set(sccd, orc, scene_c1, max_cells):
+    """(y, z) cell striping only prunes candidates: same set for any grid, no duplicates even
+    though boxes are replicated into every cell they touch."""
+    c = sccd.Context(0)
+    c.set_grid_cells(max_cells)
+    s = scene_c1
+    c.upload_mesh(s["V0"], s["V1"], s["E"], s["F"])
+    c.build_boxes(2e-3)
+    vf, ee = c.broad_phase(0), c.broad_phase(1)
+    st = c.stats()
+    c.close()
+    vb, eb, fb = orc.build_boxes(s, 2e-3)
+    ovf = orc.sort_and_sweep_two_lists(vb, fb, 0)[0]
+    oee = orc.sort_and_sweep(eb, 0)[0]
+    assert len(vf) == len(ovf) and len(ee) == len(oee)
+    assert np.array_equal(orc.canonical(vf), orc.canonical(ovf))
+    assert np.array_equal(orc.canonical(ee), orc.canonical(oee))
+    cells = [a * b for a, b in st["grid_cells"]]
+    if max_cells == 1:
+        assert cells == [1, 1] and st["n_records"] == st["n_boxes"]
+    elif max_cells == 0:
+        assert min(cells) > 16 and st["n_records"][0] <= 2 * st["n_boxes"][0] + 1024
+    else:
+        assert max(cells) <= max_cells
