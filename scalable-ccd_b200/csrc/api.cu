@@ -92,10 +92,9 @@ struct sccd_ctx {
     int* h_small = nullptr; // pinned scratch for tiny D2H results
 
     // narrow-phase state
-    DevBuf b_counters, b_queue, b_toi_q, b_checks_q, b_queries;
+    DevBuf b_counters, b_queue, b_qheads, b_pend, b_toi_q, b_checks_q, b_queries;
     NarrowCounters* h_counters = nullptr; // pinned
-    unsigned long long q_ticket = 0;
-    long long queue_items = 0;
+    long long queue_items = 0; // ring capacity per CTA
 
     sccd_stats stats {};
     LaunchCounter lc;
@@ -634,13 +633,18 @@ void narrow_setup(sccd_ctx* c)
     if (!c->h_counters)
         SCCD_CUDA(cudaMallocHost((void**)&c->h_counters, sizeof(NarrowCounters)));
     c->b_counters.reserve(sizeof(NarrowCounters));
-    const long long lanes = 2ll * c->num_sms * 256;
-    long long cap = c->queue_cap > 0 ? c->queue_cap : 8 * lanes;
-    cap = std::max(cap, 4 * lanes);
-    if (cap != c->queue_items || !c->b_queue.ptr) {
-        c->b_queue.reserve((size_t)cap * sizeof(WorkItem));
-        SCCD_CUDA(cudaMemsetAsync(c->b_queue.ptr, 0, (size_t)cap * sizeof(WorkItem), c->stream));
-        c->queue_items = cap;
+    // one bounded ring per CTA of the persistent kernel; sccd_set_queue_capacity gives the
+    // TOTAL number of items (MemoryHandler::MAX_UNIT_SIZE analogue)
+    const int grid = narrow_grid_size(c->num_sms);
+    long long per = c->queue_cap > 0 ? (c->queue_cap + grid - 1) / grid : 1024;
+    per = std::min<long long>(std::max<long long>(per, 64), 1 << 16);
+    if (per != c->queue_items || !c->b_queue.ptr) {
+        const size_t bytes = (size_t)per * grid * sizeof(WorkItem);
+        c->b_queue.reserve(bytes);
+        SCCD_CUDA(cudaMemsetAsync(c->b_queue.ptr, 0, bytes, c->stream));
+        c->b_qheads.reserve((size_t)grid * sizeof(CtaQueue));
+        SCCD_CUDA(cudaMemsetAsync(c->b_qheads.ptr, 0, (size_t)grid * sizeof(CtaQueue), c->stream));
+        c->queue_items = per;
     }
 }
 
@@ -672,8 +676,7 @@ void narrow_run(
 
     NarrowCounters init {};
     init.next_query = 0;
-    init.q_tail = init.q_head = c->q_ticket; // tickets never repeat across launches
-    init.outstanding = 0;
+    init.done = 0;
     init.toi = *toi_inout;
     *c->h_counters = init;
     SCCD_CUDA(cudaMemcpyAsync(
@@ -686,17 +689,18 @@ void narrow_run(
         checks = (unsigned int*)c->b_checks_q.reserve((size_t)in.n * 4);
         SCCD_CUDA(cudaMemsetAsync(checks, 0, (size_t)in.n * 4, c->stream));
     }
+    unsigned int* pend = (unsigned int*)c->b_pend.reserve((size_t)in.n * 4);
     const size_t kt = kt_begin(c, &c->stats.ms_k_narrow[kind]);
     launch_narrow_phase(
-        kind == SCCD_VF, in, P, c->b_counters.as<NarrowCounters>(), c->b_queue.as<WorkItem>(),
-        c->queue_items, d_toi_per_query, checks, c->num_sms, c->stream, c->lc);
+        kind == SCCD_VF, in, P, c->b_counters.as<NarrowCounters>(), c->b_qheads.as<CtaQueue>(),
+        c->b_queue.as<WorkItem>(), (int)c->queue_items, pend, d_toi_per_query, checks,
+        c->num_sms, c->stream, c->lc);
     kt_end(c, kt);
     SCCD_CUDA(cudaMemcpyAsync(
         c->h_counters, c->b_counters.ptr, sizeof(NarrowCounters), cudaMemcpyDeviceToHost,
         c->stream));
     SCCD_CUDA(cudaStreamSynchronize(c->stream));
     const NarrowCounters& r = *c->h_counters;
-    c->q_ticket = r.q_tail;
     c->stats.n_box_checks[kind] += (int64_t)r.box_checks;
     c->stats.n_donated[kind] += (int64_t)r.donated;
     c->stats.n_capped[kind] += (int64_t)r.capped;

@@ -186,15 +186,19 @@ static_assert(sizeof(WorkItem) == 64, "WorkItem");
 // read queue behind thousands of polls.
 struct alignas(128) NarrowCounters {
     alignas(128) unsigned long long next_query; // next unclaimed query index
-    alignas(128) unsigned long long q_tail;     // tickets reserved by producers
-    alignas(128) unsigned long long q_head;     // tickets reserved by consumers
-    alignas(128) long long outstanding;         // sub-trees alive (claimed or queued)
-    alignas(128) int hungry;                    // lanes with nothing to do
+    alignas(128) unsigned long long done;       // queries completely solved
     alignas(128) double toi;                    // shared earliest toi
-    alignas(128) int overflow;                  // a donation was refused (queue full)
+    alignas(128) int overflow;                  // a donation was refused (ring full)
     unsigned long long box_checks;
     unsigned long long donated;
     unsigned long long capped;
+};
+
+// One bounded ring of donated sub-boxes per CTA; tickets never repeat (the words persist
+// across launches), head == tail whenever no kernel is running.
+struct alignas(128) CtaQueue {
+    alignas(128) unsigned long long tail; // tickets reserved by producers (any CTA)
+    alignas(128) unsigned long long head; // tickets reserved by consumers (this CTA)
 };
 
 // ---- kernel launchers (defined in the .cu files) -----------------------------------
@@ -266,10 +270,12 @@ struct NarrowInput {
     const double* queries = nullptr;
     long long n = 0;
 };
+int narrow_grid_size(int num_sms); // CTAs (= rings) of the persistent narrow-phase kernel
+// pend: one uint32 per query (scratch, no initialisation needed)
 void launch_narrow_phase(
     bool is_vf, const NarrowInput& in, const NarrowParams& p, NarrowCounters* counters,
-    WorkItem* queue, long long queue_cap, double* toi_per_query, unsigned int* checks_per_query,
-    int num_sms, cudaStream_t s, LaunchCounter& lc);
+    CtaQueue* queues, WorkItem* rings, int ring_cap, unsigned int* pend, double* toi_per_query,
+    unsigned int* checks_per_query, int num_sms, cudaStream_t s, LaunchCounter& lc);
 void launch_fill_f64(double* p, long long n, double v, cudaStream_t s, LaunchCounter& lc);
 // compacts (pair, toi) of queries with toi < 1 ; *d_count receives the number
 void launch_compact_collisions(
