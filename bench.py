@@ -191,13 +191,17 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--workload", default=None,
+                    help="c1|c2|c3|c4|small; default: c2 on one GPU (config 2, the scene the "
+                         "metric is quoted on), c4 (config 4, ~50M AABBs) on several")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload is None:
+        args.workload = "c2" if max(world, args.gpus) == 1 else "c4"
     if args.impl == "reference":
         return run_reference(args, rank, world)
     args.warmup = max(args.warmup, 3)
@@ -269,7 +273,22 @@ def main():
             ms = float(t.item())
         return ms, toi, stats, clocks
 
+    single_ms = None
+    if world > 1:
+        # the same scene on ONE GPU (every rank, unsharded, untimed except on rank 0) so the
+        # line carries its own strong-scaling reference
+        single = ctx.ccd(**PARAMS)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            ctx.ccd(**PARAMS)
+        torch.cuda.synchronize()
+        single_ms = (time.perf_counter() - t0) / 2 * 1e3
+        sharded = sccd.multigpu.ShardedCCD(ctx)   # re-arm the shard after the unsharded runs
+        barrier()
     ms, toi, stats, clocks = timed(step_resident, args.steps, args.warmup, sampler=True)
+    if world > 1:
+        assert toi == single, ("sharded TOI differs from the single-GPU TOI", toi, single)
     e2e_ms, toi2, _, _ = timed(step_e2e, args.steps, 1)
     assert toi == toi2, (toi, toi2)
 
@@ -344,7 +363,9 @@ def main():
         "gpu_launches": int(avg("n_launches")) * args.steps,
         "roofline": roofline,
         "toi": toi, "n_pairs": n_pairs,
-        "pairs_per_rank": (sharded.last if sharded else None), "n_prefilter_survivors": n_cand, "n_box_checks": n_checks,
+        "pairs_per_rank": (sharded.last if sharded else None),
+        "single_gpu_ms_same_workload": single_ms,
+        "speedup_vs_single_gpu": (single_ms / ms if single_ms else None), "n_prefilter_survivors": n_cand, "n_box_checks": n_checks,
         "narrow_queries_per_s": (sum(n_pairs) / (narrow_ms * 1e-3)) if narrow_ms > 0 else None,
         "narrow_box_checks_per_s": (sum(n_checks) / (narrow_ms * 1e-3)) if narrow_ms > 0 else None,
         "narrow_fp64_instr_per_s": (fp64_instr / (narrow_ms * 1e-3)) if narrow_ms > 0 else None,

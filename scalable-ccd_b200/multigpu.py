@@ -86,13 +86,13 @@ class ShardedCCD:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.rebalance_pairs = rebalance_pairs and self.world > 1
-        ctx.set_shard(self.rank, self.world)
         self.last = {}
 
     def ccd(self, ms=0.0, max_iter=-1, tol=1e-6, allow_zero_toi=True) -> float:
         import torch
         ctx = self.ctx
         dev = torch.device("cuda", ctx.device)
+        ctx.set_shard(self.rank, self.world)
         ctx.build_boxes(ms)
         toi = 1.0
         info = {"pairs_local": [], "pairs_after": []}
@@ -118,4 +118,5 @@ class ShardedCCD:
             if self.world > 1:   # the next pass prunes with the global bound
                 toi = allreduce_min(toi, dev, self.group)
         self.last = info
+        ctx.set_shard(0, 1)
         return toi

@@ -37,6 +37,7 @@ for reb in (True, False):
     out[f"ms_rebalance_{reb}"] = (time.perf_counter() - t) / 5 * 1e3
     out[f"pairs_{reb}"] = sh.last
 if full is not None:
+    ctx.set_shard(rank, world)
     for k in (0, 1):
         mine = torch.from_numpy(ctx.broad_phase(k)).cuda()      # this rank's shard
         sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
