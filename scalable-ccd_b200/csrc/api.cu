@@ -584,6 +584,8 @@ void broad_phase_partial(sccd_ctx* c, const sccd_pair** d_pairs, int64_t* n_pair
     unsigned long long budget;
     if (c->max_pairs_per_chunk > 0)
         budget = (unsigned long long)c->max_pairs_per_chunk;
+    else if (remaining * 32ull <= (256ull << 20) && !c->memory_limit)
+        budget = remaining; // small batch: skip cudaMemGetInfo (it costs ~1 ms per call)
     else // pair (8 B) + per-query narrow-phase state; MemoryHandler::per_overlap_memory_size
         budget = std::max<size_t>(budget_bytes(c) + c->b_pairs.cap, 1 << 20) / 32;
     int end = c->shard_hi;

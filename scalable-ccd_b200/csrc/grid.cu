@@ -65,12 +65,12 @@ __global__ void __launch_bounds__(kThreads)
     }
 }
 
+// one warp; fixed reduction tree => deterministic sums
 __global__ void box_stats_final_kernel(const double* __restrict__ partials, int blocks, double* out)
 {
-    if (threadIdx.x != 0)
-        return;
+    const int lane = threadIdx.x;
     double r[6] = { DBL_MAX, -DBL_MAX, DBL_MAX, -DBL_MAX, 0.0, 0.0 };
-    for (int b = 0; b < blocks; b++) { // fixed order: deterministic sums
+    for (int b = lane; b < blocks; b += 32) {
         r[0] = fmin(r[0], partials[b * 6 + 0]);
         r[1] = fmax(r[1], partials[b * 6 + 1]);
         r[2] = fmin(r[2], partials[b * 6 + 2]);
@@ -78,8 +78,18 @@ __global__ void box_stats_final_kernel(const double* __restrict__ partials, int 
         r[4] += partials[b * 6 + 4];
         r[5] += partials[b * 6 + 5];
     }
-    for (int k = 0; k < 6; k++)
-        out[k] = r[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        r[0] = fmin(r[0], __shfl_xor_sync(0xffffffffu, r[0], o));
+        r[1] = fmax(r[1], __shfl_xor_sync(0xffffffffu, r[1], o));
+        r[2] = fmin(r[2], __shfl_xor_sync(0xffffffffu, r[2], o));
+        r[3] = fmax(r[3], __shfl_xor_sync(0xffffffffu, r[3], o));
+        r[4] += __shfl_xor_sync(0xffffffffu, r[4], o);
+        r[5] += __shfl_xor_sync(0xffffffffu, r[5], o);
+    }
+    if (lane == 0)
+        for (int k = 0; k < 6; k++)
+            out[k] = r[k];
 }
 
 __device__ __forceinline__ void cell_range(

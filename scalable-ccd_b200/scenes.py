@@ -170,17 +170,36 @@ def blob_pile(n_inst: int, seed: int, slab: bool = False, radius: float = 0.05,
 
     n_core = int(0.8 * n_inst)
     n_tail = n_inst - n_core
-    # core radius so that mean centre spacing ~ spacing * radius
-    vol = n_core * (spacing * radius) ** 3
-    sigma = (vol / (4.0 / 3.0 * np.pi)) ** (1.0 / 3.0) / 2.0
-    core = rng.normal(size=(n_core, 3)) * sigma
-    d = rng.normal(size=(n_tail, 3))
-    d /= np.linalg.norm(d, axis=1, keepdims=True)
-    rad = 2.0 * sigma * (1.0 + rng.pareto(2.5, size=(n_tail, 1)))
-    tail = d * rad
-    C = np.concatenate([core, tail], axis=0)
-    if slab:
-        C[:, 0] *= 12.0
+    # Centres sit on jittered cubic lattices so that NO two blobs touch at t0 (a blob's
+    # extent is at most 1.25 * radius; an initial interpenetration would make toi = 0 and
+    # the narrow phase trivial): the dense core on a lattice of `spacing` radii -- the
+    # lattice points closest to the origin, an ellipsoid 12:1:1 for the slab -- and the
+    # sparse shell on a 3x coarser lattice with Pareto-distributed radii.
+    stretch = np.array([12.0 if slab else 1.0, 1.0, 1.0])
+
+    def lattice(n, h, r_min):
+        k = int(np.ceil((2.0 * n / stretch[0]) ** (1.0 / 3.0))) + 2
+        gx = np.arange(-int(k * stretch[0]), int(k * stretch[0]) + 1)
+        gy = np.arange(-k, k + 1)
+        X, Y, Z = np.meshgrid(gx, gy, gy, indexing="ij")
+        pts = np.stack([X.ravel(), Y.ravel(), Z.ravel()], 1).astype(np.float64) * h
+        r = np.linalg.norm(pts / stretch, axis=1)
+        pts, r = pts[r >= r_min], r[r >= r_min]
+        return pts[np.argsort(r, kind="stable")[:n]]
+
+    h = spacing * radius
+    core = lattice(n_core, h, 0.0)
+    r_core = np.linalg.norm(core / stretch, axis=1).max() + 2.0 * h
+    shell = lattice(8 * n_tail, 3.0 * h, r_core)
+    # heavy tail: keep shell sites with probability falling off like a Pareto law
+    rs = np.linalg.norm(shell / stretch, axis=1)
+    keep = rng.random(len(shell)) < (r_core / rs) ** 2.5
+    shell = shell[keep][:n_tail]
+    if len(shell) < n_tail:  # not enough accepted sites: top up with the nearest rejected ones
+        extra = lattice(8 * n_tail, 3.0 * h, r_core)[: n_tail - len(shell)]
+        shell = np.concatenate([shell, extra + 1.5 * h], axis=0)
+    C = np.concatenate([core, shell], axis=0)
+    C += rng.uniform(-0.04, 0.04, C.shape) * radius
     C = C[rng.permutation(n_inst)]
     R = _random_rotations(rng, n_inst)
     P = np.einsum("nij,vj->nvi", R, Vb * radius) + C[:, None, :]
