@@ -239,11 +239,15 @@ def main():
     # pinned host copies for the end-to-end arm
     pinned = {k: torch.from_numpy(np.ascontiguousarray(v.T)).pin_memory() for k, v in scene.items()}
 
+    packed = sccd.multigpu.pack_mesh(scene["V0"], scene["V1"], scene["E"], scene["F"], world) \
+        if world > 1 else None
+
     def step_e2e():
         if world > 1:
+            # every rank copies 1/world of the host mesh over its own PCIe link; the slices
+            # are all-gathered over NVLink (multigpu.gather_mesh)
             ctx.reset_stats()
-            ctx.upload_mesh(pinned["V0"].data_ptr(), pinned["V1"].data_ptr(), pinned["E"].data_ptr(),
-                            pinned["F"].data_ptr(), sizes=(nV, nE, nF), host=True)
+            sharded.upload_mesh_host(packed[0], packed[1], (nV, nE, nF))
             return sharded.ccd(**PARAMS)
         return ctx.ccd_host(pinned["V0"].data_ptr(), pinned["V1"].data_ptr(), pinned["E"].data_ptr(),
                             pinned["F"].data_ptr(), sizes=(nV, nE, nF), **PARAMS)
@@ -287,8 +291,16 @@ def main():
         sharded = sccd.multigpu.ShardedCCD(ctx)   # re-arm the shard after the unsharded runs
         barrier()
     ms, toi, stats, clocks = timed(step_resident, args.steps, args.warmup, sampler=True)
+    rank_stage_ms = None
     if world > 1:
         assert toi == single, ("sharded TOI differs from the single-GPU TOI", toi, single)
+        sharded.profile = True            # one extra untimed step with per-stage events
+        step_resident()
+        sharded.profile = False
+        rank_stage_ms = sharded.last.pop("ms", None)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, rank_stage_ms)
+        rank_stage_ms = gathered
     e2e_ms, toi2, _, _ = timed(step_e2e, args.steps, 1)
     assert toi == toi2, (toi, toi2)
 
@@ -356,14 +368,17 @@ def main():
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": desc, "n_vertices": nV, "n_edges": nE, "n_faces": nF,
                    "l2": "256 MiB device write between timed steps (flush)", **PARAMS,
-                   "parallelism": f"owner-range shards x{world}" if world > 1 else "single GPU"},
+                   "parallelism": f"cell-range shards x{world}" if world > 1 else "single GPU"},
         "clocks": clocks,
         "e2e": {"value": e2e_ms, "unit": UNIT,
-                "h2d_bytes_per_step": 2 * 24 * nV + 8 * nE + 12 * nF, "d2h_bytes_per_step": 8},
+                "h2d_bytes_per_step": 2 * 24 * nV + 8 * nE + 12 * nF, "d2h_bytes_per_step": 8,
+                "note": ("whole job: each rank copies 1/N of the mesh H2D, NCCL all-gather of the "
+                         "slices" if world > 1 else "pinned host mesh -> sccd_ccd_host")},
         "gpu_launches": int(avg("n_launches")) * args.steps,
         "roofline": roofline,
         "toi": toi, "n_pairs": n_pairs,
         "pairs_per_rank": (sharded.last if sharded else None),
+        "stage_ms_per_rank": rank_stage_ms,
         "single_gpu_ms_same_workload": single_ms,
         "speedup_vs_single_gpu": (single_ms / ms if single_ms else None), "n_prefilter_survivors": n_cand, "n_box_checks": n_checks,
         "narrow_queries_per_s": (sum(n_pairs) / (narrow_ms * 1e-3)) if narrow_ms > 0 else None,

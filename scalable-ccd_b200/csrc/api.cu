@@ -78,11 +78,25 @@ struct sccd_ctx {
         SortedList sorted;
         BoxArrays unsorted;
         int n_boxes = 0;
+        int built_rank = 0, built_world = 1; // sharding the sorted records were made for
+        // sort_list_begin -> sort_list_finish hand-over
+        GridParams g_try;
+        bool try_sharded = false;
+        int try_stride = 1, attempt = 0;
     } lists[3]; // [2] = caller-made boxes (sccd_set_boxes)
     bool have_custom = false;
-    DevBuf b_sort_temp, b_stats;
-    double* h_stats = nullptr; // pinned
+    DevBuf b_sort_temp, b_stats, b_hist, b_splits;
+    // pinned: per list, box statistics + record count + multi-GPU cell splits
+    struct ListHost {
+        double stats[kNumStats];
+        unsigned long long m;
+        unsigned long long splits[2 * 16 + 2];
+    };
+    ListHost* h_lists = nullptr; // [3]
     int grid_max_cells = -1;   // < 0: choose automatically; 1 forces the plain 1-axis sweep
+    // tuning knobs (env SCCD_GRID_SCALE / SCCD_GRID_REPL): cell edge in mean box extents, and
+    // the replication (records per box) above which the grid is coarsened
+    double grid_scale = 3.0, grid_repl = 2.5;
 
     // broad-phase state
     int bp_kind = -1;
@@ -112,8 +126,8 @@ struct sccd_ctx {
     {
         if (h_small)
             cudaFreeHost(h_small);
-        if (h_stats)
-            cudaFreeHost(h_stats);
+        if (h_lists)
+            cudaFreeHost(h_lists);
         if (h_counters)
             cudaFreeHost(h_counters);
         for (auto& e : ev)
@@ -264,7 +278,7 @@ void prepare_list(sccd_ctx* c, int which, int n, bool two_lists)
 
 // Choose the (y, z) cell grid of a list from its box statistics: cells about twice the mean
 // box extent (so a box touches ~1.5 cells per axis), at most 1024 per axis / 2^20 in total.
-GridParams choose_grid(const double st[6], int n, int max_cells)
+GridParams choose_grid(const double st[6], int n, int max_cells, double scale)
 {
     GridParams g;
     if (n <= 0 || max_cells == 1)
@@ -275,7 +289,7 @@ GridParams choose_grid(const double st[6], int n, int max_cells)
     for (int a = 0; a < 2; a++) {
         if (!(ext[a] > 0) || !(mean[a] >= 0) || !std::isfinite(ext[a]))
             continue;
-        const double cell = std::max(2.0 * mean[a], ext[a] / 1024.0);
+        const double cell = std::max(scale * mean[a], ext[a] / 1024.0);
         const double k = cell > 0 ? std::floor(ext[a] / cell) : 1.0;
         s[a] = (int)std::min(1024.0, std::max(1.0, k));
     }
@@ -297,74 +311,178 @@ GridParams choose_grid(const double st[6], int n, int max_cells)
 
 // DeviceAABBs constructor + BroadPhase::build of the reference, for one list whose unsorted
 // exact records are on the device: grid choice, replication into cells, radix sort, gather.
-// Two small host syncs (statistics, record total).
-void sort_list(sccd_ctx* c, int which, cudaEvent_t ga, cudaEvent_t gb)
+//
+// Split in phases so that both mesh lists share their host synchronisations:
+//   list_stats()       (caller-made boxes only; mesh lists get theirs from the box kernels)
+//   sort_list_begin()  host: grid from the statistics; device: records per box (+ multi-GPU
+//                      cell ranges), results on their way to pinned host memory
+//   -- one stream sync --
+//   sort_list_finish() host: accept the grid (or coarsen and retry); device: keys, radix sort,
+//                      gather.
+sccd_ctx::ListHost& list_host(sccd_ctx* c, int which)
+{
+    if (!c->h_lists)
+        SCCD_CUDA(cudaMallocHost((void**)&c->h_lists, 3 * sizeof(sccd_ctx::ListHost)));
+    return c->h_lists[which];
+}
+
+void regrid(GridParams& g, const double st[kNumStats])
+{
+    g.inv_hy = g.sy > 1 ? g.sy / (st[1] - st[0]) : 0.0;
+    g.inv_hz = g.sz > 1 ? g.sz / (st[3] - st[2]) : 0.0;
+}
+
+// enqueue the record count of grid L.g_try (and, multi-GPU, this rank's cell range)
+void sort_list_count(sccd_ctx* c, int which)
 {
     auto& L = c->lists[which];
+    auto& H = list_host(c, which);
+    const int n = L.n_boxes;
+    const GridParams& g = L.g_try;
+    const long long cells = (long long)g.sy * g.sz;
+    L.try_sharded = false;
+    if (cells == 1) { // plain 1-axis sweep: one record per box, nothing to ask the device
+        H.m = (unsigned long long)n;
+        SCCD_CUDA(cudaMemsetAsync(L.copies.as<uint32_t>() + n, 0, 4, c->stream));
+        launch_expand_count(L.unsorted, n, g, nullptr, L.copies.as<uint32_t>(), c->stream, c->lc);
+        launch_scan_u32_to_u64(
+            L.copies.as<uint32_t>(), L.offs.as<unsigned long long>(), n, c->b_scan_temp.ptr,
+            c->b_scan_temp.cap, c->stream, c->lc);
+        return;
+    }
+    const unsigned long long* d_range = nullptr;
+    if (c->world > 1 && cells >= 8ll * c->world) {
+        // Multi-GPU: this rank makes, sorts and sweeps only the records of its own contiguous
+        // cell range (cells are independent sweep domains).  Every rank derives the same
+        // ranges from its replica of the boxes -- no exchange.
+        const int W = c->world;
+        L.try_stride = (int)std::min<long long>(16, std::max<long long>(1, n / (cells * 64)));
+        // shared by the lists (stream order keeps them apart): sized for the largest grid
+        uint32_t* hist = (uint32_t*)c->b_hist.reserve(std::max<size_t>((size_t)cells * 4, 4u << 20));
+        // one split record per list: the two lists are in flight together
+        unsigned long long* d_out =
+            (unsigned long long*)c->b_splits.reserve((size_t)3 * (2 * 16 + 2) * 8)
+            + (size_t)which * (2 * 16 + 2);
+        launch_cell_splits(L.unsorted, n, L.try_stride, g, W, hist, d_out, c->stream, c->lc);
+        SCCD_CUDA(cudaMemcpyAsync(
+            H.splits, d_out, (size_t)(2 * W + 2) * 8, cudaMemcpyDeviceToHost, c->stream));
+        d_range = d_out + c->rank;
+        L.try_sharded = true;
+    }
+    SCCD_CUDA(cudaMemsetAsync(L.copies.as<uint32_t>() + n, 0, 4, c->stream));
+    launch_expand_count(L.unsorted, n, g, d_range, L.copies.as<uint32_t>(), c->stream, c->lc);
+    launch_scan_u32_to_u64(
+        L.copies.as<uint32_t>(), L.offs.as<unsigned long long>(), n, c->b_scan_temp.ptr,
+        c->b_scan_temp.cap, c->stream, c->lc);
+    SCCD_CUDA(cudaMemcpyAsync(
+        &H.m, L.offs.as<unsigned long long>() + n, 8, cudaMemcpyDeviceToHost, c->stream));
+}
+
+// enqueue the statistics of a list towards list_host(c, which).stats (no sync)
+void list_stats(sccd_ctx* c, int which)
+{
+    auto& L = c->lists[which];
+    auto& H = list_host(c, which);
+    if (L.n_boxes <= 0)
+        return;
+    // one partials + result region per list: the lists are in flight together
+    const size_t per = (size_t)(kStatsBlocks + 1) * kNumStats;
+    double* base = (double*)c->b_stats.reserve(3 * per * sizeof(double)) + which * per;
+    double* d_stats = base + kStatsBlocks * kNumStats;
+    const int stride = std::min(16, std::max(1, L.n_boxes >> 18));
+    launch_box_stats(L.unsorted, L.n_boxes, stride, base, d_stats, c->stream, c->lc);
+    SCCD_CUDA(cudaMemcpyAsync(
+        H.stats, d_stats, kNumStats * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+}
+
+// requires the list's statistics in list_host(c, which).stats
+void sort_list_begin(sccd_ctx* c, int which)
+{
+    auto& L = c->lists[which];
+    auto& H = list_host(c, which);
+    const int n = L.n_boxes;
+    L.built_rank = c->rank;
+    L.built_world = c->world;
+    L.attempt = 0;
+    if (n <= 0)
+        return;
+    L.g_try = choose_grid(H.stats, n, c->grid_max_cells, c->grid_scale);
+    L.copies.reserve(((size_t)n + 1) * 4);
+    L.offs.reserve(((size_t)n + 1) * 8);
+    c->b_scan_temp.reserve(scan_temp_bytes(n));
+    sort_list_count(c, which);
+}
+
+void sort_list_finish(sccd_ctx* c, int which, cudaEvent_t ga, cudaEvent_t gb)
+{
+    auto& L = c->lists[which];
+    auto& H = list_host(c, which);
     const int n = L.n_boxes;
     if (n <= 0) {
         L.sorted.n = 0;
         L.sorted.grid = GridParams();
+        L.sorted.cell_sharded = false;
         if (ga)
             SCCD_CUDA(cudaEventRecord(ga, c->stream));
         if (gb)
             SCCD_CUDA(cudaEventRecord(gb, c->stream));
         return;
     }
-    if (!c->h_stats)
-        SCCD_CUDA(cudaMallocHost((void**)&c->h_stats, 64));
-    c->b_stats.reserve((size_t)(kStatsBlocks * 6 + 8) * sizeof(double));
-    double* d_stats = c->b_stats.as<double>() + kStatsBlocks * 6;
-    launch_box_stats(L.unsorted, n, c->b_stats.as<double>(), d_stats, c->stream, c->lc);
-    SCCD_CUDA(cudaMemcpyAsync(c->h_stats, d_stats, 48, cudaMemcpyDeviceToHost, c->stream));
-    SCCD_CUDA(cudaStreamSynchronize(c->stream));
-    GridParams g = choose_grid(c->h_stats, n, c->grid_max_cells);
-
-    L.copies.reserve(((size_t)n + 1) * 4);
-    L.offs.reserve(((size_t)n + 1) * 8);
-    c->b_scan_temp.reserve(scan_temp_bytes(n));
-    unsigned long long m = (unsigned long long)n;
-    for (int attempt = 0;; attempt++) {
-        if (g.sy * g.sz == 1) {
-            m = (unsigned long long)n;
+    // replication bound: a few huge boxes can touch every cell -- coarsen until it is modest
+    const unsigned long long m_cap = (unsigned long long)(c->grid_repl * n) + 1024;
+    GridParams g = L.g_try;
+    unsigned long long m = 0, m_total = 0;
+    for (;;) {
+        g = L.g_try;
+        m = H.m;
+        m_total = m;
+        if (L.try_sharded) // estimate (exact for stride 1) of the records of ALL ranks
+            m_total = H.splits[c->world + 1] * (unsigned long long)L.try_stride;
+        if ((long long)g.sy * g.sz == 1 || m_total <= m_cap)
             break;
+        if (++L.attempt > 12) // give up on the grid rather than explode memory
+            L.g_try = GridParams();
+        else {
+            if (L.g_try.sy >= L.g_try.sz)
+                L.g_try.sy = (L.g_try.sy + 1) / 2;
+            else
+                L.g_try.sz = (L.g_try.sz + 1) / 2;
+            regrid(L.g_try, H.stats);
         }
-        SCCD_CUDA(cudaMemsetAsync(L.copies.as<uint32_t>() + n, 0, 4, c->stream));
-        launch_expand_count(L.unsorted, n, g, L.copies.as<uint32_t>(), c->stream, c->lc);
-        launch_scan_u32_to_u64(
-            L.copies.as<uint32_t>(), L.offs.as<unsigned long long>(), n, c->b_scan_temp.ptr,
-            c->b_scan_temp.cap, c->stream, c->lc);
-        SCCD_CUDA(cudaMemcpyAsync(
-            c->h_stats + 6, L.offs.as<unsigned long long>() + n, 8, cudaMemcpyDeviceToHost,
-            c->stream));
+        sort_list_count(c, which);
         SCCD_CUDA(cudaStreamSynchronize(c->stream));
-        m = *reinterpret_cast<unsigned long long*>(c->h_stats + 6);
-        // a few huge boxes can touch every cell: coarsen until replication is modest
-        if (m <= 2ull * n + 1024 || attempt >= 12)
-            break;
-        if (g.sy >= g.sz)
-            g.sy = (g.sy + 1) / 2;
-        else
-            g.sz = (g.sz + 1) / 2;
-        g.inv_hy = g.sy > 1 ? g.sy / (c->h_stats[1] - c->h_stats[0]) : 0.0;
-        g.inv_hz = g.sz > 1 ? g.sz / (c->h_stats[3] - c->h_stats[2]) : 0.0;
     }
-    if (m > 2ull * n + 1024) { // give up on the grid rather than explode memory
-        g = GridParams();
-        m = (unsigned long long)n;
+    const bool sharded = L.try_sharded && (long long)g.sy * g.sz > 1;
+    if (sharded) {
+        g.cell_lo = (int)H.splits[c->rank];
+        g.cell_hi = (int)H.splits[c->rank + 1];
     }
+    L.sorted.cell_sharded = sharded;
     if (m >= (1ull << 27))
         throw std::invalid_argument("more than 2^27 sweep records in one list");
-    if (g.sy * g.sz == 1) { // plain 1-axis sweep: identity expansion
-        SCCD_CUDA(cudaMemsetAsync(L.copies.as<uint32_t>() + n, 0, 4, c->stream));
-        launch_expand_count(L.unsorted, n, g, L.copies.as<uint32_t>(), c->stream, c->lc);
-        launch_scan_u32_to_u64(
-            L.copies.as<uint32_t>(), L.offs.as<unsigned long long>(), n, c->b_scan_temp.ptr,
-            c->b_scan_temp.cap, c->stream, c->lc);
+    // 32-bit key = [cell | q(x) | 3 flag bits] (common.cuh).  x gets as many bits as the digit
+    // passes needed for ~32 quantisation steps per record of an average cell leave room for.
+    int cell_bits = 0;
+    while ((1ll << cell_bits) < (long long)g.sy * g.sz)
+        cell_bits++;
+    {
+        const int x_max = 32 - kKeyFlagBits - cell_bits;
+        const double per_cell = (double)m_total / (double)((long long)g.sy * g.sz);
+        int want = 5;
+        while (want < x_max && (double)(1ll << (want - 5)) < per_cell)
+            want++;
+        want = std::min(std::max(want, 9), x_max);
+        const int passes = (cell_bits + want + 7) / 8;
+        g.x_bits = std::min(x_max, passes * 8 - cell_bits);
+        const double ext = H.stats[7] - H.stats[6];
+        g.x0 = H.stats[6];
+        g.inv_hx = (ext > 0 && std::isfinite(ext)) ? std::ldexp(1.0, g.x_bits) / ext : 0.0;
+        if (!std::isfinite(g.inv_hx))
+            g.inv_hx = 0.0;
     }
     const size_t mm = (size_t)m;
-    L.keys.reserve(mm * 8);
-    L.keys_tmp.reserve(mm * 8);
+    L.keys.reserve(mm * 4);
+    L.keys_tmp.reserve(mm * 4);
     L.idx.reserve(mm * 4);
     L.idx_out.reserve(mm * 4);
     L.sorted.n = (int)m;
@@ -372,20 +490,27 @@ void sort_list(sccd_ctx* c, int which, cudaEvent_t ga, cudaEvent_t gb)
     L.sorted.box.x = (double2*)L.sx.reserve(mm * sizeof(double2));
     L.sorted.box.yz = (double4*)L.syz.reserve(mm * sizeof(double4));
     L.sorted.box.id = (int4*)L.sid.reserve(mm * sizeof(int4));
-    L.sorted.pf.key = (unsigned long long*)L.pkey.reserve(mm * 8);
-    L.sorted.pf.reach = (unsigned long long*)L.preach.reserve(mm * 8);
+    L.sorted.pf.key = (uint32_t*)L.pkey.reserve(mm * 4);
+    L.sorted.pf.reach = (uint32_t*)L.preach.reserve(mm * 4);
     L.sorted.pf.yz = (float4*)L.pyz.reserve(mm * sizeof(float4));
     c->b_sort_temp.reserve(sort_temp_bytes((int)m));
     launch_expand_fill(
-        L.unsorted, n, g, L.offs.as<unsigned long long>(), L.keys.as<unsigned long long>(),
+        L.unsorted, n, g, L.offs.as<unsigned long long>(), L.keys.as<uint32_t>(),
         L.idx.as<uint32_t>(), c->stream, c->lc);
-    int cell_bits = 0;
-    while ((1ll << cell_bits) < (long long)g.sy * g.sz)
-        cell_bits++;
     launch_sort_and_gather(
-        (int)m, 32 + cell_bits, L.keys.as<unsigned long long>(),
-        L.keys_tmp.as<unsigned long long>(), L.idx.as<uint32_t>(), L.idx_out.as<uint32_t>(),
-        c->b_sort_temp.ptr, c->b_sort_temp.cap, L.unsorted, L.sorted, c->stream, c->lc, ga, gb);
+        (int)m, cell_bits + g.x_bits, L.keys.as<uint32_t>(), L.keys_tmp.as<uint32_t>(),
+        L.idx.as<uint32_t>(), L.idx_out.as<uint32_t>(), c->b_sort_temp.ptr, c->b_sort_temp.cap,
+        L.unsorted, L.sorted, c->stream, c->lc, ga, gb);
+}
+
+// one list on its own (caller-made boxes; re-sharding an already built list)
+void sort_list(sccd_ctx* c, int which, cudaEvent_t ga, cudaEvent_t gb)
+{
+    list_stats(c, which);
+    SCCD_CUDA(cudaStreamSynchronize(c->stream));
+    sort_list_begin(c, which);
+    SCCD_CUDA(cudaStreamSynchronize(c->stream));
+    sort_list_finish(c, which, ga, gb);
 }
 
 void build_boxes(sccd_ctx* c, double inflation_radius)
@@ -406,16 +531,20 @@ void build_boxes(sccd_ctx* c, double inflation_radius)
     auto& LV = c->lists[0];
     auto& LE = c->lists[1];
     const size_t kt_boxes = kt_begin(c, &c->stats.ms_k_boxes);
-    launch_vertex_boxes(
-        c->dV0, c->dV1, nV, radius_up, c->b_vtab.as<VertexRec>(), c->b_vbox.as<double>(),
-        LV.unsorted, c->stream, c->lc);
-    launch_element_boxes(
-        c->b_vbox.as<double>(), c->dE, nE, c->dF, nF, nV, LE.unsorted, LV.unsorted, c->stream,
-        c->lc);
+    launch_mesh_boxes(
+        c->dV0, c->dV1, nV, radius_up, c->b_vtab.as<VertexRec>(), c->b_vbox.as<double>(), c->dE,
+        nE, c->dF, nF, LE.unsorted, LV.unsorted, c->stream, c->lc);
     kt_end(c, kt_boxes);
     record(c, EV_BUILD);
-    sort_list(c, 0, c->ev[EV_GA0], c->ev[EV_GB0]);
-    sort_list(c, 1, c->ev[EV_GA1], c->ev[EV_GB1]);
+    // sync 1: statistics of both lists; sync 2: record counts of both lists
+    list_stats(c, 0);
+    list_stats(c, 1);
+    SCCD_CUDA(cudaStreamSynchronize(c->stream));
+    sort_list_begin(c, 0);
+    sort_list_begin(c, 1);
+    SCCD_CUDA(cudaStreamSynchronize(c->stream));
+    sort_list_finish(c, 0, c->ev[EV_GA0], c->ev[EV_GB0]);
+    sort_list_finish(c, 1, c->ev[EV_GA1], c->ev[EV_GB1]);
     c->gather_timed = true;
     record(c, EV_SORT);
     c->have_boxes = true;
@@ -506,6 +635,8 @@ void broad_phase_begin(sccd_ctx* c, int kind)
         throw std::invalid_argument("broad_phase: kind must be SCCD_VF, SCCD_EE or SCCD_BOXES");
     if (kind == SCCD_BOXES ? !c->have_custom : !c->have_boxes)
         throw std::logic_error("Must initialize build broad phase before detecting overlaps!");
+    if (c->lists[kind].built_rank != c->rank || c->lists[kind].built_world != c->world)
+        sort_list(c, kind, nullptr, nullptr); // sccd_set_shard changed since the list was sorted
     const SortedList& L = c->lists[kind].sorted;
     const int sk = stat_slot(kind);
     small_scratch(c);
@@ -515,8 +646,9 @@ void broad_phase_begin(sccd_ctx* c, int kind)
     c->stats.n_pairs[sk] = 0;
     c->stats.n_candidates[sk] = 0;
     record(c, sk == 0 ? EV_SW0A : EV_SW1A);
-    if (c->world > 1 && L.n > 0) {
-        // balance owner slices by sweep-window length
+    if (c->world > 1 && L.n > 0 && !L.cell_sharded) {
+        // too few cells to shard by cell range: every rank holds the whole sorted list and
+        // sweeps one owner slice of it, slices balanced by sweep-window length
         c->b_counts.reserve(((size_t)L.n + 1) * 4);
         c->b_offsets.reserve(((size_t)L.n + 1) * 8);
         c->b_scan_temp.reserve(scan_temp_bytes(L.n));
@@ -859,6 +991,10 @@ int sccd_create(int device, void* stream, sccd_ctx** out)
         if (prop.major != 10)
             throw CudaError("sccd: this library is built for sm_100a (B200) only");
         c->num_sms = prop.multiProcessorCount;
+        if (const char* e = getenv("SCCD_GRID_SCALE"))
+            c->grid_scale = std::min(64.0, std::max(0.25, atof(e)));
+        if (const char* e = getenv("SCCD_GRID_REPL"))
+            c->grid_repl = std::min(16.0, std::max(1.0, atof(e)));
         for (auto& e : c->ev)
             SCCD_CUDA(cudaEventCreate(&e));
         return SCCD_OK;

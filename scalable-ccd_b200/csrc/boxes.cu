@@ -112,29 +112,23 @@ __global__ void __launch_bounds__(kThreads) element_boxes_kernel(
 
 } // namespace
 
-void launch_vertex_boxes(
-    const double* V0, const double* V1, int nV, double radius_up, VertexRec* vtab,
-    double* vbox, BoxArrays vf_unsorted, cudaStream_t s, LaunchCounter& lc)
+void launch_mesh_boxes(
+    const double* V0, const double* V1, int nV, double radius_up, VertexRec* vtab, double* vbox,
+    const int32_t* E, int nE, const int32_t* F, int nF, BoxArrays e_unsorted,
+    BoxArrays vf_unsorted, cudaStream_t s, LaunchCounter& lc)
 {
-    if (nV <= 0)
-        return;
-    vertex_boxes_kernel<<<(nV + kThreads - 1) / kThreads, kThreads, 0, s>>>(
-        V0, V1, nV, radius_up, vtab, vbox, vf_unsorted);
-    SCCD_CUDA(cudaGetLastError());
-    lc.n++;
-}
-
-void launch_element_boxes(
-    const double* vbox, const int32_t* E, int nE, const int32_t* F, int nF, int nV,
-    BoxArrays e_unsorted, BoxArrays vf_unsorted, cudaStream_t s, LaunchCounter& lc)
-{
-    const int n = nE + nF;
-    if (n <= 0)
-        return;
-    element_boxes_kernel<<<(n + kThreads - 1) / kThreads, kThreads, 0, s>>>(
-        vbox, E, nE, F, nF, nV, e_unsorted, vf_unsorted);
-    SCCD_CUDA(cudaGetLastError());
-    lc.n++;
+    if (nV > 0) {
+        vertex_boxes_kernel<<<(nV + kThreads - 1) / kThreads, kThreads, 0, s>>>(
+            V0, V1, nV, radius_up, vtab, vbox, vf_unsorted);
+        SCCD_CUDA(cudaGetLastError());
+        lc.n++;
+    }
+    if (nE + nF > 0) {
+        element_boxes_kernel<<<(nE + nF + kThreads - 1) / kThreads, kThreads, 0, s>>>(
+            vbox, E, nE, F, nF, nV, e_unsorted, vf_unsorted);
+        SCCD_CUDA(cudaGetLastError());
+        lc.n++;
+    }
 }
 
 } // namespace sccd

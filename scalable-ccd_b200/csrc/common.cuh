@@ -88,6 +88,14 @@ struct BoxArrays {
 struct GridParams {
     double y0 = 0, z0 = 0, inv_hy = 0, inv_hz = 0;
     int sy = 1, sz = 1;
+    // Multi-GPU: only records of linear cells [cell_lo, cell_hi) are made on this rank.  Cells
+    // are independent sweep domains (a pair is reported in its home cell only), so ranks that
+    // own disjoint cell ranges emit disjoint pair lists whose rank-order concatenation is the
+    // single-GPU list -- no halo, no exchange.
+    int cell_lo = 0, cell_hi = 0x7fffffff;
+    // major-axis quantisation of the 32-bit sort key (see sweep_key())
+    double x0 = 0, inv_hx = 0;
+    int x_bits = 29;
 };
 
 __host__ __device__ inline int cell_index(double v, double v0, double inv_h, int s)
@@ -101,13 +109,34 @@ __host__ __device__ inline int cell_index(double v, double v0, double inv_h, int
     return i;
 }
 
-// Prefilter view of the SORTED records: 64-bit sort key = (cell << 32) | key32(f32(xmin)
-// rounded down), reach = (cell << 32) | key32(f32(xmax) rounded up), and the f32 conservative
-// yz = (ymin dn, ymax up, zmin dn, zmax up).  For j after i in sorted order,
-// key[j] <= reach[i]  <=>  same cell and f32(xmin_j) <= f32(xmax_i).
+// 32-bit sweep key of a record:  [ cell | q(x) : x_bits | fy | fz | type ]
+//   q(x)  = monotone quantisation of the major-axis coordinate (floor of an affine map,
+//           clamped), so  xmin_j <= xmax_i  =>  q(xmin_j) <= q(xmax_i): the window test on
+//           keys is a conservative superset of the reference's  min_j <= max_i;
+//   fy/fz = the box STARTS in this cell's row / column.  A record of cell (cy, cz) always has
+//           cy0 <= cy, and cell_index() is monotone, so the home-cell rule
+//           cell(max(ymin_a, ymin_b)) == cy  is exactly  fy_a | fy_b  (same for z): the
+//           duplicate suppression costs two bit operations in the prefilter;
+//   type  = 1 for list A (vertices) of a two-list sweep (collision.cuh:27-35).
+constexpr int kKeyFlagBits = 3;
+constexpr uint32_t kKeyFlagType = 1u, kKeyFlagZ = 2u, kKeyFlagY = 4u;
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t quantize_x(double x, const GridParams& g)
+{
+    const double f = fmax((x - g.x0) * g.inv_hx, 0.0);
+    const uint32_t qmax = g.x_bits >= 32 ? 0xffffffffu : ((1u << g.x_bits) - 1u);
+    const uint32_t q = __double2uint_rd(f); // saturates
+    return q < qmax ? q : qmax;
+}
+#endif
+
+// Prefilter view of the SORTED records: key (above), reach = the same cell with q(xmax) and all
+// flag bits set, and the f32 conservative yz = (ymin dn, ymax up, zmin dn, zmax up).  For j
+// after i in sorted order,  key[j] <= reach[i]  <=>  same cell and q(xmin_j) <= q(xmax_i).
 struct PrefilterArrays {
-    unsigned long long* key = nullptr;
-    unsigned long long* reach = nullptr;
+    uint32_t* key = nullptr;
+    uint32_t* reach = nullptr;
     float4* yz = nullptr;
 };
 
@@ -115,12 +144,65 @@ struct PrefilterArrays {
 struct SortedList {
     int n = 0;
     bool two_lists = false;
+    bool cell_sharded = false; // holds only this rank's cell range (GridParams::cell_lo/hi)
     GridParams grid;
     BoxArrays box;      // sorted, exact
     PrefilterArrays pf; // sorted prefilter view
 };
 
+constexpr int kNumStats = 8;
 #ifdef __CUDACC__
+// Box statistics of a list (grid choice): r[0..7] = {min ymin, max ymax, min zmin, max zmax,
+// sum (ymax-ymin), sum (zmax-zmin), min xmin, max xmax}.  Fixed reduction trees everywhere, so
+// the sums -- and with them the chosen grid -- are deterministic.
+__device__ __forceinline__ void stats_identity(double r[kNumStats])
+{
+    r[0] = 1.7976931348623157e308, r[1] = -1.7976931348623157e308;
+    r[2] = 1.7976931348623157e308, r[3] = -1.7976931348623157e308;
+    r[4] = 0.0, r[5] = 0.0;
+    r[6] = 1.7976931348623157e308, r[7] = -1.7976931348623157e308;
+}
+__device__ __forceinline__ void stats_merge(double r[kNumStats], const double o[kNumStats])
+{
+    r[0] = fmin(r[0], o[0]);
+    r[1] = fmax(r[1], o[1]);
+    r[2] = fmin(r[2], o[2]);
+    r[3] = fmax(r[3], o[3]);
+    r[4] += o[4];
+    r[5] += o[5];
+    r[6] = fmin(r[6], o[6]);
+    r[7] = fmax(r[7], o[7]);
+}
+__device__ __forceinline__ void stats_of_box(
+    double r[kNumStats], const double lo[3], const double hi[3])
+{
+    r[0] = lo[1], r[1] = hi[1], r[2] = lo[2], r[3] = hi[2];
+    r[4] = hi[1] - lo[1], r[5] = hi[2] - lo[2], r[6] = lo[0], r[7] = hi[0];
+}
+// block reduction (blockDim.x = 32 * warps <= 1024); the result is valid on thread 0.
+// red: shared scratch of 32 * kNumStats doubles.
+__device__ __forceinline__ void stats_block_reduce(double r[kNumStats], double* red)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double v[kNumStats];
+#pragma unroll
+        for (int k = 0; k < kNumStats; k++)
+            v[k] = __shfl_xor_sync(0xffffffffu, r[k], o);
+        stats_merge(r, v);
+    }
+    __syncthreads(); // red may still be read by a previous reduction
+    if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < kNumStats; k++)
+            red[warp * kNumStats + k] = r[k];
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int w = 1; w < warps; w++)
+            stats_merge(r, red + w * kNumStats);
+}
+
 // read-only 32-byte load (there is no __ldg overload for double4)
 __device__ __forceinline__ double4 ldg_d4(const double4* p)
 {
@@ -129,36 +211,6 @@ __device__ __forceinline__ double4 ldg_d4(const double4* p)
     return make_double4(a.x, a.y, b.x, b.y);
 }
 #endif
-
-// order-preserving float <-> uint32 key
-__host__ __device__ inline uint32_t float_to_key(float f)
-{
-#ifdef __CUDA_ARCH__
-    uint32_t u = __float_as_uint(f);
-#else
-    union {
-        float f;
-        uint32_t u;
-    } c;
-    c.f = f;
-    uint32_t u = c.u;
-#endif
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__host__ __device__ inline float key_to_float(uint32_t k)
-{
-    uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
-#ifdef __CUDA_ARCH__
-    return __uint_as_float(u);
-#else
-    union {
-        float f;
-        uint32_t u;
-    } c;
-    c.u = u;
-    return c.f;
-#endif
-}
 
 // ---- narrow-phase parameters -----------------------------------------------------------
 struct NarrowParams {
@@ -206,35 +258,43 @@ struct LaunchCounter {
     int64_t n = 0;
 };
 
-void launch_vertex_boxes(
+void launch_mesh_boxes(
     const double* V0, const double* V1, int nV, double radius_up, VertexRec* vtab,
-    double* vbox /* 6*nV: min xyz, max xyz */, BoxArrays vf_unsorted, cudaStream_t s,
-    LaunchCounter& lc);
-void launch_element_boxes(
-    const double* vbox, const int32_t* E, int nE, const int32_t* F, int nF, int nV,
-    BoxArrays e_unsorted, BoxArrays vf_unsorted, cudaStream_t s, LaunchCounter& lc);
+    double* vbox /* 6*nV: min xyz, max xyz */, const int32_t* E, int nE, const int32_t* F,
+    int nF, BoxArrays e_unsorted, BoxArrays vf_unsorted, cudaStream_t s, LaunchCounter& lc);
 
 // ---- grid (csrc/grid.cu)
-// stats[6] = {min ymin, max ymax, min zmin, max zmax, sum (ymax-ymin), sum (zmax-zmin)}
+// Statistics of a list (stats_identity() layout) over every stride-th box: they only steer
+// the grid and the key quantisation, both of which clamp, so a sample is as good as the whole.
 constexpr int kStatsBlocks = 296;
 void launch_box_stats(
-    const BoxArrays& unsorted, int n, double* partials /* kStatsBlocks*6 */, double* stats,
+    const BoxArrays& unsorted, int n, int stride, double* partials /* kStatsBlocks*8 */,
+    double* stats,
     cudaStream_t s, LaunchCounter& lc);
-// copies[i] = number of cells box i touches
+// copies[i] = number of cells box i touches inside [g.cell_lo, g.cell_hi), or inside the
+// range d_range[0..1] held on the device when d_range is not null
 void launch_expand_count(
-    const BoxArrays& unsorted, int n, GridParams g, uint32_t* copies, cudaStream_t s,
-    LaunchCounter& lc);
+    const BoxArrays& unsorted, int n, GridParams g, const unsigned long long* d_range,
+    uint32_t* copies, cudaStream_t s, LaunchCounter& lc);
+// Multi-GPU: histogram of the records of every stride-th box per cell and `world` contiguous
+// cell ranges of ~equal estimated sweep work.  out (device, 2 * world + 2 words): [0..world]
+// first cell of each rank, [world+1] sampled records in total, [world+2+r] of rank r.
+// hist: g.sy * g.sz words.
+void launch_cell_splits(
+    const BoxArrays& unsorted, int n, int stride, GridParams g, int world, uint32_t* hist,
+    unsigned long long* out, cudaStream_t s, LaunchCounter& lc);
 // one (key, box index) record per touched cell, at offsets[i] ...
 void launch_expand_fill(
     const BoxArrays& unsorted, int n, GridParams g, const unsigned long long* offsets,
-    unsigned long long* keys, uint32_t* idx, cudaStream_t s, LaunchCounter& lc);
+    uint32_t* keys, uint32_t* idx, cudaStream_t s, LaunchCounter& lc);
 
 size_t sort_temp_bytes(int n);
-// sorts m (key, box index) records on the low key_bits bits and gathers the sorted views
+// sorts m (key, box index) records on key bits [kKeyFlagBits, kKeyFlagBits + key_bits) and
+// gathers the sorted views
 void launch_sort_and_gather(
-    int m, int key_bits, unsigned long long* keys_in, unsigned long long* keys_out,
-    uint32_t* idx_in, uint32_t* idx_out, void* temp, size_t temp_bytes, BoxArrays unsorted,
-    SortedList out, cudaStream_t s, LaunchCounter& lc, cudaEvent_t gather_begin = nullptr,
+    int m, int key_bits, uint32_t* keys_in, uint32_t* keys_out, uint32_t* idx_in,
+    uint32_t* idx_out, void* temp, size_t temp_bytes, BoxArrays unsorted, SortedList out,
+    cudaStream_t s, LaunchCounter& lc, cudaEvent_t gather_begin = nullptr,
     cudaEvent_t gather_end = nullptr);
 
 // window[i] = number of candidates after owner i whose f32 xmin <= owner's f32 xmax

@@ -7,7 +7,8 @@
 // (cell, xmin), and the sweep window of a record only contains records of the same cell.
 // A pair is reported in exactly one cell (see GridParams), so the emitted SET is unchanged.
 //
-// Kernels: box statistics (grid choice), copies-per-box count, (key, index) expansion.
+// Kernels: box statistics (grid choice), copies-per-box count, (key, index) expansion,
+// per-cell histogram + balanced cell ranges for the multi-GPU split.
 #include "common.cuh"
 
 #include <cfloat>
@@ -19,77 +20,44 @@ namespace {
 constexpr int kThreads = 256;
 
 __global__ void __launch_bounds__(kThreads)
-    box_stats_kernel(BoxArrays boxes, int n, double* __restrict__ partials)
+    box_stats_kernel(BoxArrays boxes, int n, int stride, double* __restrict__ partials)
 {
-    double mn_y = DBL_MAX, mx_y = -DBL_MAX, mn_z = DBL_MAX, mx_z = -DBL_MAX, sy = 0.0, sz = 0.0;
-    for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    double r[kNumStats];
+    stats_identity(r);
+    const long long step = (long long)gridDim.x * kThreads * stride;
+    for (long long ii = ((long long)blockIdx.x * kThreads + threadIdx.x) * stride; ii < n;
+         ii += step) {
+        const int i = (int)ii;
         const double4 b = ldg_d4(&boxes.yz[i]); // (ymin, zmin, ymax, zmax)
-        mn_y = fmin(mn_y, b.x);
-        mn_z = fmin(mn_z, b.y);
-        mx_y = fmax(mx_y, b.z);
-        mx_z = fmax(mx_z, b.w);
-        sy += b.z - b.x;
-        sz += b.w - b.y;
+        const double2 x = __ldg(&boxes.x[i]);
+        const double lo[3] = { x.x, b.x, b.y }, hi[3] = { x.y, b.z, b.w };
+        double v[kNumStats];
+        stats_of_box(v, lo, hi);
+        stats_merge(r, v);
     }
-    __shared__ double red[6][kThreads / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        mn_y = fmin(mn_y, __shfl_xor_sync(0xffffffffu, mn_y, o));
-        mx_y = fmax(mx_y, __shfl_xor_sync(0xffffffffu, mx_y, o));
-        mn_z = fmin(mn_z, __shfl_xor_sync(0xffffffffu, mn_z, o));
-        mx_z = fmax(mx_z, __shfl_xor_sync(0xffffffffu, mx_z, o));
-        sy += __shfl_xor_sync(0xffffffffu, sy, o);
-        sz += __shfl_xor_sync(0xffffffffu, sz, o);
-    }
-    if (lane == 0) {
-        red[0][warp] = mn_y;
-        red[1][warp] = mx_y;
-        red[2][warp] = mn_z;
-        red[3][warp] = mx_z;
-        red[4][warp] = sy;
-        red[5][warp] = sz;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < kThreads / 32; w++) {
-            red[0][0] = fmin(red[0][0], red[0][w]);
-            red[1][0] = fmax(red[1][0], red[1][w]);
-            red[2][0] = fmin(red[2][0], red[2][w]);
-            red[3][0] = fmax(red[3][0], red[3][w]);
-            red[4][0] += red[4][w];
-            red[5][0] += red[5][w];
-        }
-        for (int k = 0; k < 6; k++)
-            partials[blockIdx.x * 6 + k] = red[k][0];
-    }
+    __shared__ double red[32 * kNumStats];
+    stats_block_reduce(r, red);
+    if (threadIdx.x == 0)
+        for (int k = 0; k < kNumStats; k++)
+            partials[blockIdx.x * kNumStats + k] = r[k];
 }
 
-// one warp; fixed reduction tree => deterministic sums
-__global__ void box_stats_final_kernel(const double* __restrict__ partials, int blocks, double* out)
+// one CTA; fixed reduction tree => deterministic sums
+__global__ void __launch_bounds__(kThreads)
+    box_stats_final_kernel(const double* __restrict__ partials, int blocks, int stride, double* out)
 {
-    const int lane = threadIdx.x;
-    double r[6] = { DBL_MAX, -DBL_MAX, DBL_MAX, -DBL_MAX, 0.0, 0.0 };
-    for (int b = lane; b < blocks; b += 32) {
-        r[0] = fmin(r[0], partials[b * 6 + 0]);
-        r[1] = fmax(r[1], partials[b * 6 + 1]);
-        r[2] = fmin(r[2], partials[b * 6 + 2]);
-        r[3] = fmax(r[3], partials[b * 6 + 3]);
-        r[4] += partials[b * 6 + 4];
-        r[5] += partials[b * 6 + 5];
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        r[0] = fmin(r[0], __shfl_xor_sync(0xffffffffu, r[0], o));
-        r[1] = fmax(r[1], __shfl_xor_sync(0xffffffffu, r[1], o));
-        r[2] = fmin(r[2], __shfl_xor_sync(0xffffffffu, r[2], o));
-        r[3] = fmax(r[3], __shfl_xor_sync(0xffffffffu, r[3], o));
-        r[4] += __shfl_xor_sync(0xffffffffu, r[4], o);
-        r[5] += __shfl_xor_sync(0xffffffffu, r[5], o);
-    }
-    if (lane == 0)
-        for (int k = 0; k < 6; k++)
+    double r[kNumStats];
+    stats_identity(r);
+    for (int b = threadIdx.x; b < blocks; b += kThreads)
+        stats_merge(r, partials + b * kNumStats);
+    __shared__ double red[32 * kNumStats];
+    stats_block_reduce(r, red);
+    if (threadIdx.x == 0) {
+        r[4] *= (double)stride; // sums over a 1-in-stride sample -> estimates for the list
+        r[5] *= (double)stride;
+        for (int k = 0; k < kNumStats; k++)
             out[k] = r[k];
+    }
 }
 
 __device__ __forceinline__ void cell_range(
@@ -101,70 +69,211 @@ __device__ __forceinline__ void cell_range(
     z1 = cell_index(yz.w, g.z0, g.inv_hz, g.sz);
 }
 
-__global__ void __launch_bounds__(kThreads)
-    expand_count_kernel(BoxArrays boxes, int n, GridParams g, uint32_t* __restrict__ copies)
+// cells of row cy, columns [z0, z1], that fall in this rank's linear range [cell_lo, cell_hi)
+__device__ __forceinline__ void clip_row(const GridParams& g, int cy, int& z0, int& z1)
+{
+    const long long base = (long long)cy * g.sz;
+    const long long lo = (long long)g.cell_lo - base, hi = (long long)g.cell_hi - base - 1;
+    if (lo > z0)
+        z0 = (int)(lo < (long long)g.sz ? lo : (long long)g.sz);
+    if (hi < z1)
+        z1 = (int)(hi > -1 ? hi : -1);
+}
+
+__global__ void __launch_bounds__(kThreads) expand_count_kernel(
+    BoxArrays boxes, int n, GridParams g, const unsigned long long* __restrict__ d_range,
+    uint32_t* __restrict__ copies)
 {
     const int i = blockIdx.x * kThreads + threadIdx.x;
     if (i >= n)
         return;
+    if (d_range) { // this rank's cell range, still on the device (launch_cell_splits)
+        g.cell_lo = (int)d_range[0];
+        g.cell_hi = (int)d_range[1];
+    }
     int y0, y1, z0, z1;
     cell_range(ldg_d4(&boxes.yz[i]), g, y0, y1, z0, z1);
-    copies[i] = (uint32_t)((y1 - y0 + 1) * (z1 - z0 + 1));
+    uint32_t k = 0;
+    for (int cy = y0; cy <= y1; cy++) {
+        int a = z0, b = z1;
+        clip_row(g, cy, a, b);
+        if (b >= a)
+            k += (uint32_t)(b - a + 1);
+    }
+    copies[i] = k;
+}
+
+// hist[cell] += 1 for every cell a sampled box (every stride-th) touches: the multi-GPU cell
+// ranges only have to be balanced, not exact, and one atomic per record of a 50M-box list
+// costs more than sorting this rank's share of it.
+__global__ void __launch_bounds__(kThreads) cell_hist_kernel(
+    BoxArrays boxes, int n, int stride, GridParams g, uint32_t* __restrict__ hist)
+{
+    const long long s = ((long long)blockIdx.x * kThreads + threadIdx.x) * stride;
+    if (s >= n)
+        return;
+    const int i = (int)s;
+    int y0, y1, z0, z1;
+    cell_range(ldg_d4(&boxes.yz[i]), g, y0, y1, z0, z1);
+    for (int cy = y0; cy <= y1; cy++)
+        for (int cz = z0; cz <= z1; cz++)
+            atomicAdd(&hist[cy * g.sz + cz], 1u);
+}
+
+// Contiguous cell ranges of ~equal sweep work for `world` ranks.  Work estimate per cell = its
+// record count: with the cell grid the windows are short and the measured sweep time is
+// proportional to the records (config 4: 0.18-0.20 us per 1000 records on every rank), as are
+// sort and gather.  Exact integer arithmetic, so every rank derives the same split points from
+// its own replica.  out[0..world] = first cell of each rank (out[world] = cells),
+// out[world+1] = total SAMPLED records, out[world+2+r] = sampled records of rank r.  One CTA.
+__global__ void __launch_bounds__(1024) cell_splits_kernel(
+    const uint32_t* __restrict__ hist, int cells, int world, unsigned long long* __restrict__ out)
+{
+    __shared__ unsigned long long part[1024];
+    __shared__ unsigned long long total_s;
+    __shared__ unsigned long long recs[64];
+    __shared__ int split_s[65];
+    const int t = threadIdx.x;
+    const int per = (cells + 1023) / 1024;
+    const int c0 = min(cells, t * per), c1 = min(cells, c0 + per);
+    unsigned long long s = 0;
+    for (int c = c0; c < c1; c++)
+        s += hist[c];
+    part[t] = s;
+    if (t <= world) {
+        split_s[t] = t == 0 ? 0 : cells;
+        recs[t] = 0;
+    }
+    __syncthreads();
+    if (t == 0) {
+        unsigned long long run = 0;
+        for (int i = 0; i < 1024; i++) {
+            const unsigned long long v = part[i];
+            part[i] = run;
+            run += v;
+        }
+        total_s = run;
+    }
+    __syncthreads();
+    const unsigned long long total = total_s;
+    unsigned long long run = part[t];
+    for (int c = c0; c < c1; c++) {
+        const unsigned long long before = run;
+        run += hist[c];
+        for (int r = 1; r < world; r++) {
+            const unsigned long long target = total / (unsigned long long)world * r;
+            if (before < target && target <= run)
+                split_s[r] = c + 1; // cell c is the last one of rank r - 1
+        }
+    }
+    __syncthreads();
+    // a target of 0 (empty list) is never crossed: keep the splits monotone
+    if (t == 0)
+        for (int r = world - 1; r >= 1; r--)
+            split_s[r] = min(split_s[r], split_s[r + 1]);
+    __syncthreads();
+    unsigned long long mine[16] = {};
+    for (int c = c0; c < c1; c++) {
+        int r = 0;
+        while (r + 1 < world && c >= split_s[r + 1])
+            r++;
+        if (r < 16)
+            mine[r] += hist[c];
+    }
+    for (int r = 0; r < world && r < 16; r++)
+        if (mine[r])
+            atomicAdd(&recs[r], mine[r]);
+    __syncthreads();
+    if (t <= world)
+        out[t] = (unsigned long long)split_s[t];
+    if (t < world)
+        out[world + 2 + t] = recs[t];
+    if (t == 0) {
+        unsigned long long m = 0;
+        for (int r = 0; r < world; r++)
+            m += recs[r];
+        out[world + 1] = m;
+    }
 }
 
 __global__ void __launch_bounds__(kThreads) expand_fill_kernel(
     BoxArrays boxes, int n, GridParams g, const unsigned long long* __restrict__ offsets,
-    unsigned long long* __restrict__ keys, uint32_t* __restrict__ idx)
+    uint32_t* __restrict__ keys, uint32_t* __restrict__ idx)
 {
     const int i = blockIdx.x * kThreads + threadIdx.x;
     if (i >= n)
         return;
     int y0, y1, z0, z1;
     cell_range(ldg_d4(&boxes.yz[i]), g, y0, y1, z0, z1);
-    // x part of the key: min.x rounded DOWN to f32 (conservative for the prefilter)
-    const unsigned long long xk = float_to_key(__double2float_rd(__ldg(&boxes.x[i]).x));
+    // see sweep_key() in common.cuh
+    const uint32_t xq = quantize_x(__ldg(&boxes.x[i]).x, g) << kKeyFlagBits;
+    const uint32_t type = __ldg(&boxes.id[i]).w < 0 ? kKeyFlagType : 0u;
+    const int cell_shift = g.x_bits + kKeyFlagBits;
     unsigned long long o = offsets[i];
-    for (int cy = y0; cy <= y1; cy++)
-        for (int cz = z0; cz <= z1; cz++) {
-            const unsigned long long cell = (unsigned long long)(cy * g.sz + cz);
-            keys[o] = (cell << 32) | xk;
+    for (int cy = y0; cy <= y1; cy++) {
+        int a = z0, b = z1;
+        clip_row(g, cy, a, b);
+        for (int cz = a; cz <= b; cz++) {
+            const uint32_t cell = (uint32_t)(cy * g.sz + cz);
+            const uint32_t hi = cell_shift >= 32 ? 0u : (cell << cell_shift);
+            keys[o] = hi | xq | type | (cy == y0 ? kKeyFlagY : 0u) | (cz == z0 ? kKeyFlagZ : 0u);
             idx[o] = (uint32_t)i;
             o++;
         }
+    }
 }
 
 } // namespace
 
 void launch_box_stats(
-    const BoxArrays& unsorted, int n, double* partials, double* stats, cudaStream_t s,
-    LaunchCounter& lc)
+    const BoxArrays& unsorted, int n, int stride, double* partials, double* stats,
+    cudaStream_t s, LaunchCounter& lc)
 {
-    int blocks = (n + kThreads - 1) / kThreads;
+    int blocks = ((n + stride - 1) / stride + kThreads - 1) / kThreads;
     if (blocks > kStatsBlocks)
         blocks = kStatsBlocks;
     if (blocks < 1)
         blocks = 1;
-    box_stats_kernel<<<blocks, kThreads, 0, s>>>(unsorted, n, partials);
+    box_stats_kernel<<<blocks, kThreads, 0, s>>>(unsorted, n, stride, partials);
     SCCD_CUDA(cudaGetLastError());
-    box_stats_final_kernel<<<1, 32, 0, s>>>(partials, blocks, stats);
+    box_stats_final_kernel<<<1, kThreads, 0, s>>>(partials, blocks, stride, stats);
     SCCD_CUDA(cudaGetLastError());
     lc.n += 2;
 }
 
 void launch_expand_count(
-    const BoxArrays& unsorted, int n, GridParams g, uint32_t* copies, cudaStream_t s,
-    LaunchCounter& lc)
+    const BoxArrays& unsorted, int n, GridParams g, const unsigned long long* d_range,
+    uint32_t* copies, cudaStream_t s, LaunchCounter& lc)
 {
     if (n <= 0)
         return;
-    expand_count_kernel<<<(n + kThreads - 1) / kThreads, kThreads, 0, s>>>(unsorted, n, g, copies);
+    expand_count_kernel<<<(n + kThreads - 1) / kThreads, kThreads, 0, s>>>(
+        unsorted, n, g, d_range, copies);
+    SCCD_CUDA(cudaGetLastError());
+    lc.n++;
+}
+
+void launch_cell_splits(
+    const BoxArrays& unsorted, int n, int stride, GridParams g, int world, uint32_t* hist,
+    unsigned long long* out, cudaStream_t s, LaunchCounter& lc)
+{
+    const int cells = g.sy * g.sz;
+    SCCD_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * (size_t)cells, s));
+    if (n > 0) {
+        const int samples = (n + stride - 1) / stride;
+        cell_hist_kernel<<<(samples + kThreads - 1) / kThreads, kThreads, 0, s>>>(
+            unsorted, n, stride, g, hist);
+        SCCD_CUDA(cudaGetLastError());
+        lc.n++;
+    }
+    cell_splits_kernel<<<1, 1024, 0, s>>>(hist, cells, world, out);
     SCCD_CUDA(cudaGetLastError());
     lc.n++;
 }
 
 void launch_expand_fill(
     const BoxArrays& unsorted, int n, GridParams g, const unsigned long long* offsets,
-    unsigned long long* keys, uint32_t* idx, cudaStream_t s, LaunchCounter& lc)
+    uint32_t* keys, uint32_t* idx, cudaStream_t s, LaunchCounter& lc)
 {
     if (n <= 0)
         return;

@@ -3,11 +3,11 @@
 // Replaces thrust::sort_by_key with a comparator on 16 B keys / 48 B values, the D2D copy,
 // flip_element_ids and thrust::merge_by_key of the reference
 // (cuda/broad_phase/aabb.cu:107-109, broad_phase.cu:57-101) by:
-//   1. an LSD radix sort of (u64 key = cell << 32 | order-preserving u32 of f32(min.x rounded
-//      down), u32 box index) over only the key bits in use -- 12 B per record per pass
+//   1. an LSD radix sort of (u32 key = [cell | quantised min.x | flags] (common.cuh), u32 box
+//      index) over only the key bits in use (3-4 digit passes) -- 8 B per record per pass
 //      instead of 64 B;
 //   2. ONE gather that moves each 64 B exact record to its sorted position and emits the
-//      32 B prefilter view (key, reach, f32 yz) the sweep streams.
+//      24 B prefilter view (key, reach, f32 yz) the sweep streams.
 // The radix sort is stable, so ties keep element order and the result is deterministic.
 // The vertex-face list is sorted as one tagged list (vertex element ids are already
 // flipped at build time), so no merge is needed.
@@ -23,22 +23,25 @@ namespace {
 constexpr int kThreads = 256;
 
 __global__ void __launch_bounds__(kThreads) gather_sorted_kernel(
-    int m, const unsigned long long* __restrict__ sorted_keys,
-    const uint32_t* __restrict__ sorted_idx, BoxArrays in, BoxArrays out, PrefilterArrays pf)
+    int m, const uint32_t* __restrict__ sorted_keys, const uint32_t* __restrict__ sorted_idx,
+    BoxArrays in, BoxArrays out, PrefilterArrays pf, GridParams g)
 {
     const int j = blockIdx.x * kThreads + threadIdx.x;
     if (j >= m)
         return;
     const uint32_t src = sorted_idx[j];
-    const unsigned long long key = sorted_keys[j];
+    const uint32_t key = sorted_keys[j];
     const double2 x = __ldg(&in.x[src]);
     const double4 yz = ldg_d4(&in.yz[src]);
     const int4 id = __ldg(&in.id[src]);
     out.x[j] = x;
     out.yz[j] = yz;
     out.id[j] = id;
-    pf.key[j] = key; // (cell << 32) | key32(f32 down(xmin))
-    pf.reach[j] = (key & 0xffffffff00000000ull) | float_to_key(__double2float_ru(x.y));
+    pf.key[j] = key;
+    // same cell, q(xmax), every flag bit set (common.cuh)
+    const int cell_shift = g.x_bits + kKeyFlagBits;
+    const uint32_t cell_part = cell_shift >= 32 ? 0u : (key >> cell_shift) << cell_shift;
+    pf.reach[j] = cell_part | (quantize_x(x.y, g) << kKeyFlagBits) | ((1u << kKeyFlagBits) - 1u);
     pf.yz[j] = make_float4(
         __double2float_rd(yz.x), __double2float_ru(yz.z), __double2float_rd(yz.y),
         __double2float_ru(yz.w));
@@ -53,16 +56,15 @@ size_t sort_temp_bytes(int n)
 {
     size_t bytes = 0;
     cub::DeviceRadixSort::SortPairs(
-        nullptr, bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
-        (const uint32_t*)nullptr, (uint32_t*)nullptr, n > 0 ? n : 1, 0, 64);
+        nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
+        (uint32_t*)nullptr, n > 0 ? n : 1, 0, 32);
     return bytes;
 }
 
 void launch_sort_and_gather(
-    int m, int key_bits, unsigned long long* keys_in, unsigned long long* keys_out,
-    uint32_t* idx_in, uint32_t* idx_out, void* temp, size_t temp_bytes, BoxArrays unsorted,
-    SortedList out, cudaStream_t s, LaunchCounter& lc, cudaEvent_t gather_begin,
-    cudaEvent_t gather_end)
+    int m, int key_bits, uint32_t* keys_in, uint32_t* keys_out, uint32_t* idx_in,
+    uint32_t* idx_out, void* temp, size_t temp_bytes, BoxArrays unsorted, SortedList out,
+    cudaStream_t s, LaunchCounter& lc, cudaEvent_t gather_begin, cudaEvent_t gather_end)
 {
     if (m <= 0) {
         if (gather_begin)
@@ -71,14 +73,15 @@ void launch_sort_and_gather(
             SCCD_CUDA(cudaEventRecord(gather_end, s));
         return;
     }
+    // the flag bits are not part of the order: equal (cell, q) records keep element order
     SCCD_CUDA(cub::DeviceRadixSort::SortPairs(
-        temp, temp_bytes, (const unsigned long long*)keys_in, keys_out,
-        (const uint32_t*)idx_in, idx_out, m, 0, key_bits, s));
+        temp, temp_bytes, (const uint32_t*)keys_in, keys_out, (const uint32_t*)idx_in, idx_out, m,
+        kKeyFlagBits, kKeyFlagBits + key_bits, s));
     lc.n += 2 + (key_bits + 7) / 8; // histogram + exclusive sum + one onesweep pass per digit
     if (gather_begin)
         SCCD_CUDA(cudaEventRecord(gather_begin, s));
     gather_sorted_kernel<<<(m + kThreads - 1) / kThreads, kThreads, 0, s>>>(
-        m, keys_out, idx_out, unsorted, out.box, out.pf);
+        m, keys_out, idx_out, unsorted, out.box, out.pf, out.grid);
     SCCD_CUDA(cudaGetLastError());
     lc.n++;
     if (gather_end)

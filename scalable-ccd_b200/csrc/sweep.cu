@@ -3,18 +3,22 @@
 // Replaces sweep_and_tiniest_queue (cuda/broad_phase/sweep.cu:101-182: one warp per CTA,
 // a 64-slot shared ring rebalanced with shared atomics every round, uncoalesced 48 B
 // MiniBox loads per candidate, one global atomicAdd per emitted pair into a buffer that is
-// value-initialised on every call) with a tiled sweep:
+// value-initialised on every call) with a sliding-window sweep:
 //
-//   * a CTA owns a tile of 256 consecutive sorted records ("owners", one per lane);
-//   * the candidate window to the right of the tile is streamed through shared memory in
-//     256-record chunks of the 24-byte prefilter view (register double-buffered), every
-//     lane testing its owner against each staged candidate by shared-memory broadcast:
-//     one 64-bit compare key_j <= reach_i (same cell AND f32 xmin_j <= f32 xmax_i, see
-//     common.cuh) plus four f32 compares on y / z;
-//   * prefilter survivors (a conservative superset: min rounded down / max rounded up to
-//     f32) are ballot/scan-compacted into a per-warp shared queue -- the "tiniest queue" --
-//     and drained 32 at a time with ALL lanes running the exact double test + id tests,
-//     so the rare expensive path never diverges;
+//   * a warp owns 32 consecutive sorted records ("owners", one per lane).  In step k every
+//     lane looks at the record k places after its own: the 32 loads of a step are
+//     consecutive addresses (one coalesced request), and consecutive steps re-read the same
+//     lines from L1.  With the (y, z) cell grid a window holds a few dozen records, so this
+//     does ~32 tests per ~10 instructions with no staging, no barriers and no wasted
+//     owner x candidate combinations;
+//   * the prefilter is one unsigned compare key_j <= reach_i (same cell AND quantised
+//     xmin_j <= xmax_i), two bit operations on the key's flag bits (other list; pair is at
+//     home in this cell -- see common.cuh) and four f32 compares on y / z; the 16-byte yz
+//     record is only loaded for candidates that pass the key tests;
+//   * prefilter survivors (a conservative superset: min rounded down / max rounded up) are
+//     ballot-compacted into a per-warp shared queue -- the "tiniest queue" -- and drained 32
+//     at a time with ALL lanes running the exact double test + vertex-sharing test, so the
+//     rare expensive path never diverges;
 //   * output is count -> exclusive scan -> fill: the pair list is exactly sized, ordered by
 //     (owner position, candidate position) and therefore deterministic; no global atomics
 //     and no giant memset; 64-bit offsets.
@@ -22,11 +26,11 @@
 // The emitted SET equals the reference's: every pair with closed overlap on x, y, z
 // (cuda/broad_phase/aabb.cuh:100-104, sweep.cu:131,173), valid list membership
 // (collision.cuh:27-35) and no shared vertex (collision.cuh:17-21).  Why nothing is lost or
-// duplicated: (1) sorting on the f32 key instead of the double only changes the ORDER in
-// which ties are visited -- the window test on rounded values is a superset of
+// duplicated: (1) sorting on a quantised key instead of the double only changes the ORDER in
+// which ties are visited -- the window test on quantised values is a superset of
 // min_j <= max_i and the exact test checks both x directions; (2) two overlapping boxes both
 // own a record in the cell of (max(ymin_a,ymin_b), max(zmin_a,zmin_b)) because cell_index()
-// is monotone, and the pair is accepted in that cell only.
+// is monotone, and the pair is accepted in that cell only (flag bits fy / fz).
 #include "common.cuh"
 
 #include <cfloat>
@@ -35,31 +39,23 @@ namespace sccd {
 
 namespace {
 
-constexpr int kTile = 256;  // owners per CTA == threads per CTA
+constexpr int kTile = 256; // owners per CTA == threads per CTA
 constexpr int kWarps = kTile / 32;
-constexpr int kChunk = 256; // candidates staged per step
-constexpr int kQueueCap = 32 * 32 + 32;
+constexpr int kQueueCap = 64;
 constexpr int kRelBits = 27; // candidate position relative to the tile start
 constexpr unsigned kFull = 0xffffffffu;
-constexpr unsigned long long kKeyInf = ~0ull;
 
 struct SweepSmem {
-    unsigned long long c_key[kChunk];
-    float4 c_yz[kChunk];
-    double2 o_x[kTile];
-    double4 o_yz[kTile];
-    int4 o_id[kTile];
     unsigned long long o_off[kTile];
-    uint32_t o_cell[kTile];
     uint32_t o_cnt[kTile];
     uint32_t q[kWarps][kQueueCap];
-    unsigned long long red[kWarps];
 };
 
+// Exact test of up to 32 queued (owner lane, candidate) entries, one per lane.
 template <bool FILL, bool TWO_LISTS>
 __device__ __forceinline__ void drain32(
-    SweepSmem& sm, const BoxArrays& box, const GridParams& g, int tile0, int warp, int lane,
-    uint32_t entry, bool active, sccd_pair* __restrict__ pairs)
+    SweepSmem& sm, const BoxArrays& box, int tile0, int warp, int lane, uint32_t entry,
+    bool active, sccd_pair* __restrict__ pairs)
 {
     const int ol = active ? (int)(entry >> kRelBits) : 0;
     const int t = warp * 32 + ol;
@@ -67,28 +63,21 @@ __device__ __forceinline__ void drain32(
     bool hit = false;
     int ea = 0, eb = 0;
     if (active) {
-        const double2 ax = sm.o_x[t];
-        const double4 ayz = sm.o_yz[t];
-        const int4 aid = sm.o_id[t];
+        const int i = tile0 + t;
+        const double2 ax = __ldg(&box.x[i]);
+        const double4 ayz = ldg_d4(&box.yz[i]);
+        const int4 aid = __ldg(&box.id[i]);
         const double2 bx = __ldg(&box.x[j]);
         const double4 byz = ldg_d4(&box.yz[j]);
         const int4 bid = __ldg(&box.id[j]);
         // closed-interval overlap on all three axes (aabb.cuh:67-72 / 100-104)
         hit = ax.y >= bx.x && ax.x <= bx.y && ayz.z >= byz.x && ayz.x <= byz.z
             && ayz.w >= byz.y && ayz.y <= byz.w;
-        if (TWO_LISTS) // exactly one of the two comes from list A (collision.cuh:27-35)
-            hit = hit && ((aid.w ^ bid.w) < 0);
         // collision.cuh:17-21
         const bool share = aid.x == bid.x || aid.x == bid.y || aid.x == bid.z
             || aid.y == bid.x || aid.y == bid.y || aid.y == bid.z || aid.z == bid.x
             || aid.z == bid.y || aid.z == bid.z;
         hit = hit && !share;
-        if (g.sy * g.sz > 1) {
-            // report the pair only in its home cell (both boxes own a record there)
-            const int cy = cell_index(fmax(ayz.x, byz.x), g.y0, g.inv_hy, g.sy);
-            const int cz = cell_index(fmax(ayz.y, byz.y), g.z0, g.inv_hz, g.sz);
-            hit = hit && (uint32_t)(cy * g.sz + cz) == sm.o_cell[t];
-        }
         ea = aid.w;
         eb = bid.w;
     }
@@ -122,12 +111,11 @@ __device__ __forceinline__ void drain32(
 
 template <bool FILL, bool TWO_LISTS>
 __global__ void __launch_bounds__(kTile) sweep_kernel(
-    PrefilterArrays pf, BoxArrays box, GridParams g, int n, int shard_lo, int owner_lo,
-    int owner_hi, uint32_t* __restrict__ counts, const unsigned long long* __restrict__ offsets,
+    PrefilterArrays pf, BoxArrays box, int n, int shard_lo, int owner_lo, int owner_hi,
+    uint32_t* __restrict__ counts, const unsigned long long* __restrict__ offsets,
     sccd_pair* __restrict__ pairs, unsigned long long* __restrict__ n_candidates)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    SweepSmem& sm = *reinterpret_cast<SweepSmem*>(smem_raw);
+    __shared__ SweepSmem sm;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -136,124 +124,63 @@ __global__ void __launch_bounds__(kTile) sweep_kernel(
     const int i = tile0 + tid;
     const bool valid = i < owner_hi;
 
-    unsigned long long my_reach = 0; // an invalid owner reaches nothing (keys are > 0)
+    uint32_t my_reach = 0, my_flags = 0;
     float4 my = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid) {
-        my_reach = pf.reach[i];
-        my = pf.yz[i];
-        sm.o_x[tid] = box.x[i];
-        sm.o_yz[tid] = box.yz[i];
-        sm.o_id[tid] = box.id[i];
-        sm.o_cell[tid] = (uint32_t)(my_reach >> 32);
+        my_reach = __ldg(&pf.reach[i]);
+        my_flags = __ldg(&pf.key[i]) & ((1u << kKeyFlagBits) - 1u);
+        my = __ldg(&pf.yz[i]);
         if (FILL) // position of this owner's first pair inside the chunk being filled
             sm.o_off[tid] = offsets[i - shard_lo] - offsets[owner_lo - shard_lo];
     }
     sm.o_cnt[tid] = 0;
-
-    // reach of the warp / of the tile in sorted-key order
-    unsigned long long wmax = my_reach;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long v = __shfl_xor_sync(kFull, wmax, o);
-        wmax = v > wmax ? v : wmax;
-    }
-    if (lane == 0)
-        sm.red[warp] = wmax;
-    __syncthreads();
-    unsigned long long tile_max = sm.red[0];
-#pragma unroll
-    for (int w = 1; w < kWarps; w++)
-        tile_max = sm.red[w] > tile_max ? sm.red[w] : tile_max;
+    __syncwarp();
 
     uint32_t* q = sm.q[warp];
     int qn = 0;                    // entries waiting in this warp's queue (warp-uniform)
-    unsigned long long tested = 0; // exact tests run by this warp (lane 0's copy is used)
+    unsigned long long tested = 0; // exact tests run by this warp (warp-uniform)
+    const uint32_t rel_base = (uint32_t)(i - tile0);
+    // the pair must be at home in this cell, and (two lists) join a vertex with a face
+    constexpr uint32_t kHome = kKeyFlagY | kKeyFlagZ;
 
-    // register double buffer for the next chunk
-    int cs = tile0 + 1;
-    unsigned long long nk = kKeyInf; // +inf pads the list
-    float4 nyz = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (cs + tid < n) {
-        nk = pf.key[cs + tid];
-        nyz = pf.yz[cs + tid];
-    }
-    for (; cs < n; cs += kChunk) {
-        __syncthreads(); // previous chunk fully consumed
-        sm.c_key[tid] = nk;
-        sm.c_yz[tid] = nyz;
-        __syncthreads();
-        if (sm.c_key[0] > tile_max)
-            break; // block-uniform: the sorted list has left the tile's reach
-        {
-            const int jn = cs + kChunk + tid;
-            nk = kKeyInf;
-            if (jn < n) {
-                nk = pf.key[jn];
-                nyz = pf.yz[jn];
-            }
+    for (int k = 1;; k++) {
+        const int j = i + k;
+        uint32_t kj = 0xffffffffu;
+        if (valid && j < n)
+            kj = __ldg(&pf.key[j]);
+        const bool in_window = valid && j < n && kj <= my_reach;
+        if (!__any_sync(kFull, in_window))
+            break;
+        bool p = in_window && ((kj | my_flags) & kHome) == kHome;
+        if (TWO_LISTS)
+            p = p && ((kj ^ my_flags) & kKeyFlagType) != 0u;
+        if (p) {
+            const float4 b = __ldg(&pf.yz[j]);
+            p = (b.x <= my.y) && (my.x <= b.y) && (b.z <= my.w) && (my.z <= b.w);
         }
-        if (sm.c_key[0] > wmax)
-            continue; // warp-uniform
-        for (int k0 = 0; k0 < kChunk; k0 += 32) {
-            if (sm.c_key[k0] > wmax)
-                break; // warp-uniform
-            uint32_t mask = 0;
-#pragma unroll
-            for (int kk = 0; kk < 32; kk++) {
-                const unsigned long long kj = sm.c_key[k0 + kk];
-                const float4 b = sm.c_yz[k0 + kk];
-                const bool p = (kj <= my_reach) && (b.x <= my.y) && (my.x <= b.y)
-                    && (b.z <= my.w) && (my.z <= b.w);
-                mask |= (p ? 1u : 0u) << kk;
-            }
-            // only candidates strictly after the owner in sorted order
-            const int jbase = cs + k0;
-            const int d = i - jbase;
-            if (d >= 31)
-                mask = 0;
-            else if (d >= 0)
-                mask &= ~((2u << d) - 1u);
-            if (!__any_sync(kFull, mask != 0))
-                continue;
-
-            // ballot/scan compaction of the survivors into the warp queue
-            const int cnt = __popc(mask);
-            int incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(kFull, incl, o);
-                if (lane >= o)
-                    incl += v;
-            }
-            const int total = __shfl_sync(kFull, incl, 31);
-            int pos = qn + incl - cnt;
-            const uint32_t rel0 = (uint32_t)(jbase - tile0);
-            while (mask) {
-                const int b = __ffs(mask) - 1;
-                mask &= mask - 1;
-                q[pos++] = ((uint32_t)lane << kRelBits) | (rel0 + b);
-            }
-            qn += total;
+        const unsigned mask = __ballot_sync(kFull, p);
+        if (mask == 0u)
+            continue;
+        if (p)
+            q[qn + __popc(mask & ((1u << lane) - 1u))] =
+                ((uint32_t)lane << kRelBits) | (rel_base + (uint32_t)k);
+        qn += __popc(mask);
+        __syncwarp();
+        if (qn >= 32) {
+            drain32<FILL, TWO_LISTS>(sm, box, tile0, warp, lane, q[lane], true, pairs);
+            tested += 32;
+            const int r = qn - 32;
+            const uint32_t v = (lane < r) ? q[32 + lane] : 0u;
             __syncwarp();
-            if (qn >= 32) {
-                const int nfull = qn & ~31;
-                for (int h = 0; h < nfull; h += 32)
-                    drain32<FILL, TWO_LISTS>(
-                        sm, box, g, tile0, warp, lane, q[h + lane], true, pairs);
-                tested += nfull;
-                const int r = qn - nfull;
-                const uint32_t v = (lane < r) ? q[nfull + lane] : 0u;
-                __syncwarp();
-                if (lane < r)
-                    q[lane] = v;
-                qn = r;
-                __syncwarp();
-            }
+            if (lane < r)
+                q[lane] = v;
+            qn = r;
+            __syncwarp();
         }
     }
     if (qn > 0) {
         drain32<FILL, TWO_LISTS>(
-            sm, box, g, tile0, warp, lane, lane < qn ? q[lane] : 0u, lane < qn, pairs);
+            sm, box, tile0, warp, lane, lane < qn ? q[lane] : 0u, lane < qn, pairs);
         tested += qn;
     }
     if (!FILL) {
@@ -266,14 +193,14 @@ __global__ void __launch_bounds__(kTile) sweep_kernel(
 }
 
 // window[i] = #records j > i with key_j <= reach_i (sweep work estimate used to balance
-// owner ranges across GPUs).
+// owner ranges across GPUs when a list has too few cells to be split by cell range).
 __global__ void __launch_bounds__(256)
     sweep_window_kernel(PrefilterArrays pf, int n, uint32_t* __restrict__ window)
 {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n)
         return;
-    const unsigned long long reach = pf.reach[i];
+    const uint32_t reach = pf.reach[i];
     int lo = i + 1, hi = n; // first j in (i, n) with key[j] > reach
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
@@ -311,17 +238,9 @@ void launch_sweep(
     const int owners = owner_hi - owner_lo;
     if (owners <= 0)
         return;
-    static bool configured = false;
-    auto kern = sweep_kernel<FILL, TWO>;
-    if (!configured) {
-        SCCD_CUDA(cudaFuncSetAttribute(
-            kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem)));
-        configured = true;
-    }
     const int grid = (owners + kTile - 1) / kTile;
-    kern<<<grid, kTile, sizeof(SweepSmem), s>>>(
-        L.pf, L.box, L.grid, L.n, shard_lo, owner_lo, owner_hi, counts, offsets, pairs,
-        n_candidates);
+    sweep_kernel<FILL, TWO><<<grid, kTile, 0, s>>>(
+        L.pf, L.box, L.n, shard_lo, owner_lo, owner_hi, counts, offsets, pairs, n_candidates);
     SCCD_CUDA(cudaGetLastError());
     lc.n++;
 }

@@ -74,3 +74,49 @@ def test_balance_plan_is_consistent(sccd):
                     assert plans[s][0][d] == plans[d][1][s]      # what s sends d, d expects
             got = [sum(p[1]) for p in plans]
             assert sum(got) == sum(counts) and max(got) - min(got) <= 1
+
+
+def _mesh_worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, ROOT)
+    from _pkg import load_package
+    sccd = load_package()
+    mg = sccd.multigpu
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        s = sccd.scenes.cloth_on_sphere(11, seed=3, sphere="uv")
+        flat, offs = mg.pack_mesh(s["V0"], s["V1"], s["E"], s["F"], world, pin=False)
+        out = torch.full((flat.numel(),), 255, dtype=torch.uint8)
+        mg.gather_mesh(flat, out)
+        q.put((rank, bool(torch.equal(out, flat)), offs, flat.numel()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_mesh_slices_all_gather_to_the_whole_mesh(world, sccd):
+    """Host-buffer entry at N > 1: every rank moves 1/N of the packed mesh, the all-gather
+    rebuilds the whole mesh on every rank."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_mesh_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res)
+    assert all(r[3] % (16 * world) == 0 for r in res)
+    # the packed layout is the C ABI's: column-major arrays at 16-byte aligned offsets
+    s = sccd.scenes.cloth_on_sphere(11, seed=3, sphere="uv")
+    flat, offs = sccd.multigpu.pack_mesh(s["V0"], s["V1"], s["E"], s["F"], world, pin=False)
+    raw = flat.numpy()
+    nV, nE = s["V0"].shape[0], s["E"].shape[0]
+    v1 = np.frombuffer(raw[offs[1]:offs[1] + 24 * nV].tobytes(), np.float64).reshape(3, nV).T
+    e = np.frombuffer(raw[offs[2]:offs[2] + 8 * nE].tobytes(), np.int32).reshape(2, nE).T
+    assert np.array_equal(v1, s["V1"]) and np.array_equal(e, s["E"])
+    assert all(o % 16 == 0 for o in offs)
