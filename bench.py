@@ -45,14 +45,28 @@ def make_scene(scenes, name):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """SM clock / throttle reasons DURING the timed region: NVML from a thread of this process
+    (a second `nvidia-smi -lms` process per rank holds driver locks long enough to slow the
+    step it is supposed to watch), nvidia-smi only if NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.rows = []
-        self.proc = None
+    def __init__(self, index, period_s=0.02):
+        self.rows, self.proc, self.h, self.stop_flag = [], None, None, False
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv = nv
+            self.h = nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.period = period_s
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.h = None
         exe = shutil.which("nvidia-smi")
         if exe:
             try:
@@ -64,11 +78,37 @@ class ClockSampler:
             except Exception:
                 self.proc = None
 
+    def _poll(self):
+        nv = self.nv
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self.stop_flag:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((time.time(), mhz, r))
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
     def stop(self, t0, t1):
+        if self.h is not None:
+            self.stop_flag = True
+            self.t.join(timeout=1.0)
+            sm = [m for (t, m, _) in self.rows if t0 <= t <= t1] or [m for (_, m, _) in self.rows]
+            if not sm:
+                return None
+            return {"sm_mhz": statistics.median(sm), "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml"}
         if not self.proc:
             return None
         time.sleep(0.15)
@@ -89,7 +129,7 @@ class ClockSampler:
         if not sm:
             return None
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 def cpu_step(orc, scene):
@@ -270,7 +310,9 @@ def main():
         barrier()
         t1 = time.time()
         clocks = smp.stop(t0, t1) if smp else None
-        ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+        per_step = [a.elapsed_time(b) for a, b in ev]
+        ms = sum(per_step) / steps
+        timed.last_steps = per_step
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -291,6 +333,7 @@ def main():
         sharded = sccd.multigpu.ShardedCCD(ctx)   # re-arm the shard after the unsharded runs
         barrier()
     ms, toi, stats, clocks = timed(step_resident, args.steps, args.warmup, sampler=True)
+    ms_steps = list(timed.last_steps)
     rank_stage_ms = None
     if world > 1:
         assert toi == single, ("sharded TOI differs from the single-GPU TOI", toi, single)
@@ -378,7 +421,7 @@ def main():
         "roofline": roofline,
         "toi": toi, "n_pairs": n_pairs,
         "pairs_per_rank": (sharded.last if sharded else None),
-        "stage_ms_per_rank": rank_stage_ms,
+        "stage_ms_per_rank": rank_stage_ms, "ms_steps_rank0": ms_steps,
         "single_gpu_ms_same_workload": single_ms,
         "speedup_vs_single_gpu": (single_ms / ms if single_ms else None), "n_prefilter_survivors": n_cand, "n_box_checks": n_checks,
         "narrow_queries_per_s": (sum(n_pairs) / (narrow_ms * 1e-3)) if narrow_ms > 0 else None,

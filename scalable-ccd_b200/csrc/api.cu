@@ -106,9 +106,9 @@ struct sccd_ctx {
     int* h_small = nullptr; // pinned scratch for tiny D2H results
 
     // narrow-phase state
-    DevBuf b_counters, b_queue, b_qheads, b_pend, b_toi_q, b_checks_q, b_queries;
+    DevBuf b_counters, b_items[2], b_toi_q, b_checks_q, b_queries;
     NarrowCounters* h_counters = nullptr; // pinned
-    long long queue_items = 0; // ring capacity per CTA
+    unsigned long long item_cap = 0; // capacity of each of the two hand-on lists
 
     sccd_stats stats {};
     LaunchCounter lc;
@@ -762,23 +762,22 @@ void broad_phase_partial(sccd_ctx* c, const sccd_pair** d_pairs, int64_t* n_pair
     *n_pairs = (int64_t)n_chunk;
 }
 
-void narrow_setup(sccd_ctx* c)
+void narrow_setup(sccd_ctx* c, long long n_queries)
 {
     if (!c->h_counters)
         SCCD_CUDA(cudaMallocHost((void**)&c->h_counters, sizeof(NarrowCounters)));
     c->b_counters.reserve(sizeof(NarrowCounters));
-    // one bounded ring per CTA of the persistent kernel; sccd_set_queue_capacity gives the
-    // TOTAL number of items (MemoryHandler::MAX_UNIT_SIZE analogue)
-    const int grid = narrow_grid_size(c->num_sms);
-    long long per = c->queue_cap > 0 ? (c->queue_cap + grid - 1) / grid : 1024;
-    per = std::min<long long>(std::max<long long>(per, 64), 1 << 16);
-    if (per != c->queue_items || !c->b_queue.ptr) {
-        const size_t bytes = (size_t)per * grid * sizeof(WorkItem);
-        c->b_queue.reserve(bytes);
-        SCCD_CUDA(cudaMemsetAsync(c->b_queue.ptr, 0, bytes, c->stream));
-        c->b_qheads.reserve((size_t)grid * sizeof(CtaQueue));
-        SCCD_CUDA(cudaMemsetAsync(c->b_qheads.ptr, 0, (size_t)grid * sizeof(CtaQueue), c->stream));
-        c->queue_items = per;
+    // two bounded lists of sub-boxes handed from round to round; sccd_set_queue_capacity gives
+    // the number of items of each (MemoryHandler::MAX_UNIT_SIZE analogue).  Default: one item
+    // per 4 queries, at least 64 Ki, at most 16 Mi (1 GiB per list).
+    long long cap = c->queue_cap > 0
+        ? c->queue_cap
+        : std::min<long long>(std::max<long long>(n_queries / 4, 1 << 16), 1 << 24);
+    cap = std::max<long long>(cap, 64);
+    if ((unsigned long long)cap != c->item_cap || !c->b_items[0].ptr) {
+        c->b_items[0].reserve((size_t)cap * sizeof(WorkItem));
+        c->b_items[1].reserve((size_t)cap * sizeof(WorkItem));
+        c->item_cap = (unsigned long long)cap;
     }
 }
 
@@ -796,7 +795,7 @@ void narrow_run(
         throw std::invalid_argument("narrow_phase: more than 2^32 queries in one batch");
     if (!d_toi_per_query && *toi_inout <= 0) // narrow_phase.cu:136: nothing can be earlier
         return;
-    narrow_setup(c);
+    narrow_setup(c, in.n);
     NarrowParams P;
     P.ms = ms;
     P.tol = tol;
@@ -809,8 +808,6 @@ void narrow_run(
     }
 
     NarrowCounters init {};
-    init.next_query = 0;
-    init.done = 0;
     init.toi = *toi_inout;
     *c->h_counters = init;
     SCCD_CUDA(cudaMemcpyAsync(
@@ -823,17 +820,30 @@ void narrow_run(
         checks = (unsigned int*)c->b_checks_q.reserve((size_t)in.n * 4);
         SCCD_CUDA(cudaMemsetAsync(checks, 0, (size_t)in.n * 4, c->stream));
     }
-    unsigned int* pend = (unsigned int*)c->b_pend.reserve((size_t)in.n * 4);
     const size_t kt = kt_begin(c, &c->stats.ms_k_narrow[kind]);
     launch_narrow_phase(
-        kind == SCCD_VF, in, P, c->b_counters.as<NarrowCounters>(), c->b_qheads.as<CtaQueue>(),
-        c->b_queue.as<WorkItem>(), (int)c->queue_items, pend, d_toi_per_query, checks,
-        c->num_sms, c->stream, c->lc);
+        kind == SCCD_VF, in, P, c->b_counters.as<NarrowCounters>(), c->b_items[0].as<WorkItem>(),
+        c->b_items[1].as<WorkItem>(), c->item_cap, d_toi_per_query, checks, c->num_sms, c->stream,
+        c->lc);
     kt_end(c, kt);
     SCCD_CUDA(cudaMemcpyAsync(
         c->h_counters, c->b_counters.ptr, sizeof(NarrowCounters), cudaMemcpyDeviceToHost,
         c->stream));
     SCCD_CUDA(cudaStreamSynchronize(c->stream));
+    // the last round only hands work on when a path outgrows the lane state: rerun it
+    for (int extra = 0; c->h_counters->n_items[kNarrowRounds] != 0 && c->h_counters->overflow != 2;
+         extra++) {
+        if (extra > 64)
+            throw std::runtime_error("narrow phase: bisection deeper than 8192 levels");
+        launch_narrow_extra_round(
+            kind == SCCD_VF, in, P, c->b_counters.as<NarrowCounters>(),
+            c->b_items[0].as<WorkItem>(), c->b_items[1].as<WorkItem>(), c->item_cap, extra,
+            d_toi_per_query, checks, c->num_sms, c->stream, c->lc);
+        SCCD_CUDA(cudaMemcpyAsync(
+            c->h_counters, c->b_counters.ptr, sizeof(NarrowCounters), cudaMemcpyDeviceToHost,
+            c->stream));
+        SCCD_CUDA(cudaStreamSynchronize(c->stream));
+    }
     const NarrowCounters& r = *c->h_counters;
     c->stats.n_box_checks[kind] += (int64_t)r.box_checks;
     c->stats.n_donated[kind] += (int64_t)r.donated;
@@ -842,7 +852,7 @@ void narrow_run(
         c->stats.queue_overflow = 1;
     if (r.overflow == 2)
         throw std::runtime_error(
-            "narrow phase: work queue too small to re-root a sub-tree deeper than 128 levels; "
+            "narrow phase: item list too small to hand on a sub-tree deeper than 128 levels; "
             "raise it with sccd_set_queue_capacity");
     if (r.toi < *toi_inout)
         *toi_inout = r.toi;

@@ -222,35 +222,29 @@ struct NarrowParams {
     int flags;      // debug knobs (SCCD_NP_FLAGS env): 1 = never donate
 };
 
-// Bounded global work queue of sub-boxes handed between lanes (56-byte payload, the size
-// of the reference's CCDDomain, plus a ready ticket).
+// A pending sub-box of a query, handed from one round of the narrow phase to the next
+// (56-byte payload, the size of the reference's CCDDomain).
 struct __align__(16) WorkItem {
     double lo[3];
     double w[3];
-    unsigned long long ready; // ticket + 1 once the payload is visible
+    unsigned long long pad0;
     uint32_t query;
-    uint32_t pad;
+    uint32_t pad1;
 };
 static_assert(sizeof(WorkItem) == 64, "WorkItem");
 
-// Every hot word sits in its own 128-byte line: idle warps poll q_tail / q_head /
-// outstanding while busy lanes read toi / hungry, and sharing a line made every busy-lane
-// read queue behind thousands of polls.
+// Rounds of one narrow-phase batch (see narrow.cu); the last one has no check budget.
+constexpr int kNarrowRounds = 5;
+
+// Every hot word sits in its own 128-byte line.
 struct alignas(128) NarrowCounters {
-    alignas(128) unsigned long long next_query; // next unclaimed query index
-    alignas(128) unsigned long long done;       // queries completely solved
-    alignas(128) double toi;                    // shared earliest toi
-    alignas(128) int overflow;                  // a donation was refused (ring full)
+    alignas(128) double toi;                          // shared earliest toi
+    alignas(128) unsigned long long next[kNarrowRounds];      // next unclaimed work index
+    alignas(128) unsigned long long n_items[kNarrowRounds + 1]; // [r] = items round r reads
+    alignas(128) int overflow;                        // an item list was full (work kept local)
     unsigned long long box_checks;
     unsigned long long donated;
     unsigned long long capped;
-};
-
-// One bounded ring of donated sub-boxes per CTA; tickets never repeat (the words persist
-// across launches), head == tail whenever no kernel is running.
-struct alignas(128) CtaQueue {
-    alignas(128) unsigned long long tail; // tickets reserved by producers (any CTA)
-    alignas(128) unsigned long long head; // tickets reserved by consumers (this CTA)
 };
 
 // ---- kernel launchers (defined in the .cu files) -----------------------------------
@@ -330,12 +324,20 @@ struct NarrowInput {
     const double* queries = nullptr;
     long long n = 0;
 };
-int narrow_grid_size(int num_sms); // CTAs (= rings) of the persistent narrow-phase kernel
-// pend: one uint32 per query (scratch, no initialisation needed)
+// Enqueues every round of one batch.  items[0/1]: two lists of item_cap WorkItems each.
+// After the batch, counters->n_items[kNarrowRounds] != 0 means the last round had to hand
+// work on (path deeper than the lane state can track): run launch_narrow_extra_round until
+// it is zero.
 void launch_narrow_phase(
     bool is_vf, const NarrowInput& in, const NarrowParams& p, NarrowCounters* counters,
-    CtaQueue* queues, WorkItem* rings, int ring_cap, unsigned int* pend, double* toi_per_query,
+    WorkItem* items0, WorkItem* items1, unsigned long long item_cap, double* toi_per_query,
     unsigned int* checks_per_query, int num_sms, cudaStream_t s, LaunchCounter& lc);
+// moves n_items[kNarrowRounds] to n_items[kNarrowRounds - 1] and reruns the last round
+void launch_narrow_extra_round(
+    bool is_vf, const NarrowInput& in, const NarrowParams& p, NarrowCounters* counters,
+    WorkItem* items0, WorkItem* items1, unsigned long long item_cap, int extra_index,
+    double* toi_per_query, unsigned int* checks_per_query, int num_sms, cudaStream_t s,
+    LaunchCounter& lc);
 void launch_fill_f64(double* p, long long n, double v, cudaStream_t s, LaunchCounter& lc);
 // compacts (pair, toi) of queries with toi < 1 ; *d_count receives the number
 void launch_compact_collisions(

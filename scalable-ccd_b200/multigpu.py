@@ -1,7 +1,7 @@
 """Multi-GPU orchestration: one process per GPU, torch.distributed (NCCL on GPUs, gloo in
 the CPU tests) for the only exchanges the path has:
 
-  1. the earliest-TOI all-reduce(min) -- 8 bytes;
+  1. the earliest-TOI all-reduce(min) at the end of the step -- 8 bytes;
   2. an all-gather of per-rank pair counts -- 8 bytes per rank;
   3. an order-preserving all-to-all that evens out the candidate pairs before the narrow
      phase (the sweep is sharded by estimated sweep work, which does not equalise pairs);
@@ -57,9 +57,14 @@ def rebalance(items, group=None):
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     n = torch.tensor([items.shape[0]], dtype=torch.int64, device=items.device)
-    counts = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(counts, n, group=group)
-    counts = [int(c.item()) for c in counts]
+    if items.is_cuda:   # one collective, one host sync
+        allc = torch.empty(world, dtype=torch.int64, device=items.device)
+        dist.all_gather_into_tensor(allc, n, group=group)
+        counts = [int(c) for c in allc.tolist()]
+    else:
+        counts = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(counts, n, group=group)
+        counts = [int(c.item()) for c in counts]
     send, recv = balance_plan(counts, rank)
     out = torch.empty((sum(recv),) + tuple(items.shape[1:]), dtype=items.dtype, device=items.device)
     dist.all_to_all_single(out, items.contiguous(), recv, send, group=group)
@@ -200,9 +205,12 @@ class ShardedCCD:
                     toi = ctx.narrow_phase(kind, mine.data_ptr(), int(mine.shape[0]), ms, max_iter,
                                            tol, allow_zero_toi, toi)
             mark("narrow_" + tag)
-            if self.world > 1:   # the next pass prunes with the global bound
-                toi = allreduce_min(toi, dev, self.group)
-            mark("allreduce_" + tag)
+        # ONE all-reduce at the end: the edge-edge pass prunes with this rank's own vertex-face
+        # bound, which changes no result (the minimum is order-independent) and saves a
+        # collective + host sync in the middle of the step
+        if self.world > 1:
+            toi = allreduce_min(toi, dev, self.group)
+        mark("allreduce")
         if marks:
             torch.cuda.synchronize()
             info["ms"] = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(marks, marks[1:])}
