@@ -56,6 +56,8 @@ struct sccd_ctx {
     std::string error;
 
     size_t memory_limit = 0;
+    size_t mem_free = 0, mem_total = 0;   // last cudaMemGetInfo() answer ...
+    unsigned long long mem_epoch = 0;     // ... and the allocation epoch (+1) it was taken at
     int64_t max_pairs_per_chunk = 0;
     int64_t queue_cap = 0;
     int rank = 0, world = 1;
@@ -103,6 +105,7 @@ struct sccd_ctx {
     int shard_lo = 0, shard_hi = 0, bp_cursor = 0;
     unsigned long long bp_total = 0, bp_emitted = 0;
     DevBuf b_counts, b_offsets, b_scan_temp, b_pairs, b_small;
+    DevBuf b_stage_pairs, b_stage_tags, b_stage_count; // count pass -> place pass
     int* h_small = nullptr; // pinned scratch for tiny D2H results
 
     // narrow-phase state
@@ -214,8 +217,13 @@ void kt_resolve(sccd_ctx* c)
 
 size_t budget_bytes(sccd_ctx* c)
 {
-    size_t free_b = 0, total_b = 0;
-    SCCD_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    size_t free_b = c->mem_free, total_b = c->mem_total;
+    if (c->mem_epoch != alloc_epoch() + 1) {
+        SCCD_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        c->mem_free = free_b;
+        c->mem_total = total_b;
+        c->mem_epoch = alloc_epoch() + 1;
+    }
     // memory_handler.cpp:11-30: 95 % of what is free, or the user's limit if smaller
     size_t avail = (size_t)(0.95 * (double)free_b);
     if (c->memory_limit) {
@@ -682,9 +690,13 @@ void broad_phase_begin(sccd_ctx* c, int kind)
     SCCD_CUDA(cudaMemsetAsync(c->b_counts.as<uint32_t>() + m, 0, 4, c->stream));
     unsigned long long* d_cand = reinterpret_cast<unsigned long long*>(c->b_small.as<char>() + 128);
     SCCD_CUDA(cudaMemsetAsync(d_cand, 0, 8, c->stream));
+    c->b_stage_pairs.reserve(sweep_stage_pair_bytes(m));
+    c->b_stage_tags.reserve(sweep_stage_tag_bytes(m));
+    c->b_stage_count.reserve(sweep_stage_tiles(m) * 4);
     const size_t kt = kt_begin(c, &c->stats.ms_k_sweep_count[sk]);
     launch_sweep_count(
-        L, c->shard_lo, c->shard_hi, c->b_counts.as<uint32_t>(), d_cand, c->stream, c->lc);
+        L, c->shard_lo, c->shard_hi, c->b_counts.as<uint32_t>(), d_cand, c->b_stage_pairs.ptr,
+        c->b_stage_tags.ptr, c->b_stage_count.as<uint32_t>(), c->stream, c->lc);
     kt_end(c, kt);
     launch_scan_u32_to_u64(
         c->b_counts.as<uint32_t>(), c->b_offsets.as<unsigned long long>(), m,
@@ -751,7 +763,8 @@ void broad_phase_partial(sccd_ctx* c, const sccd_pair** d_pairs, int64_t* n_pair
         const size_t kt = kt_begin(c, &c->stats.ms_k_sweep_fill[sk]);
         launch_sweep_fill(
             L, c->shard_lo, c->bp_cursor, end, c->b_offsets.as<unsigned long long>(),
-            c->b_pairs.as<sccd_pair>(), c->stream, c->lc);
+            c->b_pairs.as<sccd_pair>(), c->b_stage_pairs.ptr, c->b_stage_tags.ptr,
+            c->b_stage_count.as<uint32_t>(), c->stream, c->lc);
         kt_end(c, kt);
     }
     c->bp_cursor = end;
@@ -769,10 +782,10 @@ void narrow_setup(sccd_ctx* c, long long n_queries)
     c->b_counters.reserve(sizeof(NarrowCounters));
     // two bounded lists of sub-boxes handed from round to round; sccd_set_queue_capacity gives
     // the number of items of each (MemoryHandler::MAX_UNIT_SIZE analogue).  Default: one item
-    // per 4 queries, at least 64 Ki, at most 16 Mi (1 GiB per list).
+    // per query, at least 1 Mi (64 MiB per list), at most 16 Mi (1 GiB per list).
     long long cap = c->queue_cap > 0
         ? c->queue_cap
-        : std::min<long long>(std::max<long long>(n_queries / 4, 1 << 16), 1 << 24);
+        : std::min<long long>(std::max<long long>(n_queries, 1 << 20), 1 << 24);
     cap = std::max<long long>(cap, 64);
     if ((unsigned long long)cap != c->item_cap || !c->b_items[0].ptr) {
         c->b_items[0].reserve((size_t)cap * sizeof(WorkItem));

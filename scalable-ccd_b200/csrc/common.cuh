@@ -30,6 +30,14 @@ inline void check(cudaError_t e, const char* what, const char* file, int line)
 #define SCCD_CUDA(expr) ::sccd::check((expr), #expr, __FILE__, __LINE__)
 
 // ---- grow-only device buffer (kept across calls: frame-to-frame reuse) -----------
+// bumped by every (re)allocation: lets the context reuse its last cudaMemGetInfo() answer
+// (the call takes milliseconds once gigabytes are mapped) while nothing was allocated
+inline unsigned long long& alloc_epoch()
+{
+    static unsigned long long e = 0;
+    return e;
+}
+
 struct DevBuf {
     void* ptr = nullptr;
     size_t cap = 0;
@@ -56,6 +64,7 @@ struct DevBuf {
                 SCCD_CUDA(cudaMalloc(&ptr, want));
             }
             cap = want;
+            alloc_epoch()++;
         }
         return ptr;
     }
@@ -219,7 +228,7 @@ struct NarrowParams {
     int max_iter;   // < 0: unlimited
     int allow_zero_toi;
     int use_ms;     // ms > 0 (selects the error filter, root_finder.cu:95-122)
-    int flags;      // debug knobs (SCCD_NP_FLAGS env): 1 = never donate
+    int flags;      // debug knobs (SCCD_NP_FLAGS env), see narrow.cu
 };
 
 // A pending sub-box of a query, handed from one round of the narrow phase to the next
@@ -294,14 +303,20 @@ void launch_sort_and_gather(
 // window[i] = number of candidates after owner i whose f32 xmin <= owner's f32 xmax
 void launch_sweep_windows(
     const SortedList& L, uint32_t* window, cudaStream_t s, LaunchCounter& lc);
+// Staging area between the count and the place pass (see sweep.cu): sizes for `owners` owners.
+size_t sweep_stage_tiles(int owners);
+size_t sweep_stage_pair_bytes(int owners);
+size_t sweep_stage_tag_bytes(int owners);
 void launch_sweep_count(
     const SortedList& L, int owner_lo, int owner_hi, uint32_t* counts,
-    unsigned long long* n_candidates, cudaStream_t s, LaunchCounter& lc);
+    unsigned long long* n_candidates, void* stage_pairs, void* stage_tags, uint32_t* stage_count,
+    cudaStream_t s, LaunchCounter& lc);
 // counts / offsets are indexed relative to the first owner of the count pass (shard_lo);
 // the fill of owner range [owner_lo, owner_hi) writes pairs[offsets[i] - offsets[owner_lo]..).
 void launch_sweep_fill(
     const SortedList& L, int shard_lo, int owner_lo, int owner_hi,
-    const unsigned long long* offsets, sccd_pair* pairs, cudaStream_t s, LaunchCounter& lc);
+    const unsigned long long* offsets, sccd_pair* pairs, void* stage_pairs, void* stage_tags,
+    uint32_t* stage_count, cudaStream_t s, LaunchCounter& lc);
 size_t scan_temp_bytes(int n);
 // offsets[0..n] = exclusive prefix sum of counts[0..n) (offsets[n] = total)
 void launch_scan_u32_to_u64(

@@ -19,9 +19,13 @@
 //     ballot-compacted into a per-warp shared queue -- the "tiniest queue" -- and drained 32
 //     at a time with ALL lanes running the exact double test + vertex-sharing test, so the
 //     rare expensive path never diverges;
-//   * output is count -> exclusive scan -> fill: the pair list is exactly sized, ordered by
+//   * output is count -> exclusive scan -> place: the pair list is exactly sized, ordered by
 //     (owner position, candidate position) and therefore deterministic; no global atomics
-//     and no giant memset; 64-bit offsets.
+//     and no giant memset; 64-bit offsets.  The sweep itself runs ONCE: the count pass parks
+//     every pair it finds, tagged (owner, rank within the owner), in a fixed-size staging
+//     area of its tile, and the place pass only moves the parked pairs to offsets[owner] +
+//     rank.  A tile whose pairs outgrow its staging area (kStage) is swept again by the
+//     place pass -- the exception, not the rule.
 //
 // The emitted SET equals the reference's: every pair with closed overlap on x, y, z
 // (cuda/broad_phase/aabb.cuh:100-104, sweep.cu:131,173), valid list membership
@@ -42,20 +46,30 @@ namespace {
 constexpr int kTile = 256; // owners per CTA == threads per CTA
 constexpr int kWarps = kTile / 32;
 constexpr int kQueueCap = 64;
+constexpr int kStage = 1024; // pairs a tile can park between the count and the place pass
 constexpr int kRelBits = 27; // candidate position relative to the tile start
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kRankBits = 24; // staging tag = owner-in-tile << 24 | rank within the owner
 
 struct SweepSmem {
     unsigned long long o_off[kTile];
     uint32_t o_cnt[kTile];
     uint32_t q[kWarps][kQueueCap];
+    uint32_t staged; // pairs this tile has parked (or tried to park) so far
+};
+
+struct Staging {
+    sccd_pair* pairs = nullptr; // kStage per tile
+    uint32_t* tags = nullptr;   // kStage per tile
+    uint32_t* count = nullptr;  // one per tile; > kStage: the tile overflowed
 };
 
 // Exact test of up to 32 queued (owner lane, candidate) entries, one per lane.
 template <bool FILL, bool TWO_LISTS>
 __device__ __forceinline__ void drain32(
     SweepSmem& sm, const BoxArrays& box, int tile0, int warp, int lane, uint32_t entry,
-    bool active, sccd_pair* __restrict__ pairs)
+    bool active, sccd_pair* __restrict__ pairs, sccd_pair* __restrict__ st_pairs,
+    uint32_t* __restrict__ st_tags)
 {
     const int ol = active ? (int)(entry >> kRelBits) : 0;
     const int t = warp * 32 + ol;
@@ -103,26 +117,50 @@ __device__ __forceinline__ void drain32(
             sm.o_cnt[t] = cur + tot;
         __syncwarp();
     } else {
+        const uint32_t cur = active ? sm.o_cnt[t] : 0;
+        __syncwarp();
+        if (hits) {
+            // park the pairs of this batch in the tile's staging area
+            uint32_t base = 0;
+            const int first = __ffs(hits) - 1;
+            if (lane == first)
+                base = atomicAdd(&sm.staged, (uint32_t)__popc(hits));
+            base = __shfl_sync(kFull, base, first);
+            const uint32_t slot = base + __popc(hits & ((1u << lane) - 1));
+            const uint32_t rank = cur + (uint32_t)__popc(mine & ((1u << lane) - 1));
+            if (hit && slot < (uint32_t)kStage && rank < (1u << kRankBits)) {
+                const int mn = min(ea, eb), mx = max(ea, eb);
+                sccd_pair p;
+                p.a = TWO_LISTS ? (-mn - 1) : mn;
+                p.b = mx;
+                st_pairs[slot] = p;
+                st_tags[slot] = ((uint32_t)t << kRankBits) | rank;
+            }
+            if (hit && rank >= (1u << kRankBits))
+                atomicAdd(&sm.staged, (uint32_t)kStage); // cannot be tagged: force a re-sweep
+        }
         if (leader && tot)
-            sm.o_cnt[t] += tot;
+            sm.o_cnt[t] = cur + tot;
         __syncwarp();
     }
 }
 
+// Sweep of the tile of kTile owners starting at tile0; only owners in [owner_lo, owner_hi)
+// take part.  FILL = false: count (counts[]) and park the pairs (staging, st_*);
+// FILL = true: write the pairs of the chunk that starts at owner chunk_lo to pairs[].
 template <bool FILL, bool TWO_LISTS>
-__global__ void __launch_bounds__(kTile) sweep_kernel(
-    PrefilterArrays pf, BoxArrays box, int n, int shard_lo, int owner_lo, int owner_hi,
-    uint32_t* __restrict__ counts, const unsigned long long* __restrict__ offsets,
-    sccd_pair* __restrict__ pairs, unsigned long long* __restrict__ n_candidates)
+__device__ __forceinline__ void sweep_tile(
+    SweepSmem& sm, const PrefilterArrays& pf, const BoxArrays& box, int n, int shard_lo,
+    int tile0, int owner_lo, int owner_hi, int chunk_lo, uint32_t* __restrict__ counts,
+    const unsigned long long* __restrict__ offsets, sccd_pair* __restrict__ pairs,
+    unsigned long long* __restrict__ n_candidates, sccd_pair* __restrict__ st_pairs,
+    uint32_t* __restrict__ st_tags)
 {
-    __shared__ SweepSmem sm;
-
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int tile0 = owner_lo + blockIdx.x * kTile;
     const int i = tile0 + tid;
-    const bool valid = i < owner_hi;
+    const bool valid = i >= owner_lo && i < owner_hi;
 
     uint32_t my_reach = 0, my_flags = 0;
     float4 my = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -131,7 +169,7 @@ __global__ void __launch_bounds__(kTile) sweep_kernel(
         my_flags = __ldg(&pf.key[i]) & ((1u << kKeyFlagBits) - 1u);
         my = __ldg(&pf.yz[i]);
         if (FILL) // position of this owner's first pair inside the chunk being filled
-            sm.o_off[tid] = offsets[i - shard_lo] - offsets[owner_lo - shard_lo];
+            sm.o_off[tid] = offsets[i - shard_lo] - offsets[chunk_lo - shard_lo];
     }
     sm.o_cnt[tid] = 0;
     __syncwarp();
@@ -167,7 +205,8 @@ __global__ void __launch_bounds__(kTile) sweep_kernel(
         qn += __popc(mask);
         __syncwarp();
         if (qn >= 32) {
-            drain32<FILL, TWO_LISTS>(sm, box, tile0, warp, lane, q[lane], true, pairs);
+            drain32<FILL, TWO_LISTS>(
+                sm, box, tile0, warp, lane, q[lane], true, pairs, st_pairs, st_tags);
             tested += 32;
             const int r = qn - 32;
             const uint32_t v = (lane < r) ? q[32 + lane] : 0u;
@@ -180,7 +219,8 @@ __global__ void __launch_bounds__(kTile) sweep_kernel(
     }
     if (qn > 0) {
         drain32<FILL, TWO_LISTS>(
-            sm, box, tile0, warp, lane, lane < qn ? q[lane] : 0u, lane < qn, pairs);
+            sm, box, tile0, warp, lane, lane < qn ? q[lane] : 0u, lane < qn, pairs, st_pairs,
+            st_tags);
         tested += qn;
     }
     if (!FILL) {
@@ -190,6 +230,57 @@ __global__ void __launch_bounds__(kTile) sweep_kernel(
         if (lane == 0 && tested && n_candidates)
             atomicAdd(n_candidates, tested);
     }
+}
+
+
+// count pass: one tile per CTA, tiles start at shard_lo
+template <bool TWO_LISTS>
+__global__ void __launch_bounds__(kTile) sweep_count_kernel(
+    PrefilterArrays pf, BoxArrays box, int n, int shard_lo, int shard_hi,
+    uint32_t* __restrict__ counts, unsigned long long* __restrict__ n_candidates, Staging st)
+{
+    __shared__ SweepSmem sm;
+    if (threadIdx.x == 0)
+        sm.staged = 0;
+    __syncthreads();
+    const int tile0 = shard_lo + blockIdx.x * kTile;
+    sweep_tile<false, TWO_LISTS>(
+        sm, pf, box, n, shard_lo, tile0, shard_lo, shard_hi, shard_lo, counts, nullptr, nullptr,
+        n_candidates, st.pairs + (size_t)blockIdx.x * kStage,
+        st.tags + (size_t)blockIdx.x * kStage);
+    __syncthreads();
+    if (threadIdx.x == 0)
+        st.count[blockIdx.x] = sm.staged;
+}
+
+// place pass over the count tiles that overlap the owner chunk [owner_lo, owner_hi)
+template <bool TWO_LISTS>
+__global__ void __launch_bounds__(kTile) sweep_place_kernel(
+    PrefilterArrays pf, BoxArrays box, int n, int shard_lo, int first_tile, int owner_lo,
+    int owner_hi, const unsigned long long* __restrict__ offsets, sccd_pair* __restrict__ pairs,
+    Staging st)
+{
+    __shared__ SweepSmem sm;
+    const int tile = first_tile + blockIdx.x;
+    const int tile0 = shard_lo + tile * kTile;
+    const uint32_t staged = st.count[tile];
+    if (staged <= (uint32_t)kStage) {
+        // the usual case: move the parked pairs to offsets[owner] + rank
+        const sccd_pair* sp = st.pairs + (size_t)tile * kStage;
+        const uint32_t* stg = st.tags + (size_t)tile * kStage;
+        const unsigned long long chunk_base = offsets[owner_lo - shard_lo];
+        for (uint32_t e = threadIdx.x; e < staged; e += kTile) {
+            const uint32_t tag = stg[e];
+            const int owner = tile0 + (int)(tag >> kRankBits);
+            if (owner >= owner_lo && owner < owner_hi)
+                pairs[offsets[owner - shard_lo] - chunk_base + (tag & ((1u << kRankBits) - 1u))] =
+                    sp[e];
+        }
+        return;
+    }
+    sweep_tile<true, TWO_LISTS>(
+        sm, pf, box, n, shard_lo, tile0, owner_lo, owner_hi, owner_lo, nullptr, offsets, pairs,
+        nullptr, nullptr, nullptr);
 }
 
 // window[i] = #records j > i with key_j <= reach_i (sweep work estimate used to balance
@@ -229,23 +320,17 @@ __global__ void find_chunk_end_kernel(
     out[0] = a;
 }
 
-template <bool FILL, bool TWO>
-void launch_sweep(
-    const SortedList& L, int shard_lo, int owner_lo, int owner_hi, uint32_t* counts,
-    const unsigned long long* offsets, sccd_pair* pairs, unsigned long long* n_candidates,
-    cudaStream_t s, LaunchCounter& lc)
-{
-    const int owners = owner_hi - owner_lo;
-    if (owners <= 0)
-        return;
-    const int grid = (owners + kTile - 1) / kTile;
-    sweep_kernel<FILL, TWO><<<grid, kTile, 0, s>>>(
-        L.pf, L.box, L.n, shard_lo, owner_lo, owner_hi, counts, offsets, pairs, n_candidates);
-    SCCD_CUDA(cudaGetLastError());
-    lc.n++;
-}
-
 } // namespace
+
+size_t sweep_stage_tiles(int owners) { return (size_t)((owners + kTile - 1) / kTile); }
+size_t sweep_stage_pair_bytes(int owners)
+{
+    return sweep_stage_tiles(owners) * kStage * sizeof(sccd_pair);
+}
+size_t sweep_stage_tag_bytes(int owners)
+{
+    return sweep_stage_tiles(owners) * kStage * sizeof(uint32_t);
+}
 
 void launch_sweep_windows(
     const SortedList& L, uint32_t* window, cudaStream_t s, LaunchCounter& lc)
@@ -259,28 +344,51 @@ void launch_sweep_windows(
 
 void launch_sweep_count(
     const SortedList& L, int owner_lo, int owner_hi, uint32_t* counts,
-    unsigned long long* n_candidates, cudaStream_t s, LaunchCounter& lc)
+    unsigned long long* n_candidates, void* stage_pairs, void* stage_tags, uint32_t* stage_count,
+    cudaStream_t s, LaunchCounter& lc)
 {
     if (L.n >= (1 << kRelBits))
         throw std::runtime_error("sweep: more than 2^27 records in one list is not supported");
+    const int owners = owner_hi - owner_lo;
+    if (owners <= 0)
+        return;
+    Staging st;
+    st.pairs = (sccd_pair*)stage_pairs;
+    st.tags = (uint32_t*)stage_tags;
+    st.count = stage_count;
+    const int grid = (owners + kTile - 1) / kTile;
     if (L.two_lists)
-        launch_sweep<false, true>(
-            L, owner_lo, owner_lo, owner_hi, counts, nullptr, nullptr, n_candidates, s, lc);
+        sweep_count_kernel<true><<<grid, kTile, 0, s>>>(
+            L.pf, L.box, L.n, owner_lo, owner_hi, counts, n_candidates, st);
     else
-        launch_sweep<false, false>(
-            L, owner_lo, owner_lo, owner_hi, counts, nullptr, nullptr, n_candidates, s, lc);
+        sweep_count_kernel<false><<<grid, kTile, 0, s>>>(
+            L.pf, L.box, L.n, owner_lo, owner_hi, counts, n_candidates, st);
+    SCCD_CUDA(cudaGetLastError());
+    lc.n++;
 }
 
 void launch_sweep_fill(
     const SortedList& L, int shard_lo, int owner_lo, int owner_hi,
-    const unsigned long long* offsets, sccd_pair* pairs, cudaStream_t s, LaunchCounter& lc)
+    const unsigned long long* offsets, sccd_pair* pairs, void* stage_pairs, void* stage_tags,
+    uint32_t* stage_count, cudaStream_t s, LaunchCounter& lc)
 {
+    if (owner_hi <= owner_lo)
+        return;
+    Staging st;
+    st.pairs = (sccd_pair*)stage_pairs;
+    st.tags = (uint32_t*)stage_tags;
+    st.count = stage_count;
+    const int first_tile = (owner_lo - shard_lo) / kTile;
+    const int last_tile = (owner_hi - 1 - shard_lo) / kTile;
+    const int grid = last_tile - first_tile + 1;
     if (L.two_lists)
-        launch_sweep<true, true>(
-            L, shard_lo, owner_lo, owner_hi, nullptr, offsets, pairs, nullptr, s, lc);
+        sweep_place_kernel<true><<<grid, kTile, 0, s>>>(
+            L.pf, L.box, L.n, shard_lo, first_tile, owner_lo, owner_hi, offsets, pairs, st);
     else
-        launch_sweep<true, false>(
-            L, shard_lo, owner_lo, owner_hi, nullptr, offsets, pairs, nullptr, s, lc);
+        sweep_place_kernel<false><<<grid, kTile, 0, s>>>(
+            L.pf, L.box, L.n, shard_lo, first_tile, owner_lo, owner_hi, offsets, pairs, st);
+    SCCD_CUDA(cudaGetLastError());
+    lc.n++;
 }
 
 void launch_find_chunk_end(
