@@ -30,18 +30,25 @@ UNIT = "ms/step"
 PARAMS = dict(ms=0.0, max_iter=-1, tol=1e-6, allow_zero_toi=True)  # tests/test_narrow_phase.cu:41-45
 
 
+DESCS = {
+    "small": "cloth 31x31 over UV sphere (~6K boxes)",
+    "c1": "config 1: cloth 101x101 over UV sphere (~62K boxes)",
+    "c2": "config 2: cloth-ball, cloth 409x409 + icosphere L5 (~1.06M primitives)",
+    "c3": "config 3: 10,000 x 602-primitive blobs, heavy-tailed pile (~6.0M boxes)",
+    "c4": "config 4: 83,000 blobs in an x-slab (~50M boxes)",
+}
+
+
+def make_desc(name):
+    return DESCS[name]
+
+
 def make_scene(scenes, name):
-    if name == "small":
-        return scenes.cloth_on_sphere(31, seed=7, sphere="uv"), "cloth 31x31 over UV sphere (~6K boxes)"
-    if name == "c1":
-        return scenes.scene_c1(), "config 1: cloth 101x101 over UV sphere (~62K boxes)"
-    if name == "c2":
-        return scenes.scene_c2(), "config 2: cloth-ball, cloth 409x409 + icosphere L5 (~1.06M primitives)"
-    if name == "c3":
-        return scenes.scene_c3(), "config 3: 10,000 x 602-primitive blobs, heavy-tailed pile (~6.0M boxes)"
-    if name == "c4":
-        return scenes.scene_c4(), "config 4: 83,000 blobs in an x-slab (~50M boxes)"
-    raise SystemExit(f"unknown workload {name}")
+    if name not in DESCS:
+        raise SystemExit(f"unknown workload {name}")
+    gen = {"small": lambda: scenes.cloth_on_sphere(31, seed=7, sphere="uv"), "c1": scenes.scene_c1,
+           "c2": scenes.scene_c2, "c3": scenes.scene_c3, "c4": scenes.scene_c4}[name]
+    return gen(), DESCS[name]
 
 
 class ClockSampler:
@@ -158,12 +165,23 @@ def cpu_step(orc, scene):
 
 
 def run_reference(args, rank, world):
+    """Reference arm: the reference's own CPU implementation of the path on the host cores
+    (oracle/_ref when it was built, else the oracle port), all host threads.  Config 4 is too
+    big for a CPU step of a few minutes, so its step is a BOUNDED SAMPLE: the same pile
+    generator with 1/16 of the instances (same density), time scaled by 16 -- stated in
+    `sample`."""
     if rank != 0:
         return
     from _pkg import load_package
     from oracle import orc
     sccd = load_package()
-    scene, desc = make_scene(sccd.scenes, args.workload)
+    scale = 1
+    if args.workload == "c4":
+        scale = 16
+        scene = sccd.scenes.scene_c4(n_inst=83_000 // scale)
+        desc = make_desc("c4")
+    else:
+        scene, desc = make_scene(sccd.scenes, args.workload)
     budget_s = 150.0
     t_start = time.perf_counter()
     steps = []
@@ -174,9 +192,13 @@ def run_reference(args, rank, world):
             steps.append(r)
         if time.perf_counter() - t_start > budget_s and steps:
             break
-    ms = statistics.mean(s["ms"] for s in steps)
+    ms = statistics.mean(s["ms"] for s in steps) * scale
     cores = orc.lib().orc_num_threads()
-    sample = (f"{len(steps)} full step(s) of the workload (time-bounded to ~{int(budget_s)} s); "
+    what = (f"{len(steps)} full step(s) of the workload" if scale == 1 else
+            f"{len(steps)} step(s) of a 1/{scale} sample of the workload (same generator and "
+            f"density, {scene['V0'].shape[0] + scene['E'].shape[0] + scene['F'].shape[0]} boxes), "
+            f"time x{scale}")
+    sample = (f"{what} (time-bounded to ~{int(budget_s)} s); "
               f"broad phase = {steps[0]['kind']} CPU sort_and_sweep "
               f"({statistics.mean(s['broad_ms'] for s in steps):.0f} ms, oneTBB replaced by an OpenMP stub), "
               f"narrow phase = oracle port with OpenMP ({statistics.mean(s['narrow_ms'] for s in steps):.0f} ms; "
@@ -372,14 +394,16 @@ def main():
     stage_ms = {"build": avg("ms_build"), "sort": avg("ms_sort"), "sweep_vf": avg("ms_sweep", 0),
                 "sweep_ee": avg("ms_sweep", 1), "narrow_vf": avg("ms_narrow", 0),
                 "narrow_ee": avg("ms_narrow", 1), "total_device": avg("ms_total")}
-    # algorithmic bytes per launch (DESIGN.md "Rooflines")
+    # algorithmic bytes per launch.  The sweep reads each box once
+    # (64 B) in the pass that finds the pairs and writes each pair once (8 B) in the pass that
+    # places them; on N > 1 GPUs a rank's sweep / gather only covers its own share of the boxes.
     loc_pairs = [avg("n_pairs", 0), avg("n_pairs", 1)]
+    share = 1.0 / world
     alg_bytes = {
         "boxes": 48 * nV + 8 * nE + 12 * nF + 64 * (nV + nE + nF),
-        "gather": 2 * 64 * (nV + nE + nF),
-        "sweep_count_vf": 64 * n_boxes[0], "sweep_count_ee": 64 * n_boxes[1],
-        "sweep_fill_vf": 64 * n_boxes[0] + 8 * loc_pairs[0],
-        "sweep_fill_ee": 64 * n_boxes[1] + 8 * loc_pairs[1],
+        "gather": 2 * 64 * (nV + nE + nF) * share,
+        "sweep_count_vf": 64 * n_boxes[0] * share, "sweep_count_ee": 64 * n_boxes[1] * share,
+        "sweep_fill_vf": 8 * loc_pairs[0], "sweep_fill_ee": 8 * loc_pairs[1],
         "narrow_vf": (8 + 192 + 8) * loc_pairs[0], "narrow_ee": (8 + 192 + 8) * loc_pairs[1],
     }
     dom = max(k_ms, key=lambda k: k_ms[k])
@@ -403,8 +427,16 @@ def main():
                 "all_kernels": {k: {"ms": k_ms[k], "GBps": (alg_bytes[k] / (k_ms[k] * 1e-3) / 1e9
                                                              if k_ms[k] > 0 else 0.0)} for k in k_ms}}
     narrow_ms = k_ms["narrow_vf"] + k_ms["narrow_ee"]
-    # FP64 work of the narrow phase (96 / 84 arithmetic instr per box check)
+    # FP64 work of the narrow phase (96 / 84 arithmetic instr per box check) against
+    # the FP64 pipe rate measured on this device by a register-only DFMA micro-benchmark
     fp64_instr = 96 * n_checks[0] + 84 * n_checks[1]
+    dfma_peak = ctx.measure_fp64_peak() * world
+    fp64 = {"bound": "fp64 pipe", "kernel": "narrow_vf + narrow_ee",
+            "achieved": (fp64_instr / (narrow_ms * 1e-3)) if narrow_ms > 0 else None,
+            "peak": dfma_peak, "unit": "thread-level FP64 instr/s (peak: measured DFMA/s)",
+            "frac": (fp64_instr / (narrow_ms * 1e-3) / dfma_peak) if narrow_ms > 0 else None,
+            "note": "96 (VF) / 84 (EE) FP64 arithmetic instructions per box check, min/max and "
+                    "compares not counted"}
     line = {
         "metric": METRIC, "value": ms, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",
@@ -418,7 +450,7 @@ def main():
                 "note": ("whole job: each rank copies 1/N of the mesh H2D, NCCL all-gather of the "
                          "slices" if world > 1 else "pinned host mesh -> sccd_ccd_host")},
         "gpu_launches": int(avg("n_launches")) * args.steps,
-        "roofline": roofline,
+        "roofline": roofline, "roofline_fp64": fp64,
         "toi": toi, "n_pairs": n_pairs,
         "pairs_per_rank": (sharded.last if sharded else None),
         "stage_ms_per_rank": rank_stage_ms, "ms_steps_rank0": ms_steps,

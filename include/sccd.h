@@ -68,10 +68,10 @@ typedef struct {
     int64_t n_candidates[2]; /* f32-prefilter survivors that reached the exact test     */
     int64_t n_queries[2];    /* narrow-phase queries run                                */
     int64_t n_box_checks[2]; /* inclusion-function evaluations (ccd_kernel bodies)      */
-    int64_t n_donated[2];    /* sub-boxes handed to other lanes through the work queue  */
+    int64_t n_donated[2];    /* sub-boxes handed on to a later round through the item list */
     int64_t n_capped[2];     /* queries that hit max_iter (conservatively accepted)     */
     int64_t n_launches;      /* kernels this library launched in the call               */
-    int64_t queue_overflow;  /* 1 if the bounded work queue ever refused a donation     */
+    int64_t queue_overflow;  /* 1 if the bounded item list was ever full (work kept local) */
     float ms_build;          /* AABB build                                              */
     float ms_sort;           /* radix sort + record gather                              */
     float ms_sweep[2];       /* sweep count + scan + fill                               */
@@ -106,8 +106,9 @@ int sccd_set_memory_limit(sccd_ctx* ctx, size_t bytes);
  * cuda/broad_phase/broad_phase.cu:194-207). */
 int sccd_set_max_pairs_per_chunk(sccd_ctx* ctx, int64_t max_pairs);
 
-/* Capacity (items) of the bounded narrow-phase work queue (0 = default).  Replaces
- * MemoryHandler::MAX_UNIT_SIZE (cuda/memory_handler.cpp:81-122). */
+/* Capacity (items of 64 bytes) of each of the two bounded narrow-phase item lists
+ * (0 = default: one per query, 1 Mi .. 16 Mi).  Replaces MemoryHandler::MAX_UNIT_SIZE
+ * (cuda/memory_handler.cpp:81-122).  A full list never drops work: the lane keeps its tree. */
 int sccd_set_queue_capacity(sccd_ctx* ctx, int64_t items);
 
 /* Upper bound on the number of (y, z) sweep cells per list: 0 = automatic (about twice the
@@ -115,9 +116,13 @@ int sccd_set_queue_capacity(sccd_ctx* ctx, int64_t items);
  * not depend on it; it only changes how many candidates the sweep has to test. */
 int sccd_set_grid_cells(sccd_ctx* ctx, int max_cells);
 
-/* Multi-GPU sharding: this context sweeps only the rank-th of `world` owner slices
- * of each sorted list (slices balanced by sweep-window length) and therefore emits
- * a disjoint part of the global pair list.  rank 0 / world 1 = everything. */
+/* Multi-GPU sharding: this context makes, sorts and sweeps only the records of the rank-th of
+ * `world` contiguous (y, z) cell ranges of each list (ranges balanced by record count; every
+ * rank derives the same ranges from its own copy of the boxes, so there is no exchange) and
+ * therefore emits a disjoint part of the global pair list; the parts concatenated in rank
+ * order are the single-device list.  Lists with too few cells fall back to owner slices of
+ * the whole sorted list, balanced by sweep-window length.  Takes effect at the next
+ * sccd_build_boxes / sccd_set_boxes / sccd_broad_phase_begin.  rank 0 / world 1 = everything. */
 int sccd_set_shard(sccd_ctx* ctx, int rank, int world);
 
 /* ---- mesh + boxes --------------------------------------------------------------- */
@@ -231,6 +236,10 @@ int sccd_get_stats(const sccd_ctx* ctx, sccd_stats* out);
  * callers that compose the phase-level entry points reset them here. */
 int sccd_reset_stats(sccd_ctx* ctx);
 int sccd_synchronize(sccd_ctx* ctx);
+/* Measures the device's FP64 pipe rate (thread-level DFMA per second) with a register-only
+ * micro-benchmark: the compute roofline the narrow phase is reported against (the reference
+ * publishes none). */
+int sccd_measure_fp64_peak(sccd_ctx* ctx, double* dfma_per_second);
 /* "major.minor.patch sm_100a" */
 const char* sccd_version(void);
 

@@ -30,7 +30,7 @@ SYMBOLS = [
     "sccd_broad_phase_partial", "sccd_broad_phase_is_complete", "sccd_broad_phase",
     "sccd_narrow_phase", "sccd_narrow_phase_queries", "sccd_ccd", "sccd_ccd_collisions",
     "sccd_ccd_host", "sccd_ipc_ccd_strategy", "sccd_get_stats", "sccd_reset_stats",
-    "sccd_synchronize",
+    "sccd_synchronize", "sccd_measure_fp64_peak",
     "sccd_version",
 ]
 
@@ -289,6 +289,12 @@ class Context:
 
     def reset_stats(self):
         self._chk(self.L.sccd_reset_stats(self._h))
+
+    def measure_fp64_peak(self) -> float:
+        """thread-level DFMA per second of this device (register-only micro-benchmark)"""
+        v = C.c_double(0.0)
+        self._chk(self.L.sccd_measure_fp64_peak(self._h, C.byref(v)))
+        return v.value
 
     def synchronize(self):
         self._chk(self.L.sccd_synchronize(self._h))

@@ -1328,6 +1328,17 @@ int sccd_reset_stats(sccd_ctx* ctx)
     });
 }
 
+int sccd_measure_fp64_peak(sccd_ctx* ctx, double* dfma_per_second)
+{
+    return guarded(ctx, [&] {
+        if (!dfma_per_second)
+            throw std::invalid_argument("measure_fp64_peak: null output");
+        SCCD_CUDA(cudaStreamSynchronize(ctx->stream));
+        *dfma_per_second = measure_dfma_per_second(ctx->num_sms, ctx->stream);
+        return SCCD_OK;
+    });
+}
+
 int sccd_synchronize(sccd_ctx* ctx)
 {
     return guarded(ctx, [&] {

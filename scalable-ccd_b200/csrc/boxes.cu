@@ -110,7 +110,53 @@ __global__ void __launch_bounds__(kThreads) element_boxes_kernel(
     }
 }
 
+// FP64 pipe yardstick for the narrow-phase roofline: 8 independent DFMA chains per thread.
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5,
+           x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+        x0 = __fma_rn(x0, a, b);
+        x1 = __fma_rn(x1, a, b);
+        x2 = __fma_rn(x2, a, b);
+        x3 = __fma_rn(x3, a, b);
+        x4 = __fma_rn(x4, a, b);
+        x5 = __fma_rn(x5, a, b);
+        x6 = __fma_rn(x6, a, b);
+        x7 = __fma_rn(x7, a, b);
+    }
+    const double r = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (r == 123.456) // never true: keeps the chains alive
+        out[0] = r;
+}
+
 } // namespace
+
+double measure_dfma_per_second(int num_sms, cudaStream_t s)
+{
+    double* d = nullptr;
+    SCCD_CUDA(cudaMalloc(&d, 8));
+    cudaEvent_t a, b;
+    SCCD_CUDA(cudaEventCreate(&a));
+    SCCD_CUDA(cudaEventCreate(&b));
+    const int iters = 1 << 14, grid = num_sms * 8;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        SCCD_CUDA(cudaEventRecord(a, s));
+        dfma_peak_kernel<<<grid, 256, 0, s>>>(d, iters, 0.999999, 1e-9);
+        SCCD_CUDA(cudaEventRecord(b, s));
+        SCCD_CUDA(cudaEventSynchronize(b));
+        float ms = 0.f;
+        SCCD_CUDA(cudaEventElapsedTime(&ms, a, b));
+        if (rep > 0 && ms < best)
+            best = ms;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d);
+    // thread-level DFMA per second
+    return (double)grid * 256.0 * 8.0 * iters / (best * 1e-3);
+}
 
 void launch_mesh_boxes(
     const double* V0, const double* V1, int nV, double radius_up, VertexRec* vtab, double* vbox,

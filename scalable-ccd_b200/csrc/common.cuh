@@ -266,6 +266,9 @@ void launch_mesh_boxes(
     double* vbox /* 6*nV: min xyz, max xyz */, const int32_t* E, int nE, const int32_t* F,
     int nF, BoxArrays e_unsorted, BoxArrays vf_unsorted, cudaStream_t s, LaunchCounter& lc);
 
+// measured FP64 pipe rate (thread-level DFMA / s): the narrow phase's compute roofline
+double measure_dfma_per_second(int num_sms, cudaStream_t s);
+
 // ---- grid (csrc/grid.cu)
 // Statistics of a list (stats_identity() layout) over every stride-th box: they only steer
 // the grid and the key quantisation, both of which clamp, so a sample is as good as the whole.

@@ -79,6 +79,32 @@ def allreduce_min(value: float, device, group=None) -> float:
     return float(t.item())
 
 
+def gather_min_and_loads(value: float, loads, device, group=None):
+    """The step's single collective: every rank contributes (toi, its per-list query counts).
+    Returns (min toi, [per-rank load lists]); the loads steer the NEXT step's decision to
+    rebalance pairs (frame-to-frame coherence), so no extra collective sits inside a step."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    mine = torch.tensor([value] + [float(x) for x in loads], dtype=torch.float64, device=device)
+    out = torch.empty(world * mine.numel(), dtype=torch.float64, device=device)
+    if out.is_cuda:
+        dist.all_gather_into_tensor(out, mine, group=group)
+    else:
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine, group=group)
+        out = torch.cat(parts)
+    rows = out.view(world, -1).tolist()
+    return min(r[0] for r in rows), [[int(x) for x in r[1:]] for r in rows]
+
+
+def imbalance(loads) -> float:
+    """max / mean of the ranks' total loads (1.0 = perfectly even)."""
+    tot = [sum(r) for r in loads]
+    mean = sum(tot) / max(len(tot), 1)
+    return max(tot) / mean if mean > 0 else 1.0
+
+
 def pack_mesh(V0, V1, E, F, world: int, pin: bool = True):
     """[V0 | V1 | E | F] (column-major, as the C ABI takes them) in ONE flat byte tensor whose
     length is a multiple of 16 * world, plus the byte offset of each array."""
@@ -135,13 +161,22 @@ class _DevArray:
 class ShardedCCD:
     """ccd() over the GPUs of one box.  `ctx` is this rank's Context with the mesh uploaded."""
 
-    def __init__(self, ctx, group=None, rebalance_pairs: bool = True):
+    # pairs are redistributed before the narrow phase only when the previous step left one
+    # rank with more than this many times the mean number of queries
+    REBALANCE_ABOVE = 1.25
+
+    def __init__(self, ctx, group=None, rebalance_pairs="auto"):
         import torch.distributed as dist
         self.ctx = ctx
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.rebalance_pairs = rebalance_pairs and self.world > 1
+        # True / False, or "auto": decided from the load imbalance of the previous step.  The
+        # cell ranges are balanced by records, which usually balances the pairs well enough
+        # (config 4: within 8 %), and every mid-step collective is also a barrier that adds the
+        # ranks' sweep skew to the step.
+        self.mode = rebalance_pairs
+        self.rebalance_pairs = (rebalance_pairs is True) and self.world > 1
         self.last = {}
         self.profile = False      # per-stage device times of the last ccd() in self.last["ms"]
         self._mesh = None
@@ -209,7 +244,10 @@ class ShardedCCD:
         # bound, which changes no result (the minimum is order-independent) and saves a
         # collective + host sync in the middle of the step
         if self.world > 1:
-            toi = allreduce_min(toi, dev, self.group)
+            toi, loads = gather_min_and_loads(toi, info["pairs_local"], dev, self.group)
+            info["imbalance"] = imbalance(loads)
+            if self.mode == "auto":
+                self.rebalance_pairs = info["imbalance"] > self.REBALANCE_ABOVE
         mark("allreduce")
         if marks:
             torch.cuda.synchronize()

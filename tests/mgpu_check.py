@@ -25,8 +25,8 @@ single = ctx.ccd(**bench.PARAMS)                       # every rank: whole probl
 full = [ctx.broad_phase(0), ctx.broad_phase(1)] if name in ("c1", "small") else None
 sh = sccd.multigpu.ShardedCCD(ctx)
 out = {}
-for reb in (True, False):
-    sh.rebalance_pairs = reb
+for reb in (True, False, "auto"):
+    sh.mode = reb; sh.rebalance_pairs = reb is True
     toi = sh.ccd(**bench.PARAMS)
     assert toi == single, (toi, single)
     torch.cuda.synchronize(); dist.barrier()

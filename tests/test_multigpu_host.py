@@ -33,6 +33,10 @@ def _worker(rank, world, port, counts, q):
         items = torch.stack([mine, -mine], dim=1)            # (n_r, 2), global order = value
         out, seen = mg.rebalance(items)
         toi = mg.allreduce_min(0.25 + rank, torch.device("cpu"))
+        toi2, loads = mg.gather_min_and_loads(0.5 + rank, [10 * rank, 7], torch.device("cpu"))
+        assert toi2 == 0.5 and loads == [[10 * r, 7] for r in range(world)]
+        assert abs(mg.imbalance(loads) - (10 * (world - 1) + 7) /
+                   (sum(10 * r + 7 for r in range(world)) / world)) < 1e-12
         q.put((rank, out.numpy().copy(), seen, toi))
     finally:
         dist.destroy_process_group()
