@@ -817,7 +817,9 @@ void narrow_run(
     P.use_ms = ms > 0 ? 1 : 0;
     {
         const char* f = getenv("SCCD_NP_FLAGS");
-        P.flags = f ? atoi(f) : 0;
+        P.flags = f ? (int)strtoll(f, nullptr, 0) : 0;
+        const char* d = getenv("SCCD_NP_DEPTH"); // test hook: exercise the "path too deep" route
+        P.max_depth = d ? std::min(128, std::max(2, atoi(d))) : 128;
     }
 
     NarrowCounters init {};

@@ -229,6 +229,7 @@ struct NarrowParams {
     int allow_zero_toi;
     int use_ms;     // ms > 0 (selects the error filter, root_finder.cu:95-122)
     int flags;      // debug knobs (SCCD_NP_FLAGS env), see narrow.cu
+    int max_depth;  // levels a walk may track before handing on (<= 128; SCCD_NP_DEPTH env)
 };
 
 // A pending sub-box of a query, handed from one round of the narrow phase to the next

@@ -164,6 +164,87 @@ def test_iteration_cap_is_conservative(ctx, orc, sccd, torch_cuda):
         assert toi <= min(1.0, full.min())
 
 
+@pytest.fixture
+def np_env():
+    """Sets / restores the narrow-phase debug knobs (read by the library at every batch)."""
+    saved = {k: os.environ.get(k) for k in ("SCCD_NP_FLAGS", "SCCD_NP_DEPTH")}
+
+    def set_(flags=None, depth=None):
+        for k, v in (("SCCD_NP_FLAGS", flags), ("SCCD_NP_DEPTH", depth)):
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = str(v)
+    yield set_
+    for k, v in saved.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+
+
+# refill | first-round budget << 8 | later budget << 16 | never-cooperate << 24 |
+# log2(coop budget) - 3 << 25 | log2(coop limit) - 13 << 28
+VARIANTS = {"lane_only": 1 << 24, "tiny_budgets": 4 | (3 << 8) | (2 << 16) | (1 << 25),
+            "refill_every_lane": 1, "refill_all_idle": 32, "coop_big_budget": 5 << 25,
+            "coop_small_limit": 1 << 28}
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
+def test_narrow_phase_scheduling_does_not_change_results(ctx, orc, sccd, torch_cuda, np_env,
+                                                          variant):
+    """How the bisection trees are cut into rounds / items and which kernel (lane-per-tree or
+    warp-cooperative) walks them must not change a single bit of the per-query TOIs."""
+    ee, vf = sccd.scenes.queries_c5(1500, seed=9)
+    for kind, q in ((0, vf), (1, ee)):
+        q = q[orc.tractable(q, kind == 0, 0.0, 1e-6)]
+        np_env()
+        toi0, tpq0 = _narrow_gpu(ctx, torch_cuda, kind, q)
+        np_env(flags=VARIANTS[variant])
+        toi1, tpq1 = _narrow_gpu(ctx, torch_cuda, kind, q)
+        shared1 = ctx.narrow_phase_queries(kind, q)
+        np_env()
+        assert np.array_equal(tpq0, tpq1) and toi0 == toi1 == shared1
+        _, otpq, _ = orc.narrow_phase(q, kind == 0)
+        assert np.array_equal(tpq1, otpq)
+
+
+@pytest.mark.parametrize("flags", [0, 1 << 24])
+def test_paths_deeper_than_the_lane_state_are_handed_on(ctx, orc, sccd, torch_cuda, np_env, flags):
+    """With only 6 trackable levels every non-trivial tree outgrows the walk state in every
+    round, including the last: the boxes are handed on and the host keeps adding rounds."""
+    ee, vf = sccd.scenes.queries_c5(400, seed=21)
+    for kind, q in ((0, vf), (1, ee)):
+        q = q[orc.tractable(q, kind == 0, 0.0, 1e-6, limit=3000)]
+        assert len(q) > 100
+        np_env(flags=flags, depth=6)
+        toi, tpq = _narrow_gpu(ctx, torch_cuda, kind, q)
+        np_env()
+        otoi, otpq, _ = orc.narrow_phase(q, kind == 0)
+        assert np.array_equal(tpq, otpq) and toi == otoi
+
+
+def test_dense_tiles_overflow_the_staging_area_and_chunk(ctx, sccd):
+    """600 coincident boxes: every tile finds far more pairs than it can park between the count
+    and the place pass, so the place pass sweeps again -- also when the list is cut in chunks
+    that end inside tiles."""
+    n = 600
+    F0 = np.zeros((0, 3), np.int32, order="F")
+    Vt = np.asfortranarray(np.tile(np.array([[0., 0, 0], [1, 1, 1]]), (n, 1)))
+    Et = np.asfortranarray(np.arange(2 * n, dtype=np.int32).reshape(n, 2))
+    ctx.upload_mesh(Vt, Vt.copy(order="F"), Et, F0)
+    ctx.build_boxes(0.0)
+    full = ctx.broad_phase(1)
+    assert len(full) == n * (n - 1) // 2
+    assert len(np.unique(full, axis=0)) == len(full)
+    ctx.set_max_pairs_per_chunk(7001)
+    try:
+        chunked = ctx.broad_phase(1)
+    finally:
+        ctx.set_max_pairs_per_chunk(0)
+    assert np.array_equal(full, chunked)
+
+
 def test_bounded_queue_and_donation(sccd, orc, torch_cuda):
     """A handful of very deep queries: the tail must be spread through the work queue and the
     answer must not depend on it."""
