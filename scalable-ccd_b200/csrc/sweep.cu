@@ -181,40 +181,59 @@ __device__ __forceinline__ void sweep_tile(
     // the pair must be at home in this cell, and (two lists) join a vertex with a face
     constexpr uint32_t kHome = kKeyFlagY | kKeyFlagZ;
 
-    for (int k = 1;; k++) {
-        const int j = i + k;
-        uint32_t kj = 0xffffffffu;
-        if (valid && j < n)
-            kj = __ldg(&pf.key[j]);
-        const bool in_window = valid && j < n && kj <= my_reach;
-        if (!__any_sync(kFull, in_window))
-            break;
-        bool p = in_window && ((kj | my_flags) & kHome) == kHome;
-        if (TWO_LISTS)
-            p = p && ((kj ^ my_flags) & kKeyFlagType) != 0u;
-        if (p) {
-            const float4 b = __ldg(&pf.yz[j]);
-            p = (b.x <= my.y) && (my.x <= b.y) && (b.z <= my.w) && (my.z <= b.w);
+    // kStep candidates per trip: their keys (then the yz records of those that pass the key
+    // tests) are loaded together, so a trip waits for two L1 round trips instead of 2 * kStep
+    // (in the single-candidate loop 7 of 13 stalled warps per issue were waiting on a load).
+    // Tried and dropped: keeping the owners' exact records in shared memory and skipping the
+    // exact fetch when inner f32 bounds already prove the overlap -- reading 64 B for EVERY
+    // owner costs more than the survivors' fetches it saves (config 4: 8.2 -> 17.8 ms).
+    constexpr int kStep = 4;
+    for (int k = 1;; k += kStep) {
+        uint32_t kj[kStep];
+#pragma unroll
+        for (int u = 0; u < kStep; u++) {
+            const int j = i + k + u;
+            kj[u] = (valid && j < n) ? __ldg(&pf.key[j]) : 0xffffffffu;
         }
-        const unsigned mask = __ballot_sync(kFull, p);
-        if (mask == 0u)
-            continue;
-        if (p)
-            q[qn + __popc(mask & ((1u << lane) - 1u))] =
-                ((uint32_t)lane << kRelBits) | (rel_base + (uint32_t)k);
-        qn += __popc(mask);
-        __syncwarp();
-        if (qn >= 32) {
-            drain32<FILL, TWO_LISTS>(
-                sm, box, tile0, warp, lane, q[lane], true, pairs, st_pairs, st_tags);
-            tested += 32;
-            const int r = qn - 32;
-            const uint32_t v = (lane < r) ? q[32 + lane] : 0u;
+        // keys are sorted: nothing later can be in a window if the first of the trip is in none
+        if (!__any_sync(kFull, valid && kj[0] <= my_reach && i + k < n))
+            break;
+        bool p[kStep];
+        float4 b[kStep];
+#pragma unroll
+        for (int u = 0; u < kStep; u++) {
+            const int j = i + k + u;
+            p[u] = valid && j < n && kj[u] <= my_reach && ((kj[u] | my_flags) & kHome) == kHome;
+            if (TWO_LISTS)
+                p[u] = p[u] && ((kj[u] ^ my_flags) & kKeyFlagType) != 0u;
+            b[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p[u])
+                b[u] = __ldg(&pf.yz[j]);
+        }
+#pragma unroll
+        for (int u = 0; u < kStep; u++) {
+            const bool hit =
+                p[u] && (b[u].x <= my.y) && (my.x <= b[u].y) && (b[u].z <= my.w) && (my.z <= b[u].w);
+            const unsigned mask = __ballot_sync(kFull, hit);
+            if (mask == 0u)
+                continue;
+            if (hit)
+                q[qn + __popc(mask & ((1u << lane) - 1u))] =
+                    ((uint32_t)lane << kRelBits) | (rel_base + (uint32_t)(k + u));
+            qn += __popc(mask);
             __syncwarp();
-            if (lane < r)
-                q[lane] = v;
-            qn = r;
-            __syncwarp();
+            if (qn >= 32) {
+                drain32<FILL, TWO_LISTS>(
+                    sm, box, tile0, warp, lane, q[lane], true, pairs, st_pairs, st_tags);
+                tested += 32;
+                const int r = qn - 32;
+                const uint32_t v = (lane < r) ? q[32 + lane] : 0u;
+                __syncwarp();
+                if (lane < r)
+                    q[lane] = v;
+                qn = r;
+                __syncwarp();
+            }
         }
     }
     if (qn > 0) {
