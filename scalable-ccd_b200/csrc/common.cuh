@@ -247,8 +247,8 @@ static_assert(sizeof(WorkItem) == 64, "WorkItem");
 constexpr int kNarrowRounds = 5;
 
 // Every hot word sits in its own 128-byte line.
+// (the running earliest toi is a separate device word so that concurrent batches share it)
 struct alignas(128) NarrowCounters {
-    alignas(128) double toi;                          // shared earliest toi
     alignas(128) unsigned long long next[kNarrowRounds];      // next unclaimed work index
     alignas(128) unsigned long long n_items[kNarrowRounds + 1]; // [r] = items round r reads
     alignas(128) int overflow;                        // an item list was full (work kept local)
@@ -349,12 +349,12 @@ struct NarrowInput {
 // it is zero.
 void launch_narrow_phase(
     bool is_vf, const NarrowInput& in, const NarrowParams& p, NarrowCounters* counters,
-    WorkItem* items0, WorkItem* items1, unsigned long long item_cap, double* toi_per_query,
+    double* g_toi, WorkItem* items0, WorkItem* items1, unsigned long long item_cap, double* toi_per_query,
     unsigned int* checks_per_query, int num_sms, cudaStream_t s, LaunchCounter& lc);
 // moves n_items[kNarrowRounds] to n_items[kNarrowRounds - 1] and reruns the last round
 void launch_narrow_extra_round(
     bool is_vf, const NarrowInput& in, const NarrowParams& p, NarrowCounters* counters,
-    WorkItem* items0, WorkItem* items1, unsigned long long item_cap, int extra_index,
+    double* g_toi, WorkItem* items0, WorkItem* items1, unsigned long long item_cap, int extra_index,
     double* toi_per_query, unsigned int* checks_per_query, int num_sms, cudaStream_t s,
     LaunchCounter& lc);
 void launch_fill_f64(double* p, long long n, double v, cudaStream_t s, LaunchCounter& lc);
