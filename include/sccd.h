@@ -86,6 +86,7 @@ typedef struct {
     float pad_;
     int64_t n_records[2];    /* sweep records = boxes replicated into the (y,z) cells   */
     int32_t grid_cells[2][2]; /* (sy, sz) cell grid chosen for each list                */
+    int64_t n_culled[2];     /* queries answered "no collision" by the separating-axis cull */
 } sccd_stats;
 
 /* ---- context ------------------------------------------------------------------ */

@@ -45,6 +45,7 @@ class Stats(C.Structure):
         ("ms_k_sweep_count", C.c_float * 2), ("ms_k_sweep_fill", C.c_float * 2),
         ("ms_k_narrow", C.c_float * 2), ("ms_k_boxes", C.c_float), ("ms_k_gather", C.c_float),
         ("pad_", C.c_float), ("n_records", C.c_int64 * 2), ("grid_cells", (C.c_int32 * 2) * 2),
+        ("n_culled", C.c_int64 * 2),
     ]
 
     def as_dict(self):

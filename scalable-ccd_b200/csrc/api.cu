@@ -112,7 +112,7 @@ struct sccd_ctx {
         DevBuf b_counts, b_offsets, b_scan, b_pairs, b_small;
         DevBuf b_stage_pairs, b_stage_tags, b_stage_count; // count pass -> place pass
         int* h_small = nullptr; // pinned scratch for tiny D2H results
-        DevBuf b_counters, b_items[2], b_toi_q, b_checks_q, b_queries;
+        DevBuf b_counters, b_items[2], b_toi_q, b_checks_q, b_queries, b_surv;
         NarrowCounters* h_counters = nullptr; // pinned
         unsigned long long item_cap = 0; // capacity of each of the two hand-on lists
         // narrow_enqueue -> narrow_finish hand-over
@@ -123,6 +123,7 @@ struct sccd_ctx {
             NarrowParams P;
             double* d_tq = nullptr;
             unsigned int* checks = nullptr;
+            bool culling = false;
         } pending;
     } runs[1];
     Run* cur = &runs[0];
@@ -881,11 +882,18 @@ void narrow_enqueue(
         checks = (unsigned int*)R.b_checks_q.reserve((size_t)in.n * 4);
         SCCD_CUDA(cudaMemsetAsync(checks, 0, (size_t)in.n * 4, st));
     }
+    // separating-axis cull in front of the solver (SCCD_NP_CULL=0 switches it off: A/B, tests)
+    uint32_t* survivors = nullptr;
+    {
+        const char* e = getenv("SCCD_NP_CULL");
+        if (!e || atoi(e) != 0)
+            survivors = (uint32_t*)R.b_surv.reserve((size_t)in.n * 4);
+    }
     const size_t kt = kt_begin(c, &c->stats.ms_k_narrow[kind]);
     launch_narrow_phase(
         kind == SCCD_VF, in, P, R.b_counters.as<NarrowCounters>(), d_gtoi,
         R.b_items[0].as<WorkItem>(), R.b_items[1].as<WorkItem>(), R.item_cap, d_toi_per_query,
-        checks, c->num_sms, st, c->lc);
+        checks, survivors, c->num_sms, st, c->lc);
     kt_end(c, kt);
     SCCD_CUDA(cudaMemcpyAsync(
         R.h_counters, R.b_counters.ptr, sizeof(NarrowCounters), cudaMemcpyDeviceToHost, st));
@@ -895,6 +903,7 @@ void narrow_enqueue(
     R.pending.P = P;
     R.pending.d_tq = d_toi_per_query;
     R.pending.checks = checks;
+    R.pending.culling = survivors != nullptr;
 }
 
 void narrow_finish(sccd_ctx* c, double* d_gtoi)
@@ -921,6 +930,8 @@ void narrow_finish(sccd_ctx* c, double* d_gtoi)
     }
     const NarrowCounters& r = *R.h_counters;
     c->stats.n_box_checks[kind] += (int64_t)r.box_checks;
+    if (R.pending.culling)
+        c->stats.n_culled[kind] += R.pending.in.n - (int64_t)r.n_items[0];
     c->stats.n_donated[kind] += (int64_t)r.donated;
     c->stats.n_capped[kind] += (int64_t)r.capped;
     if (r.overflow)
