@@ -315,10 +315,12 @@ def main():
                             pinned["F"].data_ptr(), sizes=(nV, nE, nF), **PARAMS)
 
     def timed(fn, steps, warmup, sampler=False):
+        # the sampler starts before the warm-up (NVML initialisation stalls the first CUDA calls
+        # that follow it); only samples taken inside [t0, t1] are reported
+        smp = ClockSampler(local) if sampler else None
         for _ in range(warmup):
             fn()
         barrier()
-        smp = ClockSampler(local) if sampler else None
         t0 = time.time()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
               for _ in range(steps)]
