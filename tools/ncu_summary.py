@@ -38,7 +38,7 @@ def bench_name(k, seen):
         return "sweep_count_vf" if "<(bool)1>" in k or "<1>" in k else "sweep_count_ee"
     if "sweep_place_kernel" in k:
         return "sweep_fill_vf" if "<(bool)1>" in k or "<1>" in k else "sweep_fill_ee"
-    if "narrow_round_kernel" in k:
+    if "narrow_round_kernel" in k or "narrow_cull_kernel" in k or "narrow_coop_kernel" in k:
         return "narrow_vf" if "<(bool)1>" in k or "<1>" in k else "narrow_ee"
     if "gather_sorted" in k:
         return "gather"
