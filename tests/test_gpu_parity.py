@@ -167,10 +167,10 @@ def test_iteration_cap_is_conservative(ctx, orc, sccd, torch_cuda):
 @pytest.fixture
 def np_env():
     """Sets / restores the narrow-phase debug knobs (read by the library at every batch)."""
-    saved = {k: os.environ.get(k) for k in ("SCCD_NP_FLAGS", "SCCD_NP_DEPTH")}
+    saved = {k: os.environ.get(k) for k in ("SCCD_NP_FLAGS", "SCCD_NP_DEPTH", "SCCD_NP_CULL")}
 
-    def set_(flags=None, depth=None):
-        for k, v in (("SCCD_NP_FLAGS", flags), ("SCCD_NP_DEPTH", depth)):
+    def set_(flags=None, depth=None, cull=None):
+        for k, v in (("SCCD_NP_FLAGS", flags), ("SCCD_NP_DEPTH", depth), ("SCCD_NP_CULL", cull)):
             if v is None:
                 os.environ.pop(k, None)
             else:
@@ -222,6 +222,33 @@ def test_paths_deeper_than_the_lane_state_are_handed_on(ctx, orc, sccd, torch_cu
         np_env()
         otoi, otpq, _ = orc.narrow_phase(q, kind == 0)
         assert np.array_equal(tpq, otpq) and toi == otoi
+
+
+@pytest.mark.parametrize("kw", [dict(ms=0.0, tol=1e-6), dict(ms=1e-3, tol=1e-6),
+                                dict(ms=0.0, tol=1e-3), dict(ms=1e-8, tol=1e-9)])
+def test_separating_axis_cull_changes_no_result(ctx, orc, sccd, torch_cuda, scene_c1, np_env, kw):
+    """The cull answers most candidate pairs "no collision" without the solver; every per-query
+    TOI must equal the solver's (cull off) and the oracle's, also with a minimum separation or a
+    tolerance far larger than the gaps it tests against."""
+    ctx.upload_mesh(scene_c1["V0"], scene_c1["V1"], scene_c1["E"], scene_c1["F"])
+    ctx.build_boxes(kw["ms"])
+    for kind in (0, 1):
+        pairs = ctx.broad_phase(kind)
+        q = orc.gather_queries(scene_c1, np.ascontiguousarray(pairs), kind == 0)
+        np_env(cull=1)
+        ctx.reset_stats()
+        toi1, tpq1 = _narrow_gpu(ctx, torch_cuda, kind, q, **kw)
+        culled = ctx.stats()["n_culled"][kind]
+        np_env(cull=0)
+        ctx.reset_stats()
+        toi0, tpq0 = _narrow_gpu(ctx, torch_cuda, kind, q, **kw)
+        assert ctx.stats()["n_culled"][kind] == 0
+        np_env()
+        assert np.array_equal(tpq0, tpq1) and toi0 == toi1
+        otoi, otpq, _ = orc.narrow_phase(q, kind == 0, kw["ms"], -1, kw["tol"], True)
+        assert np.array_equal(tpq1, otpq) and toi1 == otoi
+        if kw["ms"] == 0.0 and kw["tol"] == 1e-6:
+            assert culled > 0.8 * len(q)          # it does its job on a cloth scene
 
 
 def test_dense_tiles_overflow_the_staging_area_and_chunk(ctx, sccd):
