@@ -78,20 +78,24 @@ __device__ __forceinline__ void drain32(
     int ea = 0, eb = 0;
     if (active) {
         const int i = tile0 + t;
-        const double2 ax = __ldg(&box.x[i]);
-        const double4 ayz = ldg_d4(&box.yz[i]);
+        // ids first: mesh neighbours always overlap and are never admissible
+        // (collision.cuh:17-21) -- two thirds of a mesh's survivors stop here, 32 bytes in,
+        // instead of after the 128-byte exact test.  (Doing this in the window loop instead
+        // costs more than it saves: that loop is latency-bound, this stage is not.)
         const int4 aid = __ldg(&box.id[i]);
-        const double2 bx = __ldg(&box.x[j]);
-        const double4 byz = ldg_d4(&box.yz[j]);
         const int4 bid = __ldg(&box.id[j]);
-        // closed-interval overlap on all three axes (aabb.cuh:67-72 / 100-104)
-        hit = ax.y >= bx.x && ax.x <= bx.y && ayz.z >= byz.x && ayz.x <= byz.z
-            && ayz.w >= byz.y && ayz.y <= byz.w;
-        // collision.cuh:17-21
         const bool share = aid.x == bid.x || aid.x == bid.y || aid.x == bid.z
             || aid.y == bid.x || aid.y == bid.y || aid.y == bid.z || aid.z == bid.x
             || aid.z == bid.y || aid.z == bid.z;
-        hit = hit && !share;
+        if (!share) {
+            const double2 ax = __ldg(&box.x[i]);
+            const double4 ayz = ldg_d4(&box.yz[i]);
+            const double2 bx = __ldg(&box.x[j]);
+            const double4 byz = ldg_d4(&box.yz[j]);
+            // closed-interval overlap on all three axes (aabb.cuh:67-72 / 100-104)
+            hit = ax.y >= bx.x && ax.x <= bx.y && ayz.z >= byz.x && ayz.x <= byz.z
+                && ayz.w >= byz.y && ayz.y <= byz.w;
+        }
         ea = aid.w;
         eb = bid.w;
     }
