@@ -102,7 +102,7 @@ struct GridParams {
     // own disjoint cell ranges emit disjoint pair lists whose rank-order concatenation is the
     // single-GPU list -- no halo, no exchange.
     int cell_lo = 0, cell_hi = 0x7fffffff;
-    // major-axis quantisation of the 32-bit sort key (see sweep_key())
+    // major-axis quantisation of the 32-bit sort key (see "32-bit sweep key" below)
     double x0 = 0, inv_hx = 0;
     int x_bits = 29;
 };

@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kThreads) expand_fill_kernel(
         return;
     int y0, y1, z0, z1;
     cell_range(ldg_d4(&boxes.yz[i]), g, y0, y1, z0, z1);
-    // see sweep_key() in common.cuh
+    // key layout: common.cuh ("32-bit sweep key of a record")
     const uint32_t xq = quantize_x(__ldg(&boxes.x[i]).x, g) << kKeyFlagBits;
     const uint32_t type = __ldg(&boxes.id[i]).w < 0 ? kKeyFlagType : 0u;
     const int cell_shift = g.x_bits + kKeyFlagBits;
