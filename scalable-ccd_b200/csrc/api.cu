@@ -77,6 +77,7 @@ struct sccd_ctx {
         DevBuf keys, keys_tmp, idx, idx_out; // (key, box index) records, one per (box, cell)
         DevBuf sx, syz, sid;     // sorted exact records
         DevBuf pkey, preach, pyz; // sorted prefilter view
+        DevBuf sort_temp;         // radix sort scratch
         SortedList sorted;
         BoxArrays unsorted;
         int n_boxes = 0;
@@ -87,7 +88,13 @@ struct sccd_ctx {
         int try_stride = 1, attempt = 0;
     } lists[3]; // [2] = caller-made boxes (sccd_set_boxes)
     bool have_custom = false;
-    DevBuf b_sort_temp, b_scan_temp, b_stats, b_hist, b_splits;
+    DevBuf b_scan_temp, b_stats, b_hist, b_splits;
+    // The edge list is sorted on a second stream, under the vertex-face sweep and narrow phase:
+    // the sort of a 1 M-box list is a dozen latency-bound launches that leave the GPU mostly
+    // idle.  ev_counts: both lists counted (main stream); ev_sorted1: edge list sorted.
+    cudaStream_t sort_stream = nullptr;
+    cudaEvent_t ev_counts = nullptr, ev_sorted1 = nullptr;
+    bool sort1_pending = false;
     // pinned: per list, box statistics + record count + multi-GPU cell splits
     struct ListHost {
         double stats[kNumStats];
@@ -152,6 +159,12 @@ struct sccd_ctx {
         }
         if (h_gtoi)
             cudaFreeHost(h_gtoi);
+        if (sort_stream)
+            cudaStreamDestroy(sort_stream);
+        if (ev_counts)
+            cudaEventDestroy(ev_counts);
+        if (ev_sorted1)
+            cudaEventDestroy(ev_sorted1);
         if (h_lists)
             cudaFreeHost(h_lists);
         for (auto& e : ev)
@@ -446,8 +459,12 @@ void sort_list_begin(sccd_ctx* c, int which)
     sort_list_count(c, which);
 }
 
-void sort_list_finish(sccd_ctx* c, int which, cudaEvent_t ga, cudaEvent_t gb)
+// st: the stream the fill / sort / gather are enqueued on (the retry path stays on c->stream)
+void sort_list_finish(
+    sccd_ctx* c, int which, cudaEvent_t ga, cudaEvent_t gb, cudaStream_t st = nullptr)
 {
+    if (!st)
+        st = c->stream;
     auto& L = c->lists[which];
     auto& H = list_host(c, which);
     const int n = L.n_boxes;
@@ -456,9 +473,9 @@ void sort_list_finish(sccd_ctx* c, int which, cudaEvent_t ga, cudaEvent_t gb)
         L.sorted.grid = GridParams();
         L.sorted.cell_sharded = false;
         if (ga)
-            SCCD_CUDA(cudaEventRecord(ga, c->stream));
+            SCCD_CUDA(cudaEventRecord(ga, st));
         if (gb)
-            SCCD_CUDA(cudaEventRecord(gb, c->stream));
+            SCCD_CUDA(cudaEventRecord(gb, st));
         return;
     }
     // replication bound: a few huge boxes can touch every cell -- coarsen until it is modest
@@ -529,14 +546,18 @@ void sort_list_finish(sccd_ctx* c, int which, cudaEvent_t ga, cudaEvent_t gb)
     L.sorted.pf.key = (uint32_t*)L.pkey.reserve(mm * 4);
     L.sorted.pf.reach = (uint32_t*)L.preach.reserve(mm * 4);
     L.sorted.pf.yz = (float4*)L.pyz.reserve(mm * sizeof(float4));
-    c->b_sort_temp.reserve(sort_temp_bytes((int)m));
+    L.sort_temp.reserve(sort_temp_bytes((int)m)); // per list: the two sorts may overlap
+    if (st != c->stream) { // everything counted so far (incl. a retry above) is on c->stream
+        SCCD_CUDA(cudaEventRecord(c->ev_counts, c->stream));
+        SCCD_CUDA(cudaStreamWaitEvent(st, c->ev_counts, 0));
+    }
     launch_expand_fill(
         L.unsorted, n, g, L.offs.as<unsigned long long>(), L.keys.as<uint32_t>(),
-        L.idx.as<uint32_t>(), c->stream, c->lc);
+        L.idx.as<uint32_t>(), st, c->lc);
     launch_sort_and_gather(
         (int)m, cell_bits + g.x_bits, L.keys.as<uint32_t>(), L.keys_tmp.as<uint32_t>(),
-        L.idx.as<uint32_t>(), L.idx_out.as<uint32_t>(), c->b_sort_temp.ptr, c->b_sort_temp.cap,
-        L.unsorted, L.sorted, c->stream, c->lc, ga, gb);
+        L.idx.as<uint32_t>(), L.idx_out.as<uint32_t>(), L.sort_temp.ptr, L.sort_temp.cap,
+        L.unsorted, L.sorted, st, c->lc, ga, gb);
 }
 
 // one list on its own (caller-made boxes; re-sharding an already built list)
@@ -549,10 +570,20 @@ void sort_list(sccd_ctx* c, int which, cudaEvent_t ga, cudaEvent_t gb)
     sort_list_finish(c, which, ga, gb);
 }
 
+// make `st` wait for the edge-list sort that may still run on the sort stream
+void join_sort_stream(sccd_ctx* c, cudaStream_t st)
+{
+    if (c->sort1_pending) {
+        SCCD_CUDA(cudaStreamWaitEvent(st, c->ev_sorted1, 0));
+        c->sort1_pending = false;
+    }
+}
+
 void build_boxes(sccd_ctx* c, double inflation_radius)
 {
     if (!c->have_mesh)
         throw std::logic_error("build_boxes: no mesh uploaded");
+    join_sort_stream(c, c->stream); // a previous build whose edge list nobody swept
     const int nV = c->nV, nE = c->nE, nF = c->nF;
     const long long nVF = (long long)nV + nF;
     if (nVF >= (1ll << 27) || nE >= (1 << 27))
@@ -580,7 +611,11 @@ void build_boxes(sccd_ctx* c, double inflation_radius)
     sort_list_begin(c, 1);
     SCCD_CUDA(cudaStreamSynchronize(c->stream));
     sort_list_finish(c, 0, c->ev[EV_GA0], c->ev[EV_GB0]);
-    sort_list_finish(c, 1, c->ev[EV_GA1], c->ev[EV_GB1]);
+    // (if the grid of list 1 has to be coarsened, its retry runs -- and syncs -- on the main
+    // stream before anything is enqueued on the sort stream)
+    sort_list_finish(c, 1, c->ev[EV_GA1], c->ev[EV_GB1], c->sort_stream);
+    SCCD_CUDA(cudaEventRecord(c->ev_sorted1, c->sort_stream));
+    c->sort1_pending = true;
     c->gather_timed = true;
     record(c, EV_SORT);
     c->have_boxes = true;
@@ -678,6 +713,8 @@ void broad_phase_begin_enqueue(sccd_ctx* c, int kind)
         throw std::invalid_argument("broad_phase: kind must be SCCD_VF, SCCD_EE or SCCD_BOXES");
     if (kind == SCCD_BOXES ? !c->have_custom : !c->have_boxes)
         throw std::logic_error("Must initialize build broad phase before detecting overlaps!");
+    if (kind == SCCD_EE)
+        join_sort_stream(c, st); // the edge list was sorted on the sort stream
     if (c->lists[kind].built_rank != c->rank || c->lists[kind].built_world != c->world)
         sort_list(c, kind, nullptr, nullptr); // sccd_set_shard changed since the list was sorted
     const SortedList& L = c->lists[kind].sorted;
@@ -1170,6 +1207,9 @@ int sccd_create(int device, void* stream, sccd_ctx** out)
         for (auto& e : c->ev)
             SCCD_CUDA(cudaEventCreate(&e));
         c->runs[0].stream = c->stream;
+        SCCD_CUDA(cudaStreamCreateWithFlags(&c->sort_stream, cudaStreamNonBlocking));
+        SCCD_CUDA(cudaEventCreateWithFlags(&c->ev_counts, cudaEventDisableTiming));
+        SCCD_CUDA(cudaEventCreateWithFlags(&c->ev_sorted1, cudaEventDisableTiming));
         return SCCD_OK;
     });
     if (rc != SCCD_OK) {
@@ -1186,6 +1226,8 @@ void sccd_destroy(sccd_ctx* ctx)
         return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->sort_stream)
+        cudaStreamSynchronize(ctx->sort_stream);
     delete ctx;
 }
 
@@ -1493,6 +1535,7 @@ int sccd_synchronize(sccd_ctx* ctx)
 {
     return guarded(ctx, [&] {
         SCCD_CUDA(cudaStreamSynchronize(ctx->stream));
+        SCCD_CUDA(cudaStreamSynchronize(ctx->sort_stream));
         return SCCD_OK;
     });
 }
