@@ -93,7 +93,7 @@ struct sccd_ctx {
     // the sort of a 1 M-box list is a dozen latency-bound launches that leave the GPU mostly
     // idle.  ev_counts: both lists counted (main stream); ev_sorted1: edge list sorted.
     cudaStream_t sort_stream = nullptr;
-    cudaEvent_t ev_counts = nullptr, ev_sorted1 = nullptr;
+    cudaEvent_t ev_counts = nullptr, ev_sorted1 = nullptr, ev_vf_done = nullptr;
     bool sort1_pending = false;
     // pinned: per list, box statistics + record count + multi-GPU cell splits
     struct ListHost {
@@ -132,7 +132,7 @@ struct sccd_ctx {
             unsigned int* checks = nullptr;
             bool culling = false;
         } pending;
-    } runs[1];
+    } runs[2]; // [1]: the edge list's broad phase + narrow phase on the sort stream (pipeline)
     Run* cur = &runs[0];
     DevBuf b_gtoi; // earliest toi shared by the two lists of a pipeline call
     double* h_gtoi = nullptr; // pinned
@@ -165,6 +165,8 @@ struct sccd_ctx {
             cudaEventDestroy(ev_counts);
         if (ev_sorted1)
             cudaEventDestroy(ev_sorted1);
+        if (ev_vf_done)
+            cudaEventDestroy(ev_vf_done);
         if (h_lists)
             cudaFreeHost(h_lists);
         for (auto& e : ev)
@@ -307,7 +309,7 @@ void upload_mesh(
     }
     c->have_mesh = true;
     c->have_boxes = false;
-    c->runs[0].bp_kind = -1;
+    c->runs[0].bp_kind = c->runs[1].bp_kind = -1;
 }
 
 void prepare_list(sccd_ctx* c, int which, int n, bool two_lists)
@@ -619,7 +621,7 @@ void build_boxes(sccd_ctx* c, double inflation_radius)
     c->gather_timed = true;
     record(c, EV_SORT);
     c->have_boxes = true;
-    c->runs[0].bp_kind = -1;
+    c->runs[0].bp_kind = c->runs[1].bp_kind = -1;
     c->stats.n_boxes[0] = nVF;
     c->stats.n_boxes[1] = nE;
     c->stats.n_records[0] = LV.sorted.n;
@@ -686,7 +688,7 @@ void set_boxes(
     sort_list(c, 2, nullptr, nullptr);
     SCCD_CUDA(cudaStreamSynchronize(c->stream)); // host staging vectors go out of scope
     c->have_custom = true;
-    c->runs[0].bp_kind = -1;
+    c->runs[0].bp_kind = c->runs[1].bp_kind = -1;
     c->stats.n_boxes[0] = n;
     c->stats.n_records[0] = L.sorted.n;
 }
@@ -1072,17 +1074,27 @@ void run_pipeline(
     // rounds of the vertex-face pass -- so an edge-edge pass that starts before it is final
     // prunes less: +44 % box checks on config 2, +11 % on config 4, no net gain.)
     if (!ipc && !want_collisions) {
-        // Plain ccd(): the narrow phase of a list is only enqueued; the host picks its
-        // counters up after the NEXT host sync it needs anyway (the next list's pair total),
-        // and the toi travels back with them -- 5 host syncs per step instead of 8.
+        // Plain ccd().  Two streams, ONE order of the narrow phases:
+        //   main stream : VF sweep -> VF narrow phase
+        //   sort stream : EE sort -> EE sweep .......... (waits for VF narrow) -> EE narrow phase
+        // The edge list's sort and sweep run under the vertex-face work (they depend on
+        // nothing but the boxes); its narrow phase starts after the vertex-face one, so it
+        // prunes with the same earliest toi as in a sequential run.  The narrow phase of a
+        // list is only enqueued; the host picks its counters up later and the toi travels
+        // back with them.
         double* d_gtoi = gtoi_set(c, 1.0, c->stream); // ccd.cu:125
         bool any_batch = false;
+        c->cur = &c->runs[1];
+        broad_phase_begin_enqueue(c, SCCD_EE); // stream order: after the edge sort
         for (int kind = 0; kind < 2; kind++) {
-            broad_phase_begin(c, kind);   // its sync also covers the previous list's batch
-            narrow_finish(c, d_gtoi);
+            c->cur = &c->runs[kind];
+            if (kind == SCCD_VF)
+                broad_phase_begin(c, kind);
+            else
+                broad_phase_begin_finish(c);
             if (broad_phase_complete(c)) {
-                record(c, kind == SCCD_VF ? EV_SW0B : EV_SW1B);
-                record(c, kind == SCCD_VF ? EV_NP0A : EV_NP1A);
+                rrecord(c, kind == SCCD_VF ? EV_SW0B : EV_SW1B);
+                rrecord(c, kind == SCCD_VF ? EV_NP0A : EV_NP1A);
             }
             bool first = true;
             while (!broad_phase_complete(c)) {
@@ -1090,17 +1102,27 @@ void run_pipeline(
                 const sccd_pair* d_pairs = nullptr;
                 int64_t n = 0;
                 broad_phase_partial(c, &d_pairs, &n);
-                if (first)
-                    record(c, kind == SCCD_VF ? EV_NP0A : EV_NP1A);
+                if (first) {
+                    if (kind == SCCD_EE) // after the vertex-face narrow phase and the toi word
+                        SCCD_CUDA(cudaStreamWaitEvent(c->cur->stream, c->ev_vf_done, 0));
+                    rrecord(c, kind == SCCD_VF ? EV_NP0A : EV_NP1A);
+                }
                 first = false;
                 narrow_enqueue(
                     c, kind, mesh_input(c, d_pairs, n), min_distance, max_iter, tol,
                     allow_zero_toi, d_gtoi, nullptr);
                 any_batch = any_batch || c->cur->pending.active;
             }
-            record(c, kind == SCCD_VF ? EV_NP0B : EV_NP1B);
+            rrecord(c, kind == SCCD_VF ? EV_NP0B : EV_NP1B);
+            if (kind == SCCD_VF)
+                SCCD_CUDA(cudaEventRecord(c->ev_vf_done, c->stream));
         }
-        narrow_finish(c, d_gtoi);
+        for (int kind = 0; kind < 2; kind++) {
+            c->cur = &c->runs[kind];
+            narrow_finish(c, d_gtoi);
+            SCCD_CUDA(cudaStreamSynchronize(c->cur->stream));
+        }
+        c->cur = &c->runs[0];
         record(c, EV_T1);
         finish_stats(c, true);
         // the toi travelled back with the counters of the last batch (1.0 if there was none)
@@ -1210,6 +1232,8 @@ int sccd_create(int device, void* stream, sccd_ctx** out)
         SCCD_CUDA(cudaStreamCreateWithFlags(&c->sort_stream, cudaStreamNonBlocking));
         SCCD_CUDA(cudaEventCreateWithFlags(&c->ev_counts, cudaEventDisableTiming));
         SCCD_CUDA(cudaEventCreateWithFlags(&c->ev_sorted1, cudaEventDisableTiming));
+        SCCD_CUDA(cudaEventCreateWithFlags(&c->ev_vf_done, cudaEventDisableTiming));
+        c->runs[1].stream = c->sort_stream;
         return SCCD_OK;
     });
     if (rc != SCCD_OK) {
@@ -1271,7 +1295,7 @@ int sccd_set_shard(sccd_ctx* ctx, int rank, int world)
         return SCCD_ERR_ARG;
     ctx->rank = rank;
     ctx->world = world;
-    ctx->runs[0].bp_kind = -1;
+    ctx->runs[0].bp_kind = ctx->runs[1].bp_kind = -1;
     return SCCD_OK;
 }
 
