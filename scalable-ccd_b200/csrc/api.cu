@@ -1042,7 +1042,9 @@ void finish_stats(sccd_ctx* c, bool pipeline)
 {
     c->stats.n_launches = c->lc.n;
     kt_resolve(c);
-    if (c->gather_timed) {
+    // (not while the edge list is still being sorted on the sort stream: waiting for its gather
+    // here would serialise what build_boxes() just overlapped -- a later call picks it up)
+    if (c->gather_timed && !c->sort1_pending) {
         SCCD_CUDA(cudaEventSynchronize(c->ev[EV_GB1]));
         c->stats.ms_k_gather = elapsed(c, EV_GA0, EV_GB0) + elapsed(c, EV_GA1, EV_GB1);
         c->gather_timed = false;
