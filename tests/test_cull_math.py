@@ -1,0 +1,115 @@
+"""The separating-axis cull of the narrow phase (csrc/narrow.cu: narrow_cull_kernel), restated
+in numpy and checked against the oracle on the CPU: whatever it culls, the reference's root
+finder answers "no collision" -- for every tolerance / minimum separation, including the ones
+far larger than the gaps it tests against, and for the adversarial queries of config 5."""
+import numpy as np
+import pytest
+
+DIAGS = np.array([[1, 1, 0], [1, -1, 0], [1, 0, 1], [1, 0, -1], [0, 1, 1], [0, 1, -1]], float)
+
+
+def absmax(*pairs):
+    return np.max(np.stack([np.abs(b - a) for a, b in pairs]), axis=0)
+
+
+def cull_mask(q, is_vf, tol, ms):
+    """numpy mirror of narrow_cull_kernel: True = culled (answered "no collision")."""
+    p = q.reshape(-1, 2, 4, 3)                       # [query, time, vertex, xyz]
+    s, e = p[:, 0], p[:, 1]
+    if is_vf:
+        A = np.stack([s[:, 0], e[:, 0]], axis=1)
+        B = np.stack([s[:, 1], s[:, 2], s[:, 3], e[:, 1], e[:, 2], e[:, 3],
+                      s[:, 2] + s[:, 3] - s[:, 1], e[:, 2] + e[:, 3] - e[:, 1]], axis=1)
+        width = np.full(len(p), tol)
+    else:
+        A = np.stack([s[:, 0], s[:, 1], e[:, 0], e[:, 1]], axis=1)
+        B = np.stack([s[:, 2], s[:, 3], e[:, 2], e[:, 3]], axis=1)
+        L = np.zeros((3, len(p)))
+        for k in range(3):
+            s0, s1, s2, s3 = (s[:, j, k] for j in range(4))
+            e0, e1, e2, e3 = (e[:, j, k] for j in range(4))
+            p000, p001, p010, p011 = s0 - s2, s0 - s3, s1 - s2, s1 - s3
+            p100, p101, p110, p111 = e0 - e2, e0 - e3, e1 - e2, e1 - e3
+            L[0] = np.maximum(L[0], absmax((p000, p100), (p001, p101), (p011, p111), (p010, p110)))
+            L[1] = np.maximum(L[1], absmax((p000, p010), (p100, p110), (p101, p111), (p001, p011)))
+            L[2] = np.maximum(L[2], absmax((p000, p001), (p100, p101), (p110, p111), (p010, p011)))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            width = np.where((L[0] > 0) & (L[1] > 0),
+                             tol * (1 + L[1] / L[0] + L[2] / L[1]) / 3 * 1.000001, np.inf)
+        width = np.maximum(width, tol)
+    pa = A @ DIAGS.T
+    pb = B @ DIAGS.T
+    sep = np.maximum(pa.min(1) - pb.max(1), pb.min(1) - pa.max(1)).max(1)
+    maxabs = np.maximum(1.0, np.abs(p).reshape(len(p), -1).max(1))
+    extent = p.reshape(len(p), -1).max(1) - p.reshape(len(p), -1).min(1)
+    bound = 2.0 * (width + ms + 2.0 * maxabs ** 3 * 8e-15 + 1e-12 * maxabs)
+    return (extent <= tol * 1e12) & (0.5 * sep > bound)
+
+
+@pytest.mark.parametrize("tol,ms", [(1e-6, 0.0), (1e-3, 0.0), (1e-6, 1e-3), (1e-9, 1e-8), (1e-2, 1e-2)])
+def test_culled_mesh_queries_are_misses(orc, scene_c1, tol, ms):
+    s = scene_c1
+    r = orc.ccd(s)
+    for pairs, is_vf in ((r["vf"], True), (r["ee"], False)):
+        q = orc.gather_queries(s, np.ascontiguousarray(pairs), is_vf)
+        _, tpq, _ = orc.narrow_phase(q, is_vf, ms, -1, tol, True, 1.0, per_query=True)
+        culled = cull_mask(q, is_vf, tol, ms)
+        assert not np.any(culled & (tpq < 1)), "the cull dropped a query the root finder reports"
+        if tol == 1e-6 and ms == 0.0:
+            assert culled.mean() > 0.9            # and it is worth having
+
+
+@pytest.mark.parametrize("tol,ms", [(1e-6, 0.0), (1e-9, 0.0), (1e-6, 1e-8), (1e-3, 0.0)])
+def test_culled_adversarial_queries_are_misses(orc, sccd, tol, ms):
+    ee, vf = sccd.scenes.queries_c5(3000, seed=4)
+    for q, is_vf in ((vf, True), (ee, False)):
+        q = q[orc.tractable(q, is_vf, ms, tol)]
+        _, tpq, _ = orc.narrow_phase(q, is_vf, ms, -1, tol, True, 1.0, per_query=True)
+        culled = cull_mask(q, is_vf, tol, ms)
+        assert not np.any(culled & (tpq < 1))
+
+
+def test_static_edges_are_never_culled(sccd):
+    """L_t = 0 (no motion): the reference's edge-edge tolerances are infinite, so it can accept
+    boxes of any size -- the cull must keep such queries."""
+    ee, _ = sccd.scenes.queries_c5(200, seed=1)
+    q = ee.copy().reshape(-1, 2, 4, 3)
+    q[:, 1] = q[:, 0]                                # end positions = start positions
+    q[:, :, 2:, 2] += 5.0                            # far apart along z
+    assert not cull_mask(q.reshape(-1, 24), False, 1e-6, 0.0).any()
+
+
+@pytest.mark.parametrize("is_vf", [True, False])
+@pytest.mark.parametrize("tol", [1e-6, 1e-4])
+def test_fuzz_near_threshold_separations(orc, is_vf, tol):
+    """Random primitives pushed apart along random diagonals by gaps around the acceptance
+    width (where edge-edge is much looser than the co-domain tolerance because of the
+    reference's tol_u = tol_t): every culled query must be a miss of the root finder."""
+    rng = np.random.default_rng(11 if is_vf else 12)
+    n = 4000
+    base = rng.uniform(-1, 1, (n, 1, 4, 3))
+    motion = rng.uniform(-1, 1, (n, 1, 4, 3)) * 10.0 ** rng.uniform(-5, 0, (n, 1, 1, 1))
+    p = np.concatenate([base, base + motion], axis=1)          # [n, time, vertex, xyz]
+    # collapse primitive B onto A's neighbourhood, then push it away along a diagonal
+    centre_a = p[:, :, :1 if is_vf else 2].mean(axis=(1, 2), keepdims=True)
+    sl = slice(1, 4) if is_vf else slice(2, 4)
+    centre_b = p[:, :, sl].mean(axis=(1, 2), keepdims=True)
+    p[:, :, sl] += centre_a - centre_b
+    axis = DIAGS[rng.integers(0, 6, n)] * rng.choice([-1.0, 1.0], (n, 1))
+    gap = 10.0 ** rng.uniform(np.log10(tol) - 1, np.log10(tol) + 4, n)
+    # extent of both primitives along the axis, so that `gap` is the real separation
+    proj = p.reshape(n, 8, 3) @ axis[:, :, None]
+    pa = proj.reshape(n, 2, 4)[:, :, :1 if is_vf else 2].reshape(n, -1)
+    pb = proj.reshape(n, 2, 4)[:, :, sl].reshape(n, -1)
+    if is_vf:   # the face's parallelogram corner reaches further than its vertices
+        f = p[:, :, 1:4]
+        fourth = (f[:, :, 1] + f[:, :, 2] - f[:, :, 0]) @ axis[:, :, None]
+        pb = np.concatenate([pb, fourth.reshape(n, -1)], axis=1)
+    shift = (pa.max(1) - pb.min(1) + gap) / (axis * axis).sum(1)
+    p[:, :, sl] += (shift[:, None] * axis)[:, None, None, :]
+    q = np.ascontiguousarray(p.reshape(n, 24))
+    q = q[orc.tractable(q, is_vf, 0.0, tol, limit=5000)]
+    _, tpq, _ = orc.narrow_phase(q, is_vf, 0.0, -1, tol, True, 1.0, per_query=True)
+    culled = cull_mask(q, is_vf, tol, 0.0)
+    assert culled.any() and (~culled).any()                    # the sample straddles the bound
+    assert not np.any(culled & (tpq < 1))
