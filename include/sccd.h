@@ -43,6 +43,11 @@ extern "C" {
 #define SCCD_VF 0 /* vertex-face  (two lists: vertices, faces) */
 #define SCCD_EE 1 /* edge-edge    (single list)                */
 
+/* Scalar type of the computation: the reference's SCALABLE_CCD_USE_DOUBLE switch
+ * (scalar.hpp:13-19, CMakeLists.txt:69).  The C ABI stays double either way. */
+#define SCCD_F64 0 /* default build of the reference                                   */
+#define SCCD_F32 1 /* its float build: inputs cast to float, nextafterf, float solver  */
+
 typedef struct sccd_ctx sccd_ctx;
 
 /* int2 of the reference's overlap lists (cuda/broad_phase/broad_phase.cuh:58-60). */
@@ -117,6 +122,16 @@ int sccd_set_queue_capacity(sccd_ctx* ctx, int64_t items);
  * not depend on it; it only changes how many candidates the sweep has to test. */
 int sccd_set_grid_cells(sccd_ctx* ctx, int max_cells);
 
+/* The reference's compile-time Scalar (scalar.hpp:13-19) as a run-time mode.  SCCD_F32 gives the
+ * results of the reference built with SCALABLE_CCD_USE_DOUBLE=OFF: vertices are cast to float
+ * (cuda/broad_phase/aabb.cu:124-128, device_matrix.cuh:21-27), boxes are made with nextafterf and
+ * float adds, ms / tolerance / toi are rounded to float on the way in, and the narrow phase
+ * runs in float with the arithmetic nvcc gives the reference under --use_fast_math
+ * (CMakeLists.txt:219-230; flush-to-zero, a / b = a * rcp(b)) and the float error filters
+ * (root_finder.cu:102-119).  Arguments and results stay `double` in this ABI: a float value is
+ * exact in a double.  Boxes have to be rebuilt after a change. */
+int sccd_set_scalar_type(sccd_ctx* ctx, int type);
+
 /* Multi-GPU sharding: this context makes, sorts and sweeps only the records of the rank-th of
  * `world` contiguous (y, z) cell ranges of each list (ranges balanced by record count; every
  * rank derives the same ranges from its own copy of the boxes, so there is no exchange) and
@@ -145,6 +160,23 @@ int sccd_build_boxes(sccd_ctx* ctx, double inflation_radius);
  * (what build_*_boxes return; cuda/broad_phase/aabb.cuh:150-188).
  * which: 0 vertices, 1 edges, 2 faces.  out: host array of nV / nE / nF boxes. */
 int sccd_get_boxes(sccd_ctx* ctx, int which, sccd_aabb* out);
+
+/* The reference's box builders by name, for callers that make and keep the boxes themselves
+ * (tests/test_broad_phase.cu:88-91); host arrays in and out, computed on the device, no mesh
+ * or context state involved.
+ *   build_vertex_boxes(V0, V1, boxes, r)  cuda/broad_phase/aabb.cuh:160-170, aabb.cu:146-184
+ *   build_vertex_boxes(V, boxes, r)       aabb.cuh:150-153 (V1 == NULL)
+ * V0 / V1: nV x 3 column-major.  ids as the reference sets them: (i, -i-1, -i-1), element i. */
+int sccd_build_vertex_boxes(
+    sccd_ctx* ctx, const double* V0, const double* V1, int64_t nV, double inflation_radius,
+    sccd_aabb* out);
+/*   build_edge_boxes(vertex_boxes, E, edge_boxes)   aabb.cuh:172-179, aabb.cu:186-206
+ *   build_face_boxes(vertex_boxes, F, face_boxes)   aabb.cuh:181-188, aabb.cu:208-229
+ * idx: n x verts_per_element (2 or 3) column-major int32.  Box = union of the vertex boxes, ids
+ * (e0, e1, -e0-1) / (f0, f1, f2), element id = row.  SCCD_ERR_ARG if an index is out of range. */
+int sccd_build_element_boxes(
+    sccd_ctx* ctx, const sccd_aabb* vertex_boxes, int64_t nV, const int32_t* idx, int64_t n,
+    int verts_per_element, sccd_aabb* out);
 
 /* DeviceAABBs(boxes) + BroadPhase::build(boxes) / build(boxesA, boxesB) for caller-made
  * boxes (cuda/broad_phase/aabb.cu:75-111, broad_phase.cu:29-101; this is how

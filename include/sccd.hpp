@@ -6,8 +6,9 @@
 //                                                                  cuda/ccd.cuh:26-38
 //   scalable_ccd::cuda::ipc_ccd_strategy(V0, V1, E, F, min_distance, max_iter, tol)
 //                                                                  cuda/ipc_ccd_strategy.hpp:17-24
-//   scalable_ccd::cuda::build_vertex_boxes / build_edge_boxes / build_face_boxes
+//   scalable_ccd::cuda::build_vertex_boxes (x2) / build_edge_boxes / build_face_boxes
 //                                                                  cuda/broad_phase/aabb.cuh:150-188
+//   scalable_ccd::cuda::narrow_phase<is_vf>                        narrow_phase.cuh:30-46
 //   scalable_ccd::cuda::DeviceAABBs, BroadPhase                    aabb.cuh:122-148, broad_phase.cuh:15-92
 //   scalable_ccd::sort_and_sweep (both overloads)                  broad_phase/sort_and_sweep.hpp:24-42
 //
@@ -16,6 +17,10 @@
 // Eigen::MatrixXd / Eigen::MatrixXi unchanged where Eigen is installed.  Errors surface as
 // std::runtime_error, like the reference's gpuErrchk (cuda/utils/assert.cuh:12-28).
 // Link with -lsccd_b200.  There is no CPU fallback.
+//
+// Scalar: double, as in the reference's default build.  Define SCCD_SHIM_USE_FLOAT before
+// including this header for the reference's float build (SCALABLE_CCD_USE_DOUBLE off,
+// scalar.hpp:16-18): Scalar becomes float and every context is switched to SCCD_F32.
 #pragma once
 
 #include "sccd.h"
@@ -30,7 +35,11 @@
 
 namespace scalable_ccd {
 
+#ifdef SCCD_SHIM_USE_FLOAT
+using Scalar = float; // scalar.hpp:16-18
+#else
 using Scalar = double; // SCALABLE_CCD_USE_DOUBLE build (scalar.hpp:13-15)
+#endif
 
 namespace cuda {
 
@@ -43,6 +52,9 @@ namespace cuda {
             {
                 if (sccd_create(device, stream, &h) != SCCD_OK)
                     throw std::runtime_error("sccd_create failed: no usable sm_100 CUDA device");
+#ifdef SCCD_SHIM_USE_FLOAT
+                sccd_set_scalar_type(h, SCCD_F32);
+#endif
             }
             ~Ctx() { sccd_destroy(h); }
             Ctx(const Ctx&) = delete;
@@ -82,10 +94,10 @@ namespace cuda {
         auto& c = detail::default_ctx();
         c.check(sccd_set_memory_limit(c.h, (size_t)memory_limit_GB << 30));
         detail::upload(c, vertices_t0, vertices_t1, edges, faces);
-        Scalar toi = 1;
+        double toi = 1;
         c.check(sccd_ccd(
             c.h, minimum_separation_distance, max_iterations, tolerance, allow_zero_toi, &toi));
-        return toi;
+        return (Scalar)toi;
     }
 
     // SCALABLE_CCD_TOI_PER_QUERY overload (ccd.cuh:35-37)
@@ -99,7 +111,7 @@ namespace cuda {
         auto& c = detail::default_ctx();
         c.check(sccd_set_memory_limit(c.h, (size_t)memory_limit_GB << 30));
         detail::upload(c, vertices_t0, vertices_t1, edges, faces);
-        Scalar toi = 1;
+        double toi = 1;
         int64_t nvf = 0, nee = 0;
         c.check(sccd_ccd_collisions(
             c.h, minimum_separation_distance, max_iterations, tolerance, allow_zero_toi, &toi,
@@ -110,8 +122,8 @@ namespace cuda {
             c.h, minimum_separation_distance, max_iterations, tolerance, allow_zero_toi, &toi,
             ids.data(), tois.data(), (int64_t)ids.size(), &nvf, &nee));
         for (size_t i = 0; i < ids.size(); i++)
-            collisions.emplace_back(ids[i].a, ids[i].b, tois[i]);
-        return toi;
+            collisions.emplace_back(ids[i].a, ids[i].b, (Scalar)tois[i]);
+        return (Scalar)toi;
     }
 
     // ---- cuda/ipc_ccd_strategy.hpp:17-24 ------------------------------------------------
@@ -122,9 +134,35 @@ namespace cuda {
     {
         auto& c = detail::default_ctx();
         detail::upload(c, V0, V1, E, F);
-        Scalar toi = 1;
+        double toi = 1;
         c.check(sccd_ipc_ccd_strategy(c.h, min_distance, max_iterations, tolerance, &toi));
-        return toi;
+        return (Scalar)toi;
+    }
+
+    // ---- cuda/narrow_phase/narrow_phase.cuh:30-46 ------------------------------------------
+    // The reference passes its DeviceMatrix / thrust containers; here the mesh is the one the
+    // (per-thread) context holds -- upload_mesh() below -- and the overlaps are a device array
+    // of pairs, e.g. what BroadPhase::detect_overlaps_partial() returned.  `toi` is lowered in
+    // place, exactly as the reference's Scalar& toi.
+    template <typename VMat, typename IMat>
+    void upload_mesh(const VMat& V0, const VMat& V1, const IMat& E, const IMat& F,
+                     double inflation_radius = 0)
+    {
+        auto& c = detail::default_ctx();
+        detail::upload(c, V0, V1, E, F);
+        c.check(sccd_build_boxes(c.h, inflation_radius));
+    }
+    template <bool is_vf>
+    void narrow_phase(
+        const sccd_pair* d_overlaps, const int64_t n_overlaps, const int max_iter, const Scalar tol,
+        const Scalar minimum_separation_distance, const bool allow_zero_toi, Scalar& toi)
+    {
+        auto& c = detail::default_ctx();
+        double t = toi;
+        c.check(sccd_narrow_phase(
+            c.h, is_vf ? SCCD_VF : SCCD_EE, d_overlaps, n_overlaps, minimum_separation_distance,
+            max_iter, tol, allow_zero_toi, &t, nullptr));
+        toi = (Scalar)t;
     }
 
     // ---- cuda/broad_phase/aabb.cuh:150-188 ------------------------------------------------
@@ -146,6 +184,59 @@ namespace cuda {
         c.check(sccd_get_boxes(c.h, 0, vertex_boxes.data()));
         c.check(sccd_get_boxes(c.h, 1, edge_boxes.data()));
         c.check(sccd_get_boxes(c.h, 2, face_boxes.data()));
+    }
+
+    // The reference's own three builders (aabb.cuh:150-188), computed on the device from
+    // host arrays, as tests/test_broad_phase.cu:88-91 calls them.
+    template <typename VMat>
+    void build_vertex_boxes(
+        const VMat& vertices_t0, const VMat& vertices_t1, std::vector<AABB>& vertex_boxes,
+        double inflation_radius = 0)
+    {
+        if (vertices_t0.rows() != vertices_t1.rows() || vertices_t0.cols() != 3
+            || vertices_t1.cols() != 3) // asserted in aabb.cu:152-153
+            throw std::runtime_error("build_vertex_boxes: expected two (n x 3) matrices");
+        auto& c = detail::default_ctx();
+        vertex_boxes.resize((size_t)vertices_t0.rows());
+        c.check(sccd_build_vertex_boxes(
+            c.h, vertices_t0.data(), vertices_t1.data(), (int64_t)vertices_t0.rows(),
+            inflation_radius, vertex_boxes.data()));
+    }
+    template <typename VMat>
+    void build_vertex_boxes(
+        const VMat& vertices, std::vector<AABB>& vertex_boxes, const double inflation_radius = 0)
+    {
+        if (vertices.cols() != 3) // aabb.cu:121
+            throw std::runtime_error("build_vertex_boxes: expected an (n x 3) matrix");
+        auto& c = detail::default_ctx();
+        vertex_boxes.resize((size_t)vertices.rows());
+        c.check(sccd_build_vertex_boxes(
+            c.h, vertices.data(), nullptr, (int64_t)vertices.rows(), inflation_radius,
+            vertex_boxes.data()));
+    }
+    template <typename IMat>
+    void build_edge_boxes(
+        const std::vector<AABB>& vertex_boxes, const IMat& edges, std::vector<AABB>& edge_boxes)
+    {
+        if (edges.rows() > 0 && edges.cols() != 2)
+            throw std::runtime_error("build_edge_boxes: expected an (n x 2) matrix");
+        auto& c = detail::default_ctx();
+        edge_boxes.resize((size_t)edges.rows());
+        c.check(sccd_build_element_boxes(
+            c.h, vertex_boxes.data(), (int64_t)vertex_boxes.size(), edges.data(),
+            (int64_t)edges.rows(), 2, edge_boxes.data()));
+    }
+    template <typename IMat>
+    void build_face_boxes(
+        const std::vector<AABB>& vertex_boxes, const IMat& faces, std::vector<AABB>& face_boxes)
+    {
+        if (faces.rows() > 0 && faces.cols() != 3)
+            throw std::runtime_error("build_face_boxes: expected an (n x 3) matrix");
+        auto& c = detail::default_ctx();
+        face_boxes.resize((size_t)faces.rows());
+        c.check(sccd_build_element_boxes(
+            c.h, vertex_boxes.data(), (int64_t)vertex_boxes.size(), faces.data(),
+            (int64_t)faces.rows(), 3, face_boxes.data()));
     }
 
     /// A list of caller-made boxes (cuda/broad_phase/aabb.cuh:122-148).  Sorting happens on

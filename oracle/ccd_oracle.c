@@ -19,6 +19,18 @@
  * build container, see tests/test_oracle_vs_ref.py); the narrow-phase half is
  * pinned against the unmodified reference CUDA sources (oracle/_ref/
  * libref_sccd_cuda.so) run on a B200 and frozen as tests/golden/ fixtures.
+ *
+ * Two builds of this file (oracle/Makefile): liborc.so restates the reference's
+ * default double build; liborc_f32.so (-DORC_F32) restates its float build
+ * (SCALABLE_CCD_USE_DOUBLE off, scalar.hpp:16-18).  The C interface is the same
+ * -- double arrays in and out -- and in the float build every value that crosses
+ * it is a float widened to double.  Float narrow phase: the reference compiles
+ * its CUDA code with --use_fast_math (CMakeLists.txt:219-230), i.e. flush-to-zero
+ * arithmetic and a / b = a * rcp.approx(b).  FTZ is restated exactly; the
+ * hardware reciprocal (MUFU.RCP, <= 1 ulp) cannot be, so rcp() below is the
+ * correctly rounded reciprocal and the float narrow phase of this oracle is a
+ * TOLERANCE-level model of the reference (tolerances and split choices can differ
+ * in the last ulp); the float broad phase is exact.
  */
 #include <float.h>
 #include <math.h>
@@ -40,18 +52,52 @@ typedef struct {
     int32_t element_id;
 } orc_aabb;
 
+/* ---- the reference's Scalar (scalar.hpp:13-19) ------------------------------ */
+#ifdef ORC_F32
+typedef float real;
+#define REAL_MAX FLT_MAX
+#define REAL_EPSILON FLT_EPSILON
+#define r_nextafter nextafterf
+#define r_fma fmaf
+#define r_abs fabsf
+#define r_min fminf
+#define r_max fmaxf
+/* flush-to-zero of a result, sign kept (every device op of the float build is .FTZ) */
+static inline real ftz(real x) { return (x != 0 && r_abs(x) < FLT_MIN) ? copysignf(0.0f, x) : x; }
+/* a / b as the float build computes it: a * rcp(b) (MUFU.RCP + FMUL.FTZ) */
+static inline real r_div(real a, real b)
+{
+    const real rcp = ftz((real)(1.0 / (double)ftz(b)));
+    return ftz(ftz(a) * rcp);
+}
+#else
+typedef double real;
+#define REAL_MAX DBL_MAX
+#define REAL_EPSILON DBL_EPSILON
+#define r_nextafter nextafter
+#define r_fma fma
+#define r_abs fabs
+#define r_min fmin
+#define r_max fmax
+static inline real ftz(real x) { return x; }
+static inline real r_div(real a, real b) { return a / b; }
+#endif
+int orc_is_f32(void) { return sizeof(real) == 4; }
+
 /* scalar.hpp:31-49 */
-static inline double nextafter_down(double x) { return nextafter(x, -DBL_MAX); }
-static inline double nextafter_up(double x) { return nextafter(x, DBL_MAX); }
+static inline real nextafter_down(real x) { return r_nextafter(x, -REAL_MAX); }
+static inline real nextafter_up(real x) { return r_nextafter(x, REAL_MAX); }
 
 /* cuda/broad_phase/aabb.cu:19-35 (from_point + conservative_inflation),
- * CPU twin broad_phase/aabb.cpp:17-36. */
-static inline void point_box(const double p[3], double r, double mn[3], double mx[3])
+ * CPU twin broad_phase/aabb.cpp:17-36.  Host code in the reference: no FTZ.
+ * p is cast to Scalar first in the float build (aabb.cu:124-128). */
+static inline void point_box(const double p[3], double r, real mn[3], real mx[3])
 {
-    const double ru = nextafter_up(r);
+    const real ru = nextafter_up((real)r);
     for (int k = 0; k < 3; k++) {
-        mn[k] = nextafter_down(p[k]) - ru;
-        mx[k] = nextafter_up(p[k]) + ru;
+        const real q = (real)p[k];
+        mn[k] = nextafter_down(q) - ru;
+        mx[k] = nextafter_up(q) + ru;
     }
 }
 
@@ -63,7 +109,7 @@ void orc_build_vertex_boxes(
     for (int64_t i = 0; i < nV; i++) {
         double p0[3] = { V0[i], V0[i + nV], V0[i + 2 * nV] };
         double p1[3] = { V1[i], V1[i + nV], V1[i + 2 * nV] };
-        double a0[3], a1[3], b0[3], b1[3];
+        real a0[3], a1[3], b0[3], b1[3];
         point_box(p0, r, a0, a1);
         point_box(p1, r, b0, b1);
         for (int k = 0; k < 3; k++) {
@@ -148,16 +194,16 @@ static int cmp_min_axis(const void* pa, const void* pb)
  * sum(c^2) - sum(c)^2 / n over box centres (serial accumulation order). */
 static int next_axis(const orc_aabb* boxes, int64_t n)
 {
-    double s[3] = { 0, 0, 0 }, s2[3] = { 0, 0, 0 };
+    real s[3] = { 0, 0, 0 }, s2[3] = { 0, 0, 0 };
     for (int64_t i = 0; i < n; i++)
         for (int k = 0; k < 3; k++) {
-            const double c = (boxes[i].min[k] + boxes[i].max[k]) / 2;
+            const real c = ((real)boxes[i].min[k] + (real)boxes[i].max[k]) / 2;
             s[k] += c;
             s2[k] += c * c;
         }
-    double var[3];
+    real var[3];
     for (int k = 0; k < 3; k++)
-        var[k] = s2[k] - s[k] * s[k] / (double)n;
+        var[k] = s2[k] - s[k] * s[k] / (real)n;
     int ax = 0;
     if (var[1] > var[0])
         ax = 1;
@@ -281,68 +327,87 @@ int64_t orc_brute_force(
 /* ------------------------------------------------------------------------- */
 /* Narrow phase (Tight-Inclusion, Scalable-CCD GPU variant)                  */
 
-/* Per-query data: the first 192 bytes of the reference's CCDData
- * (cuda/narrow_phase/ccd_data.cuh:8-26): v0s v1s v2s v3s v0e v1e v2e v3e. */
+/* Per-query data as it crosses the C interface: the first 192 bytes of the
+ * reference's CCDData in the double build (cuda/narrow_phase/ccd_data.cuh:8-26):
+ * v0s v1s v2s v3s v0e v1e v2e v3e. */
 typedef struct {
     double s[4][3]; /* vertices at t=0 */
     double e[4][3]; /* vertices at t=1 */
 } orc_query;
 
+/* ... and in the reference's Scalar: DeviceMatrix<Scalar> / CCDData hold the
+ * vertices cast to Scalar (device_matrix.cuh:21-27); the device code flushes
+ * subnormal inputs at their first use. */
 typedef struct {
-    double tol[3];
-    double err[3];
+    real s[4][3];
+    real e[4][3];
+} rquery;
+
+static inline void to_rquery(const orc_query* q, rquery* r)
+{
+    for (int v = 0; v < 4; v++)
+        for (int k = 0; k < 3; k++) {
+            r->s[v][k] = ftz((real)q->s[v][k]);
+            r->e[v][k] = ftz((real)q->e[v][k]);
+        }
+}
+
+typedef struct {
+    real tol[3];
+    real err[3];
 } orc_bounds;
 
-static inline double linf3(const double* a, const double* b)
+static inline real linf3(const real* a, const real* b)
 {
     /* (b - a).lpNorm<Infinity>() */
-    const double x = fabs(b[0] - a[0]), y = fabs(b[1] - a[1]), z = fabs(b[2] - a[2]);
-    return fmax(fmax(x, y), z);
+    const real x = r_abs(ftz(b[0] - a[0])), y = r_abs(ftz(b[1] - a[1])),
+               z = r_abs(ftz(b[2] - a[2]));
+    return r_max(r_max(x, y), z);
 }
 
 /* cuda/narrow_phase/root_finder.cu:31-46 */
-static inline double max_linf_4(
-    const double* p1, const double* p2, const double* p3, const double* p4,
-    const double* p1e, const double* p2e, const double* p3e, const double* p4e)
+static inline real max_linf_4(
+    const real* p1, const real* p2, const real* p3, const real* p4, const real* p1e,
+    const real* p2e, const real* p3e, const real* p4e)
 {
-    return fmax(
-        fmax(linf3(p1, p1e), linf3(p2, p2e)), fmax(linf3(p3, p3e), linf3(p4, p4e)));
+    return r_max(
+        r_max(linf3(p1, p1e), linf3(p2, p2e)), r_max(linf3(p3, p3e), linf3(p4, p4e)));
 }
 
-static inline void sub3(const double* a, const double* b, double* r)
+static inline void sub3(const real* a, const real* b, real* r)
 {
-    r[0] = a[0] - b[0];
-    r[1] = a[1] - b[1];
-    r[2] = a[2] - b[2];
+    r[0] = ftz(a[0] - b[0]);
+    r[1] = ftz(a[1] - b[1]);
+    r[2] = ftz(a[2] - b[2]);
 }
 
 /* cuda/narrow_phase/root_finder.cu:48-88 (tolerances) and :90-135 (error). */
-void orc_compute_bounds(
-    const orc_query* q, int is_vf, double co_domain_tol, int use_ms, orc_bounds* out)
+static void compute_bounds(
+    const rquery* q, int is_vf, real co_domain_tol, int use_ms, orc_bounds* out)
 {
-    double p000[3], p001[3], p011[3], p010[3], p100[3], p101[3], p111[3], p110[3];
+    real p000[3], p001[3], p011[3], p010[3], p100[3], p101[3], p111[3], p110[3];
     if (is_vf) {
         /* root_finder.cu:50-59 */
-        double tmp[3];
+        real tmp[3];
         sub3(q->s[0], q->s[1], p000);
         sub3(q->s[0], q->s[3], p001);
         for (int k = 0; k < 3; k++)
-            tmp[k] = (q->s[2][k] + q->s[3][k]) - q->s[1][k];
+            tmp[k] = ftz(ftz(q->s[2][k] + q->s[3][k]) - q->s[1][k]);
         sub3(q->s[0], tmp, p011);
         sub3(q->s[0], q->s[2], p010);
         sub3(q->e[0], q->e[1], p100);
         sub3(q->e[0], q->e[3], p101);
         for (int k = 0; k < 3; k++)
-            tmp[k] = (q->e[2][k] + q->e[3][k]) - q->e[1][k];
+            tmp[k] = ftz(ftz(q->e[2][k] + q->e[3][k]) - q->e[1][k]);
         sub3(q->e[0], tmp, p111);
         sub3(q->e[0], q->e[2], p110);
         /* root_finder.cu:61-66 */
-        out->tol[0] = co_domain_tol
-            / (3 * max_linf_4(p000, p001, p011, p010, p100, p101, p111, p110));
-        out->tol[1] = co_domain_tol
-            / (3 * max_linf_4(p000, p100, p101, p001, p010, p110, p111, p011));
-        out->tol[2] = co_domain_tol
-            / (3 * max_linf_4(p000, p100, p110, p010, p001, p101, p111, p011));
+        out->tol[0] = r_div(
+            co_domain_tol, ftz(3 * max_linf_4(p000, p001, p011, p010, p100, p101, p111, p110)));
+        out->tol[1] = r_div(
+            co_domain_tol, ftz(3 * max_linf_4(p000, p100, p101, p001, p010, p110, p111, p011)));
+        out->tol[2] = r_div(
+            co_domain_tol, ftz(3 * max_linf_4(p000, p100, p110, p010, p001, p101, p111, p011)));
     } else {
         /* root_finder.cu:73-80 */
         sub3(q->s[0], q->s[2], p000);
@@ -354,92 +419,101 @@ void orc_compute_bounds(
         sub3(q->e[1], q->e[2], p110);
         sub3(q->e[1], q->e[3], p111);
         /* root_finder.cu:82-87 -- tol[1] deliberately equals tol[0] */
-        out->tol[0] = co_domain_tol
-            / (3 * max_linf_4(p000, p001, p011, p010, p100, p101, p111, p110));
+        out->tol[0] = r_div(
+            co_domain_tol, ftz(3 * max_linf_4(p000, p001, p011, p010, p100, p101, p111, p110)));
         out->tol[1] = out->tol[0];
-        out->tol[2] = co_domain_tol
-            / (3 * max_linf_4(p000, p100, p101, p001, p010, p110, p111, p011));
+        out->tol[2] = r_div(
+            co_domain_tol, ftz(3 * max_linf_4(p000, p100, p101, p001, p010, p110, p111, p011)));
     }
-    /* root_finder.cu:93-122 (double build) */
-    double filter;
+    /* root_finder.cu:93-122 */
+    real filter;
+#ifdef ORC_F32
+    if (!use_ms)
+        filter = is_vf ? 3.576279e-06f : 3.337861e-06f;
+    else
+        filter = is_vf ? 4.053116e-06f : 3.814698e-06f;
+#else
     if (!use_ms)
         filter = is_vf ? 6.661338147750939e-15 : 6.217248937900877e-15;
     else
         filter = is_vf ? 7.549516567451064e-15 : 7.105427357601002e-15;
+#endif
     /* root_finder.cu:124-134 */
     for (int k = 0; k < 3; k++) {
-        double m = 1.0;
+        real m = 1;
         for (int v = 0; v < 4; v++) {
-            m = fmax(m, fabs(q->s[v][k]));
-            m = fmax(m, fabs(q->e[v][k]));
+            m = r_max(m, r_abs(q->s[v][k]));
+            m = r_max(m, r_abs(q->e[v][k]));
         }
-        out->err[k] = m * m * m * filter;
+        out->err[k] = ftz(ftz(ftz(m * m) * m) * filter);
     }
 }
 
 /* cuda/narrow_phase/root_finder.cu:137-155: F at one (t,u,v) corner with the
  * FMA contraction nvcc applies to the reference's expressions. */
 static inline void eval_corner(
-    const orc_query* q, int is_vf, double t, double u, double v, double* r)
+    const rquery* q, int is_vf, real t, real u, real v, real* r)
 {
     for (int k = 0; k < 3; k++) {
-        const double a0 = fma(q->e[0][k] - q->s[0][k], t, q->s[0][k]);
-        const double a1 = fma(q->e[1][k] - q->s[1][k], t, q->s[1][k]);
-        const double a2 = fma(q->e[2][k] - q->s[2][k], t, q->s[2][k]);
-        const double a3 = fma(q->e[3][k] - q->s[3][k], t, q->s[3][k]);
+        const real a0 = ftz(r_fma(ftz(q->e[0][k] - q->s[0][k]), t, q->s[0][k]));
+        const real a1 = ftz(r_fma(ftz(q->e[1][k] - q->s[1][k]), t, q->s[1][k]));
+        const real a2 = ftz(r_fma(ftz(q->e[2][k] - q->s[2][k]), t, q->s[2][k]));
+        const real a3 = ftz(r_fma(ftz(q->e[3][k] - q->s[3][k]), t, q->s[3][k]));
         if (is_vf) {
             /* v - (t1-t0)*u - (t2-t0)*v - t0, root_finder.cu:144 */
-            double x = fma(-(a2 - a1), u, a0);
-            x = fma(-(a3 - a1), v, x);
-            r[k] = x - a1;
+            real x = ftz(r_fma(-ftz(a2 - a1), u, a0));
+            x = ftz(r_fma(-ftz(a3 - a1), v, x));
+            r[k] = ftz(x - a1);
         } else {
             /* ((ea1-ea0)*u+ea0) - ((eb1-eb0)*v+eb0), root_finder.cu:154 */
-            const double x = fma(a1 - a0, u, a0);
-            const double y = fma(a3 - a2, v, a2);
-            r[k] = x - y;
+            const real x = ftz(r_fma(ftz(a1 - a0), u, a0));
+            const real y = ftz(r_fma(ftz(a3 - a2), v, a2));
+            r[k] = ftz(x - y);
         }
     }
 }
 
 typedef struct {
-    double lo[3], hi[3];
+    real lo[3], hi[3];
 } orc_box;
 
 /* cuda/narrow_phase/root_finder.cu:157-198 */
 static inline int origin_in_inclusion(
-    const orc_query* q, const orc_bounds* b, int is_vf, double ms,
-    const orc_box* box, double* true_tol, int* box_in)
+    const rquery* q, const orc_bounds* b, int is_vf, real ms, const orc_box* box,
+    real* true_tol, int* box_in)
 {
-    double cmin[3] = { DBL_MAX, DBL_MAX, DBL_MAX };
-    double cmax[3] = { -DBL_MAX, -DBL_MAX, -DBL_MAX };
+    real cmin[3] = { REAL_MAX, REAL_MAX, REAL_MAX };
+    real cmax[3] = { -REAL_MAX, -REAL_MAX, -REAL_MAX };
     for (int c = 0; c < 8; c++) {
         /* interval.cuh:52-57: bit0 -> t, bit1 -> u, bit2 -> v */
-        const double t = (c & 1) ? box->hi[0] : box->lo[0];
-        const double u = (c & 2) ? box->hi[1] : box->lo[1];
-        const double v = (c & 4) ? box->hi[2] : box->lo[2];
-        double r[3];
+        const real t = (c & 1) ? box->hi[0] : box->lo[0];
+        const real u = (c & 2) ? box->hi[1] : box->lo[1];
+        const real v = (c & 4) ? box->hi[2] : box->lo[2];
+        real r[3];
         eval_corner(q, is_vf, t, u, v, r);
         for (int k = 0; k < 3; k++) {
-            cmin[k] = fmin(cmin[k], r[k]);
-            cmax[k] = fmax(cmax[k], r[k]);
+            cmin[k] = r_min(cmin[k], r[k]);
+            cmax[k] = r_max(cmax[k], r[k]);
         }
     }
-    const double w0 = cmax[0] - cmin[0], w1 = cmax[1] - cmin[1], w2 = cmax[2] - cmin[2];
-    *true_tol = fmax(0.0, fmax(fmax(w0, w1), w2));
+    const real w0 = ftz(cmax[0] - cmin[0]), w1 = ftz(cmax[1] - cmin[1]),
+               w2 = ftz(cmax[2] - cmin[2]);
+    *true_tol = r_max(0, r_max(r_max(w0, w1), w2));
     *box_in = 1;
     for (int k = 0; k < 3; k++)
-        if (cmin[k] - ms > b->err[k] || cmax[k] + ms < -b->err[k])
+        if (ftz(cmin[k] - ms) > b->err[k] || ftz(cmax[k] + ms) < -b->err[k])
             return 0;
     for (int k = 0; k < 3; k++)
-        if (cmin[k] + ms < -b->err[k] || cmax[k] - ms > b->err[k])
+        if (ftz(cmin[k] + ms) < -b->err[k] || ftz(cmax[k] - ms) > b->err[k])
             *box_in = 0;
     return 1;
 }
 
 /* cuda/narrow_phase/root_finder.cu:200-211 */
-static inline int split_dimension(const orc_bounds* b, const double* w)
+static inline int split_dimension(const orc_bounds* b, const real* w)
 {
-    const double r0 = w[0] / b->tol[0], r1 = w[1] / b->tol[1], r2 = w[2] / b->tol[2];
+    const real r0 = r_div(w[0], b->tol[0]), r1 = r_div(w[1], b->tol[1]),
+               r2 = r_div(w[2], b->tol[2]);
     if (r0 >= r1 && r0 >= r2)
         return 0;
     if (r1 >= r0 && r1 >= r2)
@@ -473,29 +547,34 @@ typedef struct {
  *   the cap is ACCEPTED at its t_lo, which can only make the answer earlier.
  */
 static int64_t solve_query(
-    const orc_query* q, int is_vf, double ms, int max_iter, double co_tol,
+    const orc_query* q_in, int is_vf, double ms_in, int max_iter, double co_tol_in,
     int allow_zero_toi, int cap_mode, double* prune_toi, double* global_toi,
     orc_np_stats* st)
 {
+    /* Scalar parameters of the reference's entry points (narrow_phase.cuh:30-46) */
+    const real ms = ftz((real)ms_in), co_tol = ftz((real)co_tol_in);
+    rquery rq;
+    to_rquery(q_in, &rq);
+    const rquery* q = &rq;
     orc_bounds bd;
-    orc_compute_bounds(q, is_vf, co_tol, ms > 0, &bd);
+    compute_bounds(q, is_vf, co_tol, ms > 0, &bd);
 
     static __thread orc_box stack[ORC_STACK_MAX];
     int sp = 0;
     for (int k = 0; k < 3; k++) {
-        stack[0].lo[k] = 0.0;
-        stack[0].hi[k] = 1.0;
+        stack[0].lo[k] = 0;
+        stack[0].hi[k] = 1;
     }
     sp = 1;
     int64_t checks = 0;
-    const double one_plus = 1 / (1 - DBL_EPSILON); /* root_finder.cu:24 */
+    const real one_plus = (real)1 / ((real)1 - REAL_EPSILON); /* root_finder.cu:24 */
     int capped = 0;
 
     while (sp > 0) {
         if (sp > st->max_stack)
             st->max_stack = sp;
         const orc_box box = stack[--sp];
-        const double min_t = box.lo[0];
+        const real min_t = box.lo[0];
         const int64_t seen = checks++; /* root_finder.cu:288-289 */
         if (min_t >= *prune_toi) /* root_finder.cu:295-300 */
             continue;
@@ -510,12 +589,12 @@ static int64_t solve_query(
             continue;
         }
         st->box_checks++;
-        double true_tol;
+        real true_tol;
         int box_in;
         if (!origin_in_inclusion(q, &bd, is_vf, ms, &box, &true_tol, &box_in))
             continue;
-        const double w[3] = { box.hi[0] - box.lo[0], box.hi[1] - box.lo[1],
-                              box.hi[2] - box.lo[2] };
+        const real w[3] = { ftz(box.hi[0] - box.lo[0]), ftz(box.hi[1] - box.lo[1]),
+                            ftz(box.hi[2] - box.lo[2]) };
         int accept = 0;
         /* Condition 1, root_finder.cu:322 */
         if (w[0] <= bd.tol[0] && w[1] <= bd.tol[1] && w[2] <= bd.tol[2])
@@ -529,7 +608,7 @@ static int64_t solve_query(
         if (!accept) {
             const int split = split_dimension(&bd, w);
             /* interval.cuh:18-27 */
-            const double mid = (box.lo[split] + box.hi[split]) / 2;
+            const real mid = ftz(ftz(box.lo[split] + box.hi[split]) / 2);
             /* Condition 4, root_finder.cu:222-225,362 */
             if (box.lo[split] >= mid || mid >= box.hi[split]) {
                 accept = 1;
@@ -541,7 +620,7 @@ static int64_t solve_query(
                 if (split == 0) /* root_finder.cu:229-232 */
                     push_second = mid <= *prune_toi;
                 else if (is_vf) /* root_finder.cu:234-247 */
-                    push_second = (mid + box.lo[split == 1 ? 2 : 1]) <= one_plus;
+                    push_second = ftz(mid + box.lo[split == 1 ? 2 : 1]) <= one_plus;
                 else /* root_finder.cu:249 */
                     push_second = 1;
                 if (sp + 2 > ORC_STACK_MAX)
@@ -579,6 +658,7 @@ void orc_narrow_phase(
     orc_np_stats* stats, int64_t* checks_per_query)
 {
     orc_np_stats total = { 0, 0, 0 };
+    *toi = (double)(real)*toi; /* Scalar& toi */
     if (toi_per_query) {
         double g = *toi;
 #pragma omp parallel
@@ -678,13 +758,16 @@ typedef struct {
 } orc_bfs_item;
 
 int64_t orc_narrow_phase_bfs(
-    const orc_query* queries, int64_t n, int is_vf, double ms, double tol,
+    const orc_query* queries_in, int64_t n, int is_vf, double ms_in, double tol_in,
     int allow_zero_toi, double* toi_per_query, int64_t* total_checks, int64_t* max_level,
     int64_t cap_items)
 {
+    const real ms = ftz((real)ms_in), tol = ftz((real)tol_in);
     orc_bounds* bd = (orc_bounds*)malloc(sizeof(orc_bounds) * (size_t)(n > 0 ? n : 1));
+    rquery* queries = (rquery*)malloc(sizeof(rquery) * (size_t)(n > 0 ? n : 1));
     for (int64_t i = 0; i < n; i++) {
-        orc_compute_bounds(&queries[i], is_vf, tol, ms > 0, &bd[i]);
+        to_rquery(&queries_in[i], &queries[i]);
+        compute_bounds(&queries[i], is_vf, tol, ms > 0, &bd[i]);
         toi_per_query[i] = INFINITY;
     }
     int64_t cap = n > 1024 ? 2 * n : 2048, cur_n = n, levels = 0;
@@ -693,12 +776,12 @@ int64_t orc_narrow_phase_bfs(
     int64_t nxt_cap = cap;
     for (int64_t i = 0; i < n; i++) {
         for (int k = 0; k < 3; k++) {
-            cur[i].box.lo[k] = 0.0;
-            cur[i].box.hi[k] = 1.0;
+            cur[i].box.lo[k] = 0;
+            cur[i].box.hi[k] = 1;
         }
         cur[i].query = (int32_t)i;
     }
-    const double one_plus = 1 / (1 - DBL_EPSILON);
+    const real one_plus = (real)1 / ((real)1 - REAL_EPSILON);
     *total_checks = 0;
     *max_level = n;
     while (cur_n > 0) {
@@ -707,16 +790,16 @@ int64_t orc_narrow_phase_bfs(
         for (int64_t b = 0; b < cur_n; b++) {
             const orc_box box = cur[b].box;
             const int32_t q = cur[b].query;
-            const double min_t = box.lo[0];
+            const real min_t = box.lo[0];
             if (min_t >= toi_per_query[q])
                 continue;
             (*total_checks)++;
-            double true_tol;
+            real true_tol;
             int box_in;
             if (!origin_in_inclusion(&queries[q], &bd[q], is_vf, ms, &box, &true_tol, &box_in))
                 continue;
-            const double w[3] = { box.hi[0] - box.lo[0], box.hi[1] - box.lo[1],
-                                  box.hi[2] - box.lo[2] };
+            const real w[3] = { ftz(box.hi[0] - box.lo[0]), ftz(box.hi[1] - box.lo[1]),
+                                ftz(box.hi[2] - box.lo[2]) };
             int accept = 0;
             if (w[0] <= bd[q].tol[0] && w[1] <= bd[q].tol[1] && w[2] <= bd[q].tol[2])
                 accept = 1;
@@ -726,7 +809,7 @@ int64_t orc_narrow_phase_bfs(
                 accept = 1;
             if (!accept) {
                 const int split = split_dimension(&bd[q], w);
-                const double mid = (box.lo[split] + box.hi[split]) / 2;
+                const real mid = ftz(ftz(box.lo[split] + box.hi[split]) / 2);
                 if (box.lo[split] >= mid || mid >= box.hi[split]) {
                     accept = 1;
                 } else {
@@ -734,6 +817,7 @@ int64_t orc_narrow_phase_bfs(
                         nxt_cap *= 2;
                         if (cap_items > 0 && nxt_cap > 4 * cap_items) {
                             free(bd);
+                            free(queries);
                             free(cur);
                             free(nxt);
                             *max_level = nxt_cap;
@@ -749,7 +833,7 @@ int64_t orc_narrow_phase_bfs(
                     if (split == 0)
                         push_second = mid <= toi_per_query[q];
                     else if (is_vf)
-                        push_second = (mid + box.lo[split == 1 ? 2 : 1]) <= one_plus;
+                        push_second = ftz(mid + box.lo[split == 1 ? 2 : 1]) <= one_plus;
                     else
                         push_second = 1;
                     if (push_second) {
@@ -778,6 +862,7 @@ int64_t orc_narrow_phase_bfs(
         cur_n = nn;
     }
     free(bd);
+    free(queries);
     free(cur);
     free(nxt);
     return levels;

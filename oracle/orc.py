@@ -26,24 +26,29 @@ def build(ref: bool = False) -> None:
     """Compile liborc.so (and oracle/_ref when the reference sources are present)."""
     subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
     if ref and os.path.isdir("/root/reference/src"):
-        subprocess.check_call(["make", "-s", "-j8", "-C", HERE, "ref_cpu", "ref_cuda"])
+        subprocess.check_call(["make", "-s", "-j8", "-C", HERE, "ref_cpu", "ref_cuda", "ref_f32"])
 
 
-_lib = None
+_libs = {}
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        path = os.path.join(HERE, "liborc.so")
+def lib(f32: bool = False):
+    """liborc.so (the reference's default double build) or liborc_f32.so (its float build,
+    SCALABLE_CCD_USE_DOUBLE off).  Same C interface: double arrays in and out."""
+    f32 = bool(f32)
+    if f32 not in _libs:
+        path = os.path.join(HERE, "liborc_f32.so" if f32 else "liborc.so")
         if not os.path.exists(path):
             build()
-        _lib = C.CDLL(path)
-        _lib.orc_sort_and_sweep.restype = C.c_int64
-        _lib.orc_sort_and_sweep_two_lists.restype = C.c_int64
-        _lib.orc_brute_force.restype = C.c_int64
-        assert _lib.orc_sizeof_aabb() == 64 and _lib.orc_sizeof_query() == 192
-    return _lib
+        L = C.CDLL(path)
+        L.orc_sort_and_sweep.restype = C.c_int64
+        L.orc_sort_and_sweep_two_lists.restype = C.c_int64
+        L.orc_brute_force.restype = C.c_int64
+        L.orc_narrow_phase_bfs.restype = C.c_int64
+        assert L.orc_sizeof_aabb() == 64 and L.orc_sizeof_query() == 192
+        assert bool(L.orc_is_f32()) == f32
+        _libs[f32] = L
+    return _libs[f32]
 
 
 class NpStats(C.Structure):
@@ -57,14 +62,14 @@ def _mesh_args(s):
     return V0, V1, E, F
 
 
-def build_boxes(scene, r: float = 0.0):
+def build_boxes(scene, r: float = 0.0, f32: bool = False):
     """(vertex, edge, face) boxes as AABB_DTYPE arrays -- aabb.cu:115-229."""
     V0, V1, E, F = _mesh_args(scene)
     nV, nE, nF = V0.shape[0], E.shape[0], F.shape[0]
     vb = np.zeros(nV, AABB_DTYPE)
     eb = np.zeros(nE, AABB_DTYPE)
     fb = np.zeros(nF, AABB_DTYPE)
-    L = lib()
+    L = lib(f32)
     L.orc_build_vertex_boxes(_p(V0), _p(V1), C.c_int64(nV), C.c_double(r), _p(vb))
     L.orc_build_edge_boxes(_p(vb), _p(E), C.c_int64(nE), _p(eb))
     L.orc_build_face_boxes(_p(vb), _p(F), C.c_int64(nF), _p(fb))
@@ -81,10 +86,11 @@ def _grow(fn, guess):
         cap = int(n)
 
 
-def sort_and_sweep(boxes, axis: int = 0):
-    """Single-list SAP -- sort_and_sweep.cpp:198-211.  Returns (pairs, next_axis)."""
+def sort_and_sweep(boxes, axis: int = 0, f32: bool = False):
+    """Single-list SAP -- sort_and_sweep.cpp:198-211.  Returns (pairs, next_axis).
+    (f32 only matters for the next axis: the variance is accumulated in Scalar.)"""
     ax = C.c_int(axis)
-    L = lib()
+    L = lib(f32)
 
     def fn(out, cap):
         ax.value = axis
@@ -95,10 +101,10 @@ def sort_and_sweep(boxes, axis: int = 0):
     return pairs, ax.value
 
 
-def sort_and_sweep_two_lists(A, B, axis: int = 0):
+def sort_and_sweep_two_lists(A, B, axis: int = 0, f32: bool = False):
     """Two-list SAP (A = vertices, B = faces) -- sort_and_sweep.cpp:213-239."""
     ax = C.c_int(axis)
-    L = lib()
+    L = lib(f32)
 
     def fn(out, cap):
         ax.value = axis
@@ -141,7 +147,7 @@ def gather_queries(scene, pairs, is_vf: bool) -> np.ndarray:
 
 def narrow_phase(queries, is_vf: bool, ms: float = 0.0, max_iter: int = -1, tol: float = 1e-6,
                  allow_zero_toi: bool = True, toi: float = 1.0, per_query: bool = True,
-                 cap_mode: int = 1):
+                 cap_mode: int = 1, f32: bool = False):
     """Tight-Inclusion over (n, 24) query arrays.  Returns (toi, toi_per_query | None,
     stats dict); stats["checks"] holds the per-query box counts."""
     q = np.ascontiguousarray(queries, dtype=np.float64).reshape(-1, 24)
@@ -149,7 +155,7 @@ def narrow_phase(queries, is_vf: bool, ms: float = 0.0, max_iter: int = -1, tol:
     tpq = np.empty(len(q), np.float64) if per_query else None
     st = NpStats()
     checks = np.zeros(len(q), np.int64)
-    lib().orc_narrow_phase(
+    lib(f32).orc_narrow_phase(
         _p(q), C.c_int64(len(q)), C.c_int(int(is_vf)), C.c_double(ms), C.c_int(max_iter),
         C.c_double(tol), C.c_int(int(allow_zero_toi)), C.c_int(cap_mode), C.byref(t),
         _p(tpq) if per_query else None, C.byref(st), _p(checks))
@@ -158,22 +164,21 @@ def narrow_phase(queries, is_vf: bool, ms: float = 0.0, max_iter: int = -1, tol:
 
 
 def tractable(queries, is_vf: bool, ms: float, tol: float, allow_zero_toi: bool = True,
-              limit: int = 20000) -> np.ndarray:
+              limit: int = 20000, f32: bool = False) -> np.ndarray:
     """Mask of the queries the solver finishes within `limit` box checks.  Grazing
     queries with ms > 0 can need >1e8 boxes (for the reference as well); uncapped parity
     runs use this mask, capped runs use everything."""
-    _, _, st = narrow_phase(queries, is_vf, ms, limit, tol, allow_zero_toi, cap_mode=1)
+    _, _, st = narrow_phase(queries, is_vf, ms, limit, tol, allow_zero_toi, cap_mode=1, f32=f32)
     return st["checks"] <= limit
 
 
 def narrow_phase_bfs(queries, is_vf: bool, ms: float = 0.0, tol: float = 1e-6,
-                     allow_zero_toi: bool = True, cap_items: int = 0):
+                     allow_zero_toi: bool = True, cap_items: int = 0, f32: bool = False):
     """The reference's level-synchronous traversal (root_finder.cu:431-447).  Returns
     (toi_per_query, levels, total_checks, widest_level); levels == -1 if the front outgrew
     4 * cap_items and the run was abandoned."""
     q = np.ascontiguousarray(queries, dtype=np.float64).reshape(-1, 24)
-    L = lib()
-    L.orc_narrow_phase_bfs.restype = C.c_int64
+    L = lib(f32)
     tpq = np.empty(len(q), np.float64)
     tc, ml = C.c_int64(0), C.c_int64(0)
     lv = L.orc_narrow_phase_bfs(
@@ -183,7 +188,7 @@ def narrow_phase_bfs(queries, is_vf: bool, ms: float = 0.0, tol: float = 1e-6,
 
 
 def tractable_bfs(queries, is_vf: bool, ms: float, tol: float, allow_zero_toi: bool = True,
-                  front_limit: int = 4096) -> np.ndarray:
+                  front_limit: int = 4096, f32: bool = False) -> np.ndarray:
     """Mask of the queries whose BREADTH-first front stays below front_limit entries.  The
     reference's ring queue silently wraps over unprocessed boxes when a front outgrows it
     (the full-check is not atomic with the push, ccd_buffer.cuh:25-34), so goldens frozen
@@ -192,30 +197,31 @@ def tractable_bfs(queries, is_vf: bool, ms: float, tol: float, allow_zero_toi: b
     mask = np.zeros(len(q), bool)
     for i in range(len(q)):
         _, lv, _, ml = narrow_phase_bfs(q[i:i + 1], is_vf, ms, tol, allow_zero_toi,
-                                        cap_items=front_limit)
+                                        cap_items=front_limit, f32=f32)
         mask[i] = lv > 0 and ml <= front_limit
     return mask
 
 
 def ccd(scene, ms: float = 0.0, max_iter: int = -1, tol: float = 1e-6,
-        allow_zero_toi: bool = True, per_query: bool = True):
+        allow_zero_toi: bool = True, per_query: bool = True, f32: bool = False):
     """Whole pipeline on the CPU, as cuda/ccd.cu:80-146 composes it."""
-    vb, eb, fb = build_boxes(scene, ms)
-    vf, _ = sort_and_sweep_two_lists(vb, fb, 0)
-    ee, _ = sort_and_sweep(eb, 0)
+    vb, eb, fb = build_boxes(scene, ms, f32)
+    vf, _ = sort_and_sweep_two_lists(vb, fb, 0, f32)
+    ee, _ = sort_and_sweep(eb, 0, f32)
     vf, ee = canonical(vf), canonical(ee)
     toi = 1.0
     toi, tvf, s1 = narrow_phase(gather_queries(scene, vf, True), True, ms, max_iter, tol,
-                                allow_zero_toi, toi, per_query)
+                                allow_zero_toi, toi, per_query, f32=f32)
     toi, tee, s2 = narrow_phase(gather_queries(scene, ee, False), False, ms, max_iter, tol,
-                                allow_zero_toi, toi, per_query)
+                                allow_zero_toi, toi, per_query, f32=f32)
     return {"toi": toi, "vf": vf, "ee": ee, "toi_vf": tvf, "toi_ee": tee,
             "box_checks": s1["box_checks"] + s2["box_checks"]}
 
 
 # ----------------------------------------------------------------------------- _ref
-def ref_cpu():
-    path = os.path.join(REF_DIR, "libref_sccd_cpu.so")
+def ref_cpu(f32: bool = False):
+    """The unmodified reference CPU broad phase (f32: built with SCALABLE_CCD_USE_DOUBLE off)."""
+    path = os.path.join(REF_DIR, "libref_sccd_cpu_f32.so" if f32 else "libref_sccd_cpu.so")
     if not os.path.exists(path):
         return None
     L = C.CDLL(path)
@@ -223,8 +229,8 @@ def ref_cpu():
     return L
 
 
-def ref_cpu_build_boxes(scene, r: float = 0.0):
-    L = ref_cpu()
+def ref_cpu_build_boxes(scene, r: float = 0.0, f32: bool = False):
+    L = ref_cpu(f32)
     V0, V1, E, F = _mesh_args(scene)
     nV, nE, nF = V0.shape[0], E.shape[0], F.shape[0]
     vb = np.zeros(nV, AABB_DTYPE)
@@ -235,10 +241,11 @@ def ref_cpu_build_boxes(scene, r: float = 0.0):
     return vb, eb, fb
 
 
-def ref_cpu_broad_phase(scene, r: float = 0.0, axis: int = 0, want_pairs: bool = True):
+def ref_cpu_broad_phase(scene, r: float = 0.0, axis: int = 0, want_pairs: bool = True,
+                        f32: bool = False):
     """Unmodified reference CPU path: boxes + sort_and_sweep VF + EE.
     Returns dict(vf, ee, axes, seconds, threads)."""
-    L = ref_cpu()
+    L = ref_cpu(f32)
     V0, V1, E, F = _mesh_args(scene)
     nV, nE, nF = V0.shape[0], E.shape[0], F.shape[0]
     counts = (C.c_int64 * 2)()
@@ -263,8 +270,9 @@ def ref_cpu_broad_phase(scene, r: float = 0.0, axis: int = 0, want_pairs: bool =
             "seconds": sec, "threads": L.ref_cpu_num_threads()}
 
 
-def ref_cuda(per_query: bool = False):
-    path = os.path.join(REF_DIR, "libref_sccd_cuda_pq.so" if per_query else "libref_sccd_cuda.so")
+def ref_cuda(per_query: bool = False, f32: bool = False):
+    name = "libref_sccd_cuda" + ("_pq" if per_query else "") + ("_f32" if f32 else "") + ".so"
+    path = os.path.join(REF_DIR, name)
     if not os.path.exists(path):
         return None
     if path in _ref_cuda_libs:
@@ -282,8 +290,8 @@ _ref_cuda_libs = {}
 
 
 def ref_cuda_ccd(scene, ms=0.0, max_iter=-1, tol=1e-6, allow_zero_toi=True, per_query=False,
-                 coll_cap=0):
-    L = ref_cuda(per_query)
+                 coll_cap=0, f32=False):
+    L = ref_cuda(per_query, f32)
     V0, V1, E, F = _mesh_args(scene)
     ids = np.empty((max(coll_cap, 1), 2), np.int32)
     tois = np.empty(max(coll_cap, 1), np.float64)
@@ -299,8 +307,8 @@ def ref_cuda_ccd(scene, ms=0.0, max_iter=-1, tol=1e-6, allow_zero_toi=True, per_
             "coll_toi": tois[:n]}
 
 
-def ref_cuda_broad_phase(scene, r=0.0, want_pairs=True):
-    L = ref_cuda(False)
+def ref_cuda_broad_phase(scene, r=0.0, want_pairs=True, f32=False):
+    L = ref_cuda(False, f32)
     V0, V1, E, F = _mesh_args(scene)
     counts = (C.c_int64 * 2)()
     ms_el = C.c_double(0)
@@ -323,8 +331,8 @@ def ref_cuda_broad_phase(scene, r=0.0, want_pairs=True):
 
 
 def ref_cuda_narrow_queries(queries, is_vf, ms=0.0, max_iter=-1, tol=1e-6, allow_zero_toi=True,
-                            toi=1.0, per_query=True, min_queue_units=1 << 26):
-    L = ref_cuda(per_query)
+                            toi=1.0, per_query=True, min_queue_units=1 << 26, f32=False):
+    L = ref_cuda(per_query, f32)
     q = np.ascontiguousarray(queries, dtype=np.float64).reshape(-1, 24)
     t = C.c_double(toi)
     tpq = np.empty(len(q), np.float64) if per_query else None

@@ -9,7 +9,9 @@
 #ifdef REF_WITH_CUDA
 #define SCALABLE_CCD_WITH_CUDA
 #endif
+#ifndef REF_USE_FLOAT /* float build: scalar.hpp:16-18 */
 #define SCALABLE_CCD_USE_DOUBLE
+#endif
 #ifdef REF_TOI_PER_QUERY
 #define SCALABLE_CCD_TOI_PER_QUERY
 #endif

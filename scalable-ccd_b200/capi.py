@@ -15,6 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsccd_b200.so")
 
 VF, EE, BOXES = 0, 1, 2
+F64, F32 = 0, 1  # sccd_set_scalar_type: the reference's SCALABLE_CCD_USE_DOUBLE switch
 OK, ERR_CUDA, ERR_ARG, ERR_STATE, ERR_MEMORY = 0, -1, -2, -3, -4
 
 AABB_DTYPE = np.dtype(
@@ -24,7 +25,8 @@ AABB_DTYPE = np.dtype(
 SYMBOLS = [
     "sccd_create", "sccd_destroy", "sccd_last_error", "sccd_set_memory_limit",
     "sccd_set_max_pairs_per_chunk", "sccd_set_queue_capacity", "sccd_set_grid_cells",
-    "sccd_set_shard",
+    "sccd_set_shard", "sccd_set_scalar_type",
+    "sccd_build_vertex_boxes", "sccd_build_element_boxes",
     "sccd_upload_mesh", "sccd_build_boxes", "sccd_get_boxes", "sccd_set_boxes",
     "sccd_broad_phase_begin",
     "sccd_broad_phase_partial", "sccd_broad_phase_is_complete", "sccd_broad_phase",
@@ -136,6 +138,35 @@ class Context:
 
     def set_shard(self, rank: int, world: int):
         self._chk(self.L.sccd_set_shard(self._h, C.c_int(rank), C.c_int(world)))
+
+    def set_scalar_type(self, scalar: int):
+        """F64 (default) or F32 = the reference built with SCALABLE_CCD_USE_DOUBLE=OFF."""
+        self._chk(self.L.sccd_set_scalar_type(self._h, C.c_int(scalar)))
+
+    # ---- the reference's box builders by name, host arrays in and out
+    def build_vertex_boxes(self, V0, V1=None, inflation_radius: float = 0.0):
+        """build_vertex_boxes(V0, V1, boxes, r) / build_vertex_boxes(V, boxes, r)."""
+        V0 = np.asfortranarray(V0, dtype=np.float64)
+        if V1 is not None:
+            V1 = np.asfortranarray(V1, dtype=np.float64)
+            if V1.shape != V0.shape:
+                raise ValueError("V0 and V1 must have the same shape")
+        out = np.zeros(max(len(V0), 1), AABB_DTYPE)
+        self._chk(self.L.sccd_build_vertex_boxes(
+            self._h, _ptr(V0), _ptr(V1), C.c_int64(len(V0)), C.c_double(inflation_radius),
+            _ptr(out)))
+        return out[:len(V0)]
+
+    def build_element_boxes(self, vertex_boxes, idx):
+        """build_edge_boxes (idx n x 2) / build_face_boxes (idx n x 3) from vertex boxes."""
+        vb = np.ascontiguousarray(vertex_boxes)
+        assert vb.dtype == AABB_DTYPE
+        idx = np.asfortranarray(idx, dtype=np.int32)
+        out = np.zeros(max(len(idx), 1), AABB_DTYPE)
+        self._chk(self.L.sccd_build_element_boxes(
+            self._h, _ptr(vb), C.c_int64(len(vb)), _ptr(idx), C.c_int64(len(idx)),
+            C.c_int(idx.shape[1]), _ptr(out)))
+        return out[:len(idx)]
 
     # ---- mesh + boxes
     def upload_mesh(self, V0, V1, E, F, sizes=None, host=False):

@@ -61,6 +61,10 @@ struct sccd_ctx {
     int64_t max_pairs_per_chunk = 0;
     int64_t queue_cap = 0;
     int rank = 0, world = 1;
+    // SCCD_F32: the reference's float build (scalar.hpp:16-18) -- inputs rounded to float, boxes
+    // by nextafterf, narrow phase in float arithmetic; every buffer stays double (float values
+    // are exact in double and compare the same)
+    bool f32 = false;
 
     // mesh
     int nV = 0, nE = 0, nF = 0;
@@ -69,6 +73,7 @@ struct sccd_ctx {
     const int32_t *dE = nullptr, *dF = nullptr;
     DevBuf bV0, bV1, bE, bF;
     DevBuf b_vtab, b_vbox;
+    DevBuf b_io[3]; // staging of the stand-alone box builders (sccd_build_vertex/element_boxes)
 
     // box lists: [0] = vertex+face (two lists), [1] = edges
     struct ListBufs {
@@ -595,14 +600,17 @@ void build_boxes(sccd_ctx* c, double inflation_radius)
     prepare_list(c, 0, (int)nVF, true);
     prepare_list(c, 1, nE, false);
 
-    // aabb.cu:31-34: the radius itself is rounded up once
-    const double radius_up = std::nextafter(inflation_radius, DBL_MAX);
+    // aabb.cu:31-34: the radius itself is rounded up once (float build: converted to Scalar
+    // first, scalar.hpp:43-49)
+    const double radius_up = c->f32
+        ? (double)std::nextafterf((float)inflation_radius, FLT_MAX)
+        : std::nextafter(inflation_radius, DBL_MAX);
     auto& LV = c->lists[0];
     auto& LE = c->lists[1];
     const size_t kt_boxes = kt_begin(c, &c->stats.ms_k_boxes);
     launch_mesh_boxes(
-        c->dV0, c->dV1, nV, radius_up, c->b_vtab.as<VertexRec>(), c->b_vbox.as<double>(), c->dE,
-        nE, c->dF, nF, LE.unsorted, LV.unsorted, c->stream, c->lc);
+        c->dV0, c->dV1, nV, radius_up, c->f32, c->b_vtab.as<VertexRec>(), c->b_vbox.as<double>(),
+        c->dE, nE, c->dF, nF, LE.unsorted, LV.unsorted, c->stream, c->lc);
     kt_end(c, kt_boxes);
     record(c, EV_BUILD);
     // sync 1: statistics of both lists; sync 2: record counts of both lists
@@ -905,8 +913,11 @@ void narrow_enqueue(
         throw std::invalid_argument("narrow_phase: more than 2^32 queries in one batch");
     narrow_setup(c, in.n);
     NarrowParams P;
-    P.ms = ms;
-    P.tol = tol;
+    // float build: ms / tol are Scalar parameters of the reference's entry points, i.e. rounded
+    // to float on the way in (narrow_phase.cuh:30-46 with Scalar = float)
+    P.ms = c->f32 ? (double)(float)ms : ms;
+    P.tol = c->f32 ? (double)(float)tol : tol;
+    ms = P.ms;
     P.max_iter = max_iter;
     P.allow_zero_toi = allow_zero_toi ? 1 : 0;
     P.use_ms = ms > 0 ? 1 : 0;
@@ -928,12 +939,12 @@ void narrow_enqueue(
     uint32_t* survivors = nullptr;
     {
         const char* e = getenv("SCCD_NP_CULL");
-        if (!e || atoi(e) != 0)
+        if (!c->f32 && (!e || atoi(e) != 0)) // (argued for the double build's filters only)
             survivors = (uint32_t*)R.b_surv.reserve((size_t)in.n * 4);
     }
     const size_t kt = kt_begin(c, &c->stats.ms_k_narrow[kind]);
     launch_narrow_phase(
-        kind == SCCD_VF, in, P, R.b_counters.as<NarrowCounters>(), d_gtoi,
+        kind == SCCD_VF, c->f32, in, P, R.b_counters.as<NarrowCounters>(), d_gtoi,
         R.b_items[0].as<WorkItem>(), R.b_items[1].as<WorkItem>(), R.item_cap, d_toi_per_query,
         checks, survivors, c->num_sms, st, c->lc);
     kt_end(c, kt);
@@ -964,7 +975,7 @@ void narrow_finish(sccd_ctx* c, double* d_gtoi)
         if (extra > 64)
             throw std::runtime_error("narrow phase: bisection deeper than 8192 levels");
         launch_narrow_extra_round(
-            kind == SCCD_VF, R.pending.in, R.pending.P, R.b_counters.as<NarrowCounters>(), d_gtoi,
+            kind == SCCD_VF, c->f32, R.pending.in, R.pending.P, R.b_counters.as<NarrowCounters>(), d_gtoi,
             R.b_items[0].as<WorkItem>(), R.b_items[1].as<WorkItem>(), R.item_cap, extra,
             R.pending.d_tq, R.pending.checks, c->num_sms, st, c->lc);
         SCCD_CUDA(cudaMemcpyAsync(
@@ -1007,6 +1018,8 @@ void narrow_run(
         c->stats.n_queries[kind] += in.n;
         return;
     }
+    if (c->f32) // Scalar& toi of the float build
+        *toi_inout = (double)(float)*toi_inout;
     double* d_gtoi = gtoi_set(c, *toi_inout, c->cur->stream);
     narrow_enqueue(c, kind, in, ms, max_iter, tol, allow_zero_toi, d_gtoi, d_toi_per_query);
     if (!c->cur->pending.active)
@@ -1160,6 +1173,8 @@ void run_pipeline(
                     toi = before;
                     narrow_run(c, kind, in, 0.0, -1, tol, false, &toi, nullptr);
                     toi *= 0.8;
+                    if (c->f32) // earliest_toi is a float there (ipc_ccd_strategy.cu:88)
+                        toi = (double)(float)toi;
                 }
             }
             if (d_tq) {
@@ -1291,6 +1306,18 @@ int sccd_set_grid_cells(sccd_ctx* ctx, int max_cells)
     return SCCD_OK;
 }
 
+int sccd_set_scalar_type(sccd_ctx* ctx, int type)
+{
+    if (!ctx || (type != SCCD_F64 && type != SCCD_F32))
+        return SCCD_ERR_ARG;
+    if (ctx->f32 != (type == SCCD_F32)) {
+        ctx->f32 = type == SCCD_F32;
+        ctx->have_boxes = false; // boxes and the vertex table depend on the scalar type
+        ctx->runs[0].bp_kind = ctx->runs[1].bp_kind = -1;
+    }
+    return SCCD_OK;
+}
+
 int sccd_set_shard(sccd_ctx* ctx, int rank, int world)
 {
     if (!ctx || world < 1 || rank < 0 || rank >= world || world > 16)
@@ -1317,6 +1344,68 @@ int sccd_build_boxes(sccd_ctx* ctx, double inflation_radius)
         record(ctx, EV_T0);
         build_boxes(ctx, inflation_radius);
         finish_stats(ctx, false);
+        return SCCD_OK;
+    });
+}
+
+int sccd_build_vertex_boxes(
+    sccd_ctx* ctx, const double* V0, const double* V1, int64_t nV, double inflation_radius,
+    sccd_aabb* out)
+{
+    return guarded(ctx, [&] {
+        if (nV < 0 || nV >= (1ll << 31) || (nV && (!V0 || !out)))
+            throw std::invalid_argument("build_vertex_boxes: bad argument");
+        if (nV == 0)
+            return SCCD_OK;
+        const size_t vb = sizeof(double) * 3 * (size_t)nV;
+        double* d0 = (double*)ctx->b_io[0].reserve(vb);
+        double* d1 = d0; // single frame: the box of a point (aabb.cuh:150-153)
+        SCCD_CUDA(cudaMemcpyAsync(d0, V0, vb, cudaMemcpyHostToDevice, ctx->stream));
+        if (V1) {
+            d1 = (double*)ctx->b_io[1].reserve(vb);
+            SCCD_CUDA(cudaMemcpyAsync(d1, V1, vb, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        sccd_aabb* d_out = (sccd_aabb*)ctx->b_io[2].reserve(sizeof(sccd_aabb) * (size_t)nV);
+        const double radius_up = ctx->f32
+            ? (double)std::nextafterf((float)inflation_radius, FLT_MAX)
+            : std::nextafter(inflation_radius, DBL_MAX);
+        launch_vertex_aabbs(d0, d1, (int)nV, radius_up, ctx->f32, d_out, ctx->stream, ctx->lc);
+        SCCD_CUDA(cudaMemcpyAsync(
+            out, d_out, sizeof(sccd_aabb) * (size_t)nV, cudaMemcpyDeviceToHost, ctx->stream));
+        SCCD_CUDA(cudaStreamSynchronize(ctx->stream));
+        return SCCD_OK;
+    });
+}
+
+int sccd_build_element_boxes(
+    sccd_ctx* ctx, const sccd_aabb* vertex_boxes, int64_t nV, const int32_t* idx, int64_t n,
+    int verts_per_element, sccd_aabb* out)
+{
+    return guarded(ctx, [&] {
+        if (nV < 0 || n < 0 || nV >= (1ll << 31) || n >= (1ll << 31)
+            || (verts_per_element != 2 && verts_per_element != 3)
+            || (n && (!idx || !out || !vertex_boxes)))
+            throw std::invalid_argument("build_element_boxes: bad argument");
+        if (n == 0)
+            return SCCD_OK;
+        const size_t ib = sizeof(int32_t) * (size_t)verts_per_element * (size_t)n;
+        sccd_aabb* d_vb = (sccd_aabb*)ctx->b_io[0].reserve(sizeof(sccd_aabb) * (size_t)std::max<int64_t>(nV, 1));
+        int32_t* d_idx = (int32_t*)ctx->b_io[1].reserve(ib + 16);
+        sccd_aabb* d_out = (sccd_aabb*)ctx->b_io[2].reserve(sizeof(sccd_aabb) * (size_t)n);
+        int* d_bad = reinterpret_cast<int*>(reinterpret_cast<char*>(d_idx) + ((ib + 3) & ~(size_t)3));
+        SCCD_CUDA(cudaMemcpyAsync(
+            d_vb, vertex_boxes, sizeof(sccd_aabb) * (size_t)nV, cudaMemcpyHostToDevice, ctx->stream));
+        SCCD_CUDA(cudaMemcpyAsync(d_idx, idx, ib, cudaMemcpyHostToDevice, ctx->stream));
+        SCCD_CUDA(cudaMemsetAsync(d_bad, 0, 4, ctx->stream));
+        launch_element_aabbs(
+            d_vb, (int)nV, d_idx, (int)n, verts_per_element, d_out, d_bad, ctx->stream, ctx->lc);
+        int bad = 0;
+        SCCD_CUDA(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        SCCD_CUDA(cudaMemcpyAsync(
+            out, d_out, sizeof(sccd_aabb) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        SCCD_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (bad)
+            throw std::invalid_argument("build_element_boxes: vertex index out of range");
         return SCCD_OK;
     });
 }

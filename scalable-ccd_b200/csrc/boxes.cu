@@ -18,6 +18,9 @@ constexpr int kThreads = 256;
 
 __device__ __forceinline__ double next_down(double x) { return nextafter(x, -DBL_MAX); }
 __device__ __forceinline__ double next_up(double x) { return nextafter(x, DBL_MAX); }
+// float build of the reference (scalar.hpp:31-49 with Scalar = float)
+__device__ __forceinline__ float next_down(float x) { return nextafterf(x, -FLT_MAX); }
+__device__ __forceinline__ float next_up(float x) { return nextafterf(x, FLT_MAX); }
 
 __device__ __forceinline__ void store_record(
     const BoxArrays& out, int k, const double lo[3], const double hi[3], int4 id)
@@ -28,6 +31,12 @@ __device__ __forceinline__ void store_record(
 }
 
 // aabb.cu:146-184 build_vertex_boxes(V0, V1, r) + from_point + conservative_inflation.
+// F32: the reference's float build -- the vertices are cast to float first (aabb.cu:124-128,
+// round to nearest), the box is made with nextafterf and float adds, and everything downstream
+// (vertex table, exact records) holds those float values widened to double, which is exact and
+// keeps every comparison of the sweep unchanged.  This file is compiled without -ftz, like the
+// reference's host code that makes its boxes.
+template <bool F32>
 __global__ void __launch_bounds__(kThreads) vertex_boxes_kernel(
     const double* __restrict__ V0, const double* __restrict__ V1, int nV, double radius_up,
     VertexRec* __restrict__ vtab, double* __restrict__ vbox, BoxArrays vf)
@@ -40,13 +49,26 @@ __global__ void __launch_bounds__(kThreads) vertex_boxes_kernel(
     for (int k = 0; k < 3; k++) {
         p0[k] = V0[i + (size_t)k * nV];
         p1[k] = V1[i + (size_t)k * nV];
-        // aabb.cu:29-34 on each end point, then AABB(a, b) = componentwise min / max
-        const double a_lo = __dsub_rn(next_down(p0[k]), radius_up);
-        const double b_lo = __dsub_rn(next_down(p1[k]), radius_up);
-        const double a_hi = __dadd_rn(next_up(p0[k]), radius_up);
-        const double b_hi = __dadd_rn(next_up(p1[k]), radius_up);
-        lo[k] = fmin(a_lo, b_lo);
-        hi[k] = fmax(a_hi, b_hi);
+        if (F32) {
+            const float q0 = __double2float_rn(p0[k]), q1 = __double2float_rn(p1[k]);
+            const float r = (float)radius_up; // already a float value (made on the host)
+            const float a_lo = __fsub_rn(next_down(q0), r);
+            const float b_lo = __fsub_rn(next_down(q1), r);
+            const float a_hi = __fadd_rn(next_up(q0), r);
+            const float b_hi = __fadd_rn(next_up(q1), r);
+            lo[k] = (double)fminf(a_lo, b_lo);
+            hi[k] = (double)fmaxf(a_hi, b_hi);
+            p0[k] = (double)q0;
+            p1[k] = (double)q1;
+        } else {
+            // aabb.cu:29-34 on each end point, then AABB(a, b) = componentwise min / max
+            const double a_lo = __dsub_rn(next_down(p0[k]), radius_up);
+            const double b_lo = __dsub_rn(next_down(p1[k]), radius_up);
+            const double a_hi = __dadd_rn(next_up(p0[k]), radius_up);
+            const double b_hi = __dadd_rn(next_up(p1[k]), radius_up);
+            lo[k] = fmin(a_lo, b_lo);
+            hi[k] = fmax(a_hi, b_hi);
+        }
     }
     VertexRec r;
 #pragma unroll
@@ -110,6 +132,69 @@ __global__ void __launch_bounds__(kThreads) element_boxes_kernel(
     }
 }
 
+// ---- the reference's three box builders by name, on caller-made arrays ------------------
+// (cuda/broad_phase/aabb.cuh:150-188).  The pipeline uses the fused mesh kernels above; these
+// serve callers that build and keep the boxes themselves, as tests/test_broad_phase.cu:88-91 does.
+// AoS in and out (the reference's 64-byte cuda::AABB).
+template <bool F32>
+__global__ void __launch_bounds__(kThreads) vertex_aabb_kernel(
+    const double* __restrict__ V0, const double* __restrict__ V1, int nV, double radius_up,
+    sccd_aabb* __restrict__ out)
+{
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= nV)
+        return;
+    sccd_aabb b;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const double p0 = V0[i + (size_t)k * nV], p1 = V1[i + (size_t)k * nV];
+        if (F32) {
+            const float q0 = __double2float_rn(p0), q1 = __double2float_rn(p1);
+            const float r = (float)radius_up;
+            b.min[k] = (double)fminf(__fsub_rn(next_down(q0), r), __fsub_rn(next_down(q1), r));
+            b.max[k] = (double)fmaxf(__fadd_rn(next_up(q0), r), __fadd_rn(next_up(q1), r));
+        } else {
+            b.min[k] = fmin(__dsub_rn(next_down(p0), radius_up), __dsub_rn(next_down(p1), radius_up));
+            b.max[k] = fmax(__dadd_rn(next_up(p0), radius_up), __dadd_rn(next_up(p1), radius_up));
+        }
+    }
+    b.vertex_ids[0] = i, b.vertex_ids[1] = -i - 1, b.vertex_ids[2] = -i - 1; // aabb.cu:140-141
+    b.element_id = i;
+    out[i] = b;
+}
+
+// aabb.cu:186-229: union of 2 (edge) or 3 (face) vertex boxes; idx is n x k column-major
+__global__ void __launch_bounds__(kThreads) element_aabb_kernel(
+    const sccd_aabb* __restrict__ vb, int nV, const int32_t* __restrict__ idx, int n, int k,
+    sccd_aabb* __restrict__ out, int* __restrict__ bad)
+{
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n)
+        return;
+    int v[3];
+    v[0] = idx[i], v[1] = idx[i + (size_t)n], v[2] = k == 3 ? idx[i + (size_t)2 * n] : v[0];
+    if ((unsigned)v[0] >= (unsigned)nV || (unsigned)v[1] >= (unsigned)nV
+        || (unsigned)v[2] >= (unsigned)nV) {
+        *bad = 1; // the reference would index out of bounds
+        return;
+    }
+    sccd_aabb b;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        double lo = fmin(vb[v[0]].min[c], vb[v[1]].min[c]);
+        double hi = fmax(vb[v[0]].max[c], vb[v[1]].max[c]);
+        if (k == 3) {
+            lo = fmin(lo, vb[v[2]].min[c]);
+            hi = fmax(hi, vb[v[2]].max[c]);
+        }
+        b.min[c] = lo, b.max[c] = hi;
+    }
+    b.vertex_ids[0] = v[0], b.vertex_ids[1] = v[1];
+    b.vertex_ids[2] = k == 3 ? v[2] : -v[0] - 1; // aabb.cu:199-203 / :221-226
+    b.element_id = i;
+    out[i] = b;
+}
+
 // FP64 pipe yardstick for the narrow-phase roofline: 8 independent DFMA chains per thread.
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b)
 {
@@ -158,14 +243,46 @@ double measure_dfma_per_second(int num_sms, cudaStream_t s)
     return (double)grid * 256.0 * 8.0 * iters / (best * 1e-3);
 }
 
+void launch_vertex_aabbs(
+    const double* V0, const double* V1, int nV, double radius_up, bool f32, sccd_aabb* out,
+    cudaStream_t s, LaunchCounter& lc)
+{
+    if (nV <= 0)
+        return;
+    const int grid = (nV + kThreads - 1) / kThreads;
+    if (f32)
+        vertex_aabb_kernel<true><<<grid, kThreads, 0, s>>>(V0, V1, nV, radius_up, out);
+    else
+        vertex_aabb_kernel<false><<<grid, kThreads, 0, s>>>(V0, V1, nV, radius_up, out);
+    SCCD_CUDA(cudaGetLastError());
+    lc.n++;
+}
+
+void launch_element_aabbs(
+    const sccd_aabb* vb, int nV, const int32_t* idx, int n, int k, sccd_aabb* out, int* bad,
+    cudaStream_t s, LaunchCounter& lc)
+{
+    if (n <= 0)
+        return;
+    element_aabb_kernel<<<(n + kThreads - 1) / kThreads, kThreads, 0, s>>>(
+        vb, nV, idx, n, k, out, bad);
+    SCCD_CUDA(cudaGetLastError());
+    lc.n++;
+}
+
 void launch_mesh_boxes(
-    const double* V0, const double* V1, int nV, double radius_up, VertexRec* vtab, double* vbox,
-    const int32_t* E, int nE, const int32_t* F, int nF, BoxArrays e_unsorted,
+    const double* V0, const double* V1, int nV, double radius_up, bool f32, VertexRec* vtab,
+    double* vbox, const int32_t* E, int nE, const int32_t* F, int nF, BoxArrays e_unsorted,
     BoxArrays vf_unsorted, cudaStream_t s, LaunchCounter& lc)
 {
     if (nV > 0) {
-        vertex_boxes_kernel<<<(nV + kThreads - 1) / kThreads, kThreads, 0, s>>>(
-            V0, V1, nV, radius_up, vtab, vbox, vf_unsorted);
+        const int grid = (nV + kThreads - 1) / kThreads;
+        if (f32)
+            vertex_boxes_kernel<true><<<grid, kThreads, 0, s>>>(
+                V0, V1, nV, radius_up, vtab, vbox, vf_unsorted);
+        else
+            vertex_boxes_kernel<false><<<grid, kThreads, 0, s>>>(
+                V0, V1, nV, radius_up, vtab, vbox, vf_unsorted);
         SCCD_CUDA(cudaGetLastError());
         lc.n++;
     }

@@ -262,10 +262,20 @@ struct LaunchCounter {
     int64_t n = 0;
 };
 
+// f32: boxes of the reference's float build (float values, stored widened); radius_up is then
+// nextafterf((float)r) computed by the caller
 void launch_mesh_boxes(
-    const double* V0, const double* V1, int nV, double radius_up, VertexRec* vtab,
+    const double* V0, const double* V1, int nV, double radius_up, bool f32, VertexRec* vtab,
     double* vbox /* 6*nV: min xyz, max xyz */, const int32_t* E, int nE, const int32_t* F,
     int nF, BoxArrays e_unsorted, BoxArrays vf_unsorted, cudaStream_t s, LaunchCounter& lc);
+
+// the reference's box builders by name, on caller-made AoS arrays (aabb.cuh:150-188)
+void launch_vertex_aabbs(
+    const double* V0, const double* V1, int nV, double radius_up, bool f32, sccd_aabb* out,
+    cudaStream_t s, LaunchCounter& lc);
+void launch_element_aabbs(
+    const sccd_aabb* vb, int nV, const int32_t* idx, int n, int k, sccd_aabb* out, int* bad,
+    cudaStream_t s, LaunchCounter& lc);
 
 // measured FP64 pipe rate (thread-level DFMA / s): the narrow phase's compute roofline
 double measure_dfma_per_second(int num_sms, cudaStream_t s);
@@ -347,14 +357,16 @@ struct NarrowInput {
 // After the batch, counters->n_items[kNarrowRounds] != 0 means the last round had to hand
 // work on (path deeper than the lane state can track): run launch_narrow_extra_round until
 // it is zero.
+// f32: the reference's float build (SCALABLE_CCD_USE_DOUBLE off) -- float arithmetic on the
+// same (float-valued) double buffers, lane-per-tree kernel only, no cull
 void launch_narrow_phase(
-    bool is_vf, const NarrowInput& in, const NarrowParams& p, NarrowCounters* counters,
+    bool is_vf, bool f32, const NarrowInput& in, const NarrowParams& p, NarrowCounters* counters,
     double* g_toi, WorkItem* items0, WorkItem* items1, unsigned long long item_cap, double* toi_per_query,
     unsigned int* checks_per_query, uint32_t* survivors /* in.n words, or null: no cull */,
     int num_sms, cudaStream_t s, LaunchCounter& lc);
 // moves n_items[kNarrowRounds] to n_items[kNarrowRounds - 1] and reruns the last round
 void launch_narrow_extra_round(
-    bool is_vf, const NarrowInput& in, const NarrowParams& p, NarrowCounters* counters,
+    bool is_vf, bool f32, const NarrowInput& in, const NarrowParams& p, NarrowCounters* counters,
     double* g_toi, WorkItem* items0, WorkItem* items1, unsigned long long item_cap, int extra_index,
     double* toi_per_query, unsigned int* checks_per_query, int num_sms, cudaStream_t s,
     LaunchCounter& lc);

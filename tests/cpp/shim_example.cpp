@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 // minimal column-major matrix with Eigen's dense interface
@@ -48,6 +49,18 @@ int main(int argc, char** argv)
 
     std::vector<AABB> vb, eb, fb;
     build_boxes(V0, V1, E, F, vb, eb, fb);
+    // the reference's own three builders (tests/test_broad_phase.cu:88-91) give the same boxes
+    std::vector<AABB> vb2, eb2, fb2, vb_static;
+    build_vertex_boxes(V0, V1, vb2);
+    build_edge_boxes(vb2, E, eb2);
+    build_face_boxes(vb2, F, fb2);
+    build_vertex_boxes(V0, vb_static);
+    auto same = [](const std::vector<AABB>& a, const std::vector<AABB>& b) {
+        return a.size() == b.size()
+            && (a.empty() || std::memcmp(a.data(), b.data(), a.size() * sizeof(AABB)) == 0);
+    };
+    const bool builders_ok = same(vb, vb2) && same(eb, eb2) && same(fb, fb2)
+        && vb_static.size() == vb.size() && vb_static[3].max[2] >= 1.0 && vb_static[3].min[2] > 0.9;
     BroadPhase broad_phase;
     bool threw = false;
     try {
@@ -60,10 +73,22 @@ int main(int argc, char** argv)
     int axis = 0;
     std::vector<std::pair<int, int>> ee;
     sort_and_sweep(eb, axis, ee);
+    // step-wise: partial overlaps on the device -> narrow_phase<true> (ccd.cu:55-76)
+    upload_mesh(V0, V1, E, F);
+    BroadPhase bp2;
+    bp2.build(std::make_shared<DeviceAABBs>(vb), std::make_shared<DeviceAABBs>(fb));
+    Scalar toi4 = 1;
+    while (!bp2.is_complete()) {
+        const auto& ov = bp2.detect_overlaps_partial();
+        narrow_phase<true>(ov.first, ov.second, max_iterations, tolerance, min_distance,
+                           allow_zero_toi, toi4);
+    }
 
-    std::printf("toi=%.17g toi_pq=%.17g ipc=%.17g collisions=%zu vf=%zu ee=%zu threw=%d\n", toi,
-                toi2, toi3, collisions.size(), vf.size(), ee.size(), (int)threw);
-    const bool ok = toi <= 0.5 && 0.5 - toi < 1e-5 && toi2 == toi && toi3 == toi
+    std::printf("toi=%.17g toi_pq=%.17g ipc=%.17g stepwise=%.17g collisions=%zu vf=%zu ee=%zu "
+                "threw=%d builders=%d\n", (double)toi, (double)toi2, (double)toi3, (double)toi4,
+                collisions.size(), vf.size(), ee.size(), (int)threw, (int)builders_ok);
+    const bool ok = toi <= 0.5 && 0.5 - toi < 1e-5 && toi2 == toi && toi3 == toi && toi4 == toi
+        && builders_ok
         && collisions.size() == 1 && std::get<0>(collisions[0]) == 3 && vf.size() == 1
         && vf[0].first == 3 && vf[0].second == 0 && ee.empty() && threw;
     return ok ? 0 : 1;

@@ -2,6 +2,9 @@
 
   python tests/golden/make_golden.py cpu  [outdir]   # reference CPU broad phase (no GPU)
   python tests/golden/make_golden.py cuda [outdir]   # reference CUDA path (needs a GPU)
+  python tests/golden/make_golden.py cpu_f32  [outdir]  # the same three for the reference's float
+  python tests/golden/make_golden.py prep_f32 [outdir]  #   build (SCALABLE_CCD_USE_DOUBLE off);
+  python tests/golden/make_golden.py cuda_f32 [outdir]  #   prep_f32 = CPU-side query selection
 
 Inputs are the deterministic generators in scalable-ccd_b200/scenes.py; each fixture
 stores a hash of its inputs so generator drift is detected.  Outputs committed under
@@ -50,10 +53,11 @@ NARROW_CASES = [  # (name, ms, max_iter, tol, allow_zero_toi)
 ]
 
 
-def make_cpu(out):
+def make_cpu(out, f32=False):
+    sfx = "_f32" if f32 else ""
     fix = {}
     for name, s in (("c1", scenes.scene_c1()), ("small", small_scene())):
-        r = orc.ref_cpu_broad_phase(s)
+        r = orc.ref_cpu_broad_phase(s, f32=f32)
         vf, ee = orc.canonical(r["vf"]), orc.canonical(r["ee"])
         assert len(vf) == r["n_vf"] and len(ee) == r["n_ee"], "reference emitted duplicates"
         fix[name] = {
@@ -61,11 +65,14 @@ def make_cpu(out):
             "next_axes": list(r["axes"]), "vf_sha256": sha(vf), "ee_sha256": sha(ee),
             "sizes": [int(s["V0"].shape[0]), int(s["E"].shape[0]), int(s["F"].shape[0])],
         }
-        vb, eb, fb = orc.ref_cpu_build_boxes(s)
+        vb, eb, fb = orc.ref_cpu_build_boxes(s, f32=f32)
         fix[name]["boxes_sha256"] = sha(vb, eb, fb)
+        if f32:  # inflated boxes too: the radius goes through nextafterf((float)r)
+            vb, eb, fb = orc.ref_cpu_build_boxes(s, 1e-3, f32=True)
+            fix[name]["boxes_r1e-3_sha256"] = sha(vb, eb, fb)
         if name == "small":
-            np.savez_compressed(os.path.join(out, "broad_small_ref_cpu.npz"), vf=vf, ee=ee)
-    with open(os.path.join(out, "broad_ref_cpu.json"), "w") as f:
+            np.savez_compressed(os.path.join(out, f"broad_small_ref_cpu{sfx}.npz"), vf=vf, ee=ee)
+    with open(os.path.join(out, f"broad_ref_cpu{sfx}.json"), "w") as f:
         json.dump(fix, f, indent=1, sort_keys=True)
     print("wrote", out, json.dumps(fix)[:300])
 
@@ -134,8 +141,93 @@ def make_cuda(out):
     print(json.dumps(meta, indent=1)[:3000])
 
 
+# ---- the reference's float build ------------------------------------------------------
+# Float queries are far cheaper to select than to solve on the GPU box, so the selection
+# (which queries the reference can solve without its ring queue wrapping) is made on the CPU
+# with the float oracle and committed; cuda_f32 then only runs the reference.
+NARROW_CASES_F32 = [  # (name, ms, max_iter, tol, allow_zero_toi)
+    ("default", 0.0, -1, 1e-6, True),
+    ("loose", 0.0, -1, 1e-4, True),
+    ("ms", 1e-5, -1, 1e-6, True),
+    ("nozero", 0.0, -1, 1e-6, False),
+]
+
+
+def prep_f32(out):
+    ee_q, vf_q = c5_small()
+    arrays = {}
+    for cname, ms, mi, tol, az in NARROW_CASES_F32:
+        for kind, q in (("vf", vf_q), ("ee", ee_q)):
+            mask = orc.tractable(q, kind == "vf", ms, tol, az, f32=True)
+            mask &= orc.tractable_bfs(q, kind == "vf", ms, tol, az, f32=True)
+            arrays[f"{cname}_{kind}_idx"] = np.flatnonzero(mask).astype(np.int32)
+            print(cname, kind, int(mask.sum()))
+    # (The float build's error filters are ~1e9 times the double build's, so breadth-first
+    # fronts are much wider: on config 1 the vertex-face front is 132,722 boxes against the
+    # 43,424 slots the reference's pipeline gives its ring queue, which then wraps and loses
+    # hits at random -- see make_cuda().  The pipeline golden of the float build is therefore
+    # composed from the reference's broad phase and its root finder run with a large queue.)
+    arrays["c5_sha256"] = np.frombuffer(bytes.fromhex(sha(ee_q, vf_q)), np.uint8)
+    np.savez_compressed(os.path.join(out, "narrow_c5_f32_idx.npz"), **arrays)
+
+
+def make_cuda_f32(out):
+    here = os.path.dirname(os.path.abspath(__file__))
+    sel = np.load(os.path.join(here, "narrow_c5_f32_idx.npz"))
+    meta = {}
+    s = scenes.scene_c1()
+    b = orc.ref_cuda_broad_phase(s, f32=True)
+    vf, ee = orc.canonical(b["vf"]), orc.canonical(b["ee"])
+    meta["broad_c1"] = {"n_vf": int(b["n_vf"]), "n_ee": int(b["n_ee"]), "n_vf_unique": len(vf),
+                        "n_ee_unique": len(ee), "vf_sha256": sha(vf), "ee_sha256": sha(ee),
+                        "scene_sha256": scene_hash(s)}
+    # pipeline = reference broad phase + reference root finder (large queue) on its pairs
+    tv = orc.ref_cuda_narrow_queries(orc.gather_queries(s, vf, True), True, f32=True)
+    te = orc.ref_cuda_narrow_queries(orc.gather_queries(s, ee, False), False, f32=True)
+    toi = min(1.0, tv["toi"], te["toi"])
+    hv, he = tv["toi_per_query"] < 1, te["toi_per_query"] < 1
+    ids = np.concatenate([vf[hv], ee[he]])
+    tq = np.concatenate([tv["toi_per_query"][hv], te["toi_per_query"][he]])
+    np.savez_compressed(os.path.join(out, "ccd_c1_ref_cuda_f32.npz"), coll_ids=ids, coll_toi=tq,
+                        n_vf_hits=np.int64(hv.sum()), toi=np.float64(toi))
+    meta["ccd_c1"] = {"toi": toi, "n_coll": int(len(ids)), "reruns": [tv["reruns"], te["reruns"]]}
+    # the reference's own pipeline calls, for the record (queue may wrap: not a golden)
+    meta["ccd_c1_pipeline_calls"] = {
+        "toi": orc.ref_cuda_ccd(s, per_query=False, f32=True)["toi"]}
+    meta["ipc_c1"] = {}
+    L = orc.ref_cuda(False, f32=True)
+    import ctypes as C
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    for md, mi in ((0.0, -1), (1e-4, 200)):
+        el = C.c_double(0)
+        t = L.ref_cuda_ipc_ccd_strategy(
+            p(s["V0"]), p(s["V1"]), C.c_int64(s["V0"].shape[0]), p(s["E"]),
+            C.c_int64(s["E"].shape[0]), p(s["F"]), C.c_int64(s["F"].shape[0]),
+            C.c_double(md), C.c_int(mi), C.c_double(1e-6), C.byref(el))
+        meta["ipc_c1"][f"md{md}_mi{mi}"] = t
+    ee_q, vf_q = c5_small()
+    arrays = {}
+    for cname, ms, mi, tol, az in NARROW_CASES_F32:
+        for kind, q in (("vf", vf_q), ("ee", ee_q)):
+            idx = sel[f"{cname}_{kind}_idx"]
+            qq = q[idx]
+            r = orc.ref_cuda_narrow_queries(qq, kind == "vf", ms, mi, tol, az, 1.0, True, f32=True)
+            g = orc.ref_cuda_narrow_queries(qq, kind == "vf", ms, mi, tol, az, 1.0, False, f32=True)
+            arrays[f"{cname}_{kind}_tpq"] = r["toi_per_query"]
+            arrays[f"{cname}_{kind}_toi"] = np.float64(g["toi"])
+            meta[f"narrow_{cname}_{kind}"] = {
+                "toi_pq_build": r["toi"], "toi": g["toi"], "reruns": [r["reruns"], g["reruns"]],
+                "hits": int((r["toi_per_query"] < 1).sum()), "n": int(len(idx))}
+    meta["c5_sha256"] = sha(ee_q, vf_q)
+    np.savez_compressed(os.path.join(out, "narrow_c5_ref_cuda_f32.npz"), **arrays)
+    with open(os.path.join(out, "ref_cuda_f32_meta.json"), "w") as f:
+        json.dump(meta, f, indent=1, sort_keys=True)
+    print(json.dumps(meta, indent=1)[:3000])
+
+
 if __name__ == "__main__":
     mode = sys.argv[1]
     out = sys.argv[2] if len(sys.argv) > 2 else os.path.dirname(os.path.abspath(__file__))
     os.makedirs(out, exist_ok=True)
-    {"cpu": make_cpu, "cuda": make_cuda}[mode](out)
+    {"cpu": make_cpu, "cuda": make_cuda, "cpu_f32": lambda o: make_cpu(o, True),
+     "prep_f32": prep_f32, "cuda_f32": make_cuda_f32}[mode](out)
