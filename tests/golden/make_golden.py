@@ -191,20 +191,6 @@ def make_cuda_f32(out):
     np.savez_compressed(os.path.join(out, "ccd_c1_ref_cuda_f32.npz"), coll_ids=ids, coll_toi=tq,
                         n_vf_hits=np.int64(hv.sum()), toi=np.float64(toi))
     meta["ccd_c1"] = {"toi": toi, "n_coll": int(len(ids)), "reruns": [tv["reruns"], te["reruns"]]}
-    # the reference's own pipeline calls, for the record (queue may wrap: not a golden)
-    meta["ccd_c1_pipeline_calls"] = {
-        "toi": orc.ref_cuda_ccd(s, per_query=False, f32=True)["toi"]}
-    meta["ipc_c1"] = {}
-    L = orc.ref_cuda(False, f32=True)
-    import ctypes as C
-    p = lambda a: a.ctypes.data_as(C.c_void_p)
-    for md, mi in ((0.0, -1), (1e-4, 200)):
-        el = C.c_double(0)
-        t = L.ref_cuda_ipc_ccd_strategy(
-            p(s["V0"]), p(s["V1"]), C.c_int64(s["V0"].shape[0]), p(s["E"]),
-            C.c_int64(s["E"].shape[0]), p(s["F"]), C.c_int64(s["F"].shape[0]),
-            C.c_double(md), C.c_int(mi), C.c_double(1e-6), C.byref(el))
-        meta["ipc_c1"][f"md{md}_mi{mi}"] = t
     ee_q, vf_q = c5_small()
     arrays = {}
     for cname, ms, mi, tol, az in NARROW_CASES_F32:
