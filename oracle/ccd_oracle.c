@@ -28,9 +28,12 @@
  * its CUDA code with --use_fast_math (CMakeLists.txt:219-230), i.e. flush-to-zero
  * arithmetic and a / b = a * rcp.approx(b).  FTZ is restated exactly; the
  * hardware reciprocal (MUFU.RCP, <= 1 ulp) cannot be, so rcp() below is the
- * correctly rounded reciprocal and the float narrow phase of this oracle is a
- * TOLERANCE-level model of the reference (tolerances and split choices can differ
- * in the last ulp); the float broad phase is exact.
+ * correctly rounded reciprocal and the float narrow phase of this oracle is in
+ * principle a TOLERANCE-level model of the reference (tolerances and split choices
+ * can differ in the last ulp); the float broad phase is exact.  Pinned: on every
+ * committed fixture frozen from the reference's float CUDA build on a B200
+ * (tests/golden, files named ..._f32...: 1,489 collisions of config 1 with their TOIs, 3,424
+ * adversarial queries) the two agree bit for bit (tests/test_f32.py).
  */
 #include <float.h>
 #include <math.h>

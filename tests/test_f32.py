@@ -116,6 +116,49 @@ def test_float_flush_to_zero_and_tiny_inputs(orc):
     assert a == b
 
 
+CASES_F32 = {"default": dict(ms=0.0, max_iter=-1, tol=1e-6, allow_zero_toi=True),
+             "loose": dict(ms=0.0, max_iter=-1, tol=1e-4, allow_zero_toi=True),
+             "ms": dict(ms=1e-5, max_iter=-1, tol=1e-6, allow_zero_toi=True),
+             "nozero": dict(ms=0.0, max_iter=-1, tol=1e-6, allow_zero_toi=False)}
+
+
+def test_float_oracle_matches_reference_cuda_float_golden_queries(orc, sccd):
+    """Float oracle vs per-query TOIs frozen from the unmodified reference CUDA float build.
+    The oracle's reciprocal is the correctly rounded one, not MUFU.RCP (see its header), so
+    equality is not guaranteed in general -- on these fixtures it holds bit for bit."""
+    z = np.load(os.path.join(GOLD, "narrow_c5_ref_cuda_f32.npz"))
+    sel = np.load(os.path.join(GOLD, "narrow_c5_f32_idx.npz"))
+    ee, vf = sccd.scenes.queries_c5(3000, seed=4)
+    assert sha(ee, vf) == bytes(sel["c5_sha256"]).hex()
+    n_hits = 0
+    for case, kw in CASES_F32.items():
+        for name, q in (("vf", vf), ("ee", ee)):
+            idx = sel[f"{case}_{name}_idx"]
+            toi, tpq, _ = orc.narrow_phase(q[idx], name == "vf", kw["ms"], kw["max_iter"],
+                                           kw["tol"], kw["allow_zero_toi"], f32=True)
+            ref = z[f"{case}_{name}_tpq"]
+            assert np.array_equal(tpq < 1, ref < 1), (case, name)
+            assert np.array_equal(tpq, ref), (case, name)
+            assert toi == float(z[f"{case}_{name}_toi"])
+            n_hits += int((ref < 1).sum())
+    assert n_hits > 150
+
+
+def test_float_oracle_matches_reference_cuda_float_golden_pipeline(orc, scene_c1):
+    """config 1 in float: 1,489 collisions with their TOIs, from the reference's float broad
+    phase + float root finder."""
+    z = np.load(os.path.join(GOLD, "ccd_c1_ref_cuda_f32.npz"))
+    r = orc.ccd(scene_c1, f32=True)
+    assert r["toi"] == float(z["toi"])
+    hv, he = r["toi_vf"] < 1, r["toi_ee"] < 1
+    nv = int(z["n_vf_hits"])
+    assert (int(hv.sum()), int(he.sum())) == (nv, len(z["coll_ids"]) - nv) and nv > 100
+    assert np.array_equal(r["vf"][hv], z["coll_ids"][:nv])       # both in canonical order
+    assert np.array_equal(r["ee"][he], z["coll_ids"][nv:])
+    assert np.array_equal(r["toi_vf"][hv], z["coll_toi"][:nv])
+    assert np.array_equal(r["toi_ee"][he], z["coll_toi"][nv:])
+
+
 # ------------------------------------------------------------------------------- GPU
 @pytest.fixture()
 def ctx32(ctx, sccd):
@@ -186,12 +229,6 @@ def test_gpu_named_box_builders(ctx, sccd, orc, scene_small, f32):
         assert len(ctx.build_element_boxes(vb, np.zeros((0, 2), np.int32, order="F"))) == 0
     finally:
         ctx.set_scalar_type(sccd.capi.F64)
-
-
-CASES_F32 = {"default": dict(ms=0.0, max_iter=-1, tol=1e-6, allow_zero_toi=True),
-             "loose": dict(ms=0.0, max_iter=-1, tol=1e-4, allow_zero_toi=True),
-             "ms": dict(ms=1e-5, max_iter=-1, tol=1e-6, allow_zero_toi=True),
-             "nozero": dict(ms=0.0, max_iter=-1, tol=1e-6, allow_zero_toi=False)}
 
 
 def _narrow_gpu(ctx, torch, kind, q, **kw):
