@@ -939,7 +939,7 @@ void narrow_enqueue(
     uint32_t* survivors = nullptr;
     {
         const char* e = getenv("SCCD_NP_CULL");
-        if (!c->f32 && (!e || atoi(e) != 0)) // (argued for the double build's filters only)
+        if (!e || atoi(e) != 0)
             survivors = (uint32_t*)R.b_surv.reserve((size_t)in.n * 4);
     }
     const size_t kt = kt_begin(c, &c->stats.ms_k_narrow[kind]);

@@ -12,10 +12,29 @@ def absmax(*pairs):
     return np.max(np.stack([np.abs(b - a) for a, b in pairs]), axis=0)
 
 
-def cull_mask(q, is_vf, tol, ms):
-    """numpy mirror of narrow_cull_kernel: True = culled (answered "no collision")."""
+def cull_mask(q, is_vf, tol, ms, f32=False):
+    """numpy mirror of narrow_cull_kernel: True = culled (answered "no collision").
+    f32: the variant for the reference's float build (SCCD_F32): inputs as the float solver
+    sees them, the float error filters, and a scale test that keeps every tol_k above the
+    float resolution of the parameters (so that condition 4 cannot fire)."""
+    if f32:
+        q = q.astype(np.float32).astype(np.float64)
+        tol, ms = float(np.float32(tol)), float(np.float32(ms))
     p = q.reshape(-1, 2, 4, 3)                       # [query, time, vertex, xyz]
     s, e = p[:, 0], p[:, 1]
+    L = np.zeros((3, len(p)))
+    for k in range(3):
+        s0, s1, s2, s3 = (s[:, j, k] for j in range(4))
+        e0, e1, e2, e3 = (e[:, j, k] for j in range(4))
+        if is_vf:   # root_finder.cu:50-59
+            p000, p001, p011, p010 = s0 - s1, s0 - s3, s0 - (s2 + s3 - s1), s0 - s2
+            p100, p101, p111, p110 = e0 - e1, e0 - e3, e0 - (e2 + e3 - e1), e0 - e2
+        else:       # root_finder.cu:73-80
+            p000, p001, p010, p011 = s0 - s2, s0 - s3, s1 - s2, s1 - s3
+            p100, p101, p110, p111 = e0 - e2, e0 - e3, e1 - e2, e1 - e3
+        L[0] = np.maximum(L[0], absmax((p000, p100), (p001, p101), (p011, p111), (p010, p110)))
+        L[1] = np.maximum(L[1], absmax((p000, p010), (p100, p110), (p101, p111), (p001, p011)))
+        L[2] = np.maximum(L[2], absmax((p000, p001), (p100, p101), (p110, p111), (p010, p011)))
     if is_vf:
         A = np.stack([s[:, 0], e[:, 0]], axis=1)
         B = np.stack([s[:, 1], s[:, 2], s[:, 3], e[:, 1], e[:, 2], e[:, 3],
@@ -24,15 +43,6 @@ def cull_mask(q, is_vf, tol, ms):
     else:
         A = np.stack([s[:, 0], s[:, 1], e[:, 0], e[:, 1]], axis=1)
         B = np.stack([s[:, 2], s[:, 3], e[:, 2], e[:, 3]], axis=1)
-        L = np.zeros((3, len(p)))
-        for k in range(3):
-            s0, s1, s2, s3 = (s[:, j, k] for j in range(4))
-            e0, e1, e2, e3 = (e[:, j, k] for j in range(4))
-            p000, p001, p010, p011 = s0 - s2, s0 - s3, s1 - s2, s1 - s3
-            p100, p101, p110, p111 = e0 - e2, e0 - e3, e1 - e2, e1 - e3
-            L[0] = np.maximum(L[0], absmax((p000, p100), (p001, p101), (p011, p111), (p010, p110)))
-            L[1] = np.maximum(L[1], absmax((p000, p010), (p100, p110), (p101, p111), (p001, p011)))
-            L[2] = np.maximum(L[2], absmax((p000, p001), (p100, p101), (p110, p111), (p010, p011)))
         with np.errstate(divide="ignore", invalid="ignore"):
             width = np.where((L[0] > 0) & (L[1] > 0),
                              tol * (1 + L[1] / L[0] + L[2] / L[1]) / 3 * 1.000001, np.inf)
@@ -42,30 +52,39 @@ def cull_mask(q, is_vf, tol, ms):
     sep = np.maximum(pa.min(1) - pb.max(1), pb.min(1) - pa.max(1)).max(1)
     maxabs = np.maximum(1.0, np.abs(p).reshape(len(p), -1).max(1))
     extent = p.reshape(len(p), -1).max(1) - p.reshape(len(p), -1).min(1)
-    bound = 2.0 * (width + ms + 2.0 * maxabs ** 3 * 8e-15 + 1e-12 * maxabs)
-    return (extent <= tol * 1e12) & (0.5 * sep > bound)
+    if f32:     # 8e-6 >= every float error filter (root_finder.cu:102-119)
+        bound = 2.0 * (width + ms + 2.0 * maxabs ** 3 * 8e-6 + 1e-6 * maxabs)
+        sane = (extent <= tol * 1e12) & (L.max(0) <= tol * 1e6)     # tol_k >= 3e-7 > 2^-23
+    else:
+        bound = 2.0 * (width + ms + 2.0 * maxabs ** 3 * 8e-15 + 1e-12 * maxabs)
+        sane = extent <= tol * 1e12
+    return sane & (0.5 * sep > bound)
 
 
+@pytest.mark.parametrize("f32", [False, True])
 @pytest.mark.parametrize("tol,ms", [(1e-6, 0.0), (1e-3, 0.0), (1e-6, 1e-3), (1e-9, 1e-8), (1e-2, 1e-2)])
-def test_culled_mesh_queries_are_misses(orc, scene_c1, tol, ms):
+def test_culled_mesh_queries_are_misses(orc, scene_c1, tol, ms, f32):
     s = scene_c1
-    r = orc.ccd(s)
+    if f32 and ms == 1e-3:
+        pytest.skip("float build with ms = 1e-3: >1e8 box checks on the CPU")
+    r = orc.ccd(s, f32=f32, per_query=False)        # the candidate pairs of that scalar type
     for pairs, is_vf in ((r["vf"], True), (r["ee"], False)):
         q = orc.gather_queries(s, np.ascontiguousarray(pairs), is_vf)
-        _, tpq, _ = orc.narrow_phase(q, is_vf, ms, -1, tol, True, 1.0, per_query=True)
-        culled = cull_mask(q, is_vf, tol, ms)
+        _, tpq, _ = orc.narrow_phase(q, is_vf, ms, -1, tol, True, 1.0, per_query=True, f32=f32)
+        culled = cull_mask(q, is_vf, tol, ms, f32)
         assert not np.any(culled & (tpq < 1)), "the cull dropped a query the root finder reports"
         if tol == 1e-6 and ms == 0.0:
-            assert culled.mean() > 0.9            # and it is worth having
+            assert culled.mean() > (0.85 if f32 else 0.9)      # and it is worth having
 
 
+@pytest.mark.parametrize("f32", [False, True])
 @pytest.mark.parametrize("tol,ms", [(1e-6, 0.0), (1e-9, 0.0), (1e-6, 1e-8), (1e-3, 0.0)])
-def test_culled_adversarial_queries_are_misses(orc, sccd, tol, ms):
-    ee, vf = sccd.scenes.queries_c5(3000, seed=4)
+def test_culled_adversarial_queries_are_misses(orc, sccd, tol, ms, f32):
+    ee, vf = sccd.scenes.queries_c5(3000 if not f32 else 1200, seed=4)
     for q, is_vf in ((vf, True), (ee, False)):
-        q = q[orc.tractable(q, is_vf, ms, tol)]
-        _, tpq, _ = orc.narrow_phase(q, is_vf, ms, -1, tol, True, 1.0, per_query=True)
-        culled = cull_mask(q, is_vf, tol, ms)
+        q = q[orc.tractable(q, is_vf, ms, tol, f32=f32)]
+        _, tpq, _ = orc.narrow_phase(q, is_vf, ms, -1, tol, True, 1.0, per_query=True, f32=f32)
+        culled = cull_mask(q, is_vf, tol, ms, f32)
         assert not np.any(culled & (tpq < 1))
 
 
@@ -77,11 +96,24 @@ def test_static_edges_are_never_culled(sccd):
     q[:, 1] = q[:, 0]                                # end positions = start positions
     q[:, :, 2:, 2] += 5.0                            # far apart along z
     assert not cull_mask(q.reshape(-1, 24), False, 1e-6, 0.0).any()
+    assert not cull_mask(q.reshape(-1, 24), False, 1e-6, 0.0, f32=True).any()
 
 
+def test_float_cull_keeps_queries_whose_tolerance_nears_the_float_resolution(sccd):
+    """tol_k = tol / (3 L_k) below ~2^-23: the float solver can stop on condition 4 (interval
+    cannot be split) with a hull of any size, so such queries must reach it."""
+    ee, vf = sccd.scenes.queries_c5(200, seed=2)
+    for q, is_vf in ((vf, True), (ee, False)):
+        big = q.reshape(-1, 2, 4, 3).copy()
+        big[:, :, 2:] += 1e3                         # far apart: L ~ 1e3 >> tol * 1e6
+        assert cull_mask(big.reshape(-1, 24), is_vf, 1e-6, 0.0).any()           # double: culled
+        assert not cull_mask(big.reshape(-1, 24), is_vf, 1e-6, 0.0, f32=True).any()
+
+
+@pytest.mark.parametrize("f32", [False, True])
 @pytest.mark.parametrize("is_vf", [True, False])
 @pytest.mark.parametrize("tol", [1e-6, 1e-4])
-def test_fuzz_near_threshold_separations(orc, is_vf, tol):
+def test_fuzz_near_threshold_separations(orc, is_vf, tol, f32):
     """Random primitives pushed apart along random diagonals by gaps around the acceptance
     width (where edge-edge is much looser than the co-domain tolerance because of the
     reference's tol_u = tol_t): every culled query must be a miss of the root finder."""
@@ -108,8 +140,8 @@ def test_fuzz_near_threshold_separations(orc, is_vf, tol):
     shift = (pa.max(1) - pb.min(1) + gap) / (axis * axis).sum(1)
     p[:, :, sl] += (shift[:, None] * axis)[:, None, None, :]
     q = np.ascontiguousarray(p.reshape(n, 24))
-    q = q[orc.tractable(q, is_vf, 0.0, tol, limit=5000)]
-    _, tpq, _ = orc.narrow_phase(q, is_vf, 0.0, -1, tol, True, 1.0, per_query=True)
-    culled = cull_mask(q, is_vf, tol, 0.0)
+    q = q[orc.tractable(q, is_vf, 0.0, tol, limit=5000, f32=f32)]
+    _, tpq, _ = orc.narrow_phase(q, is_vf, 0.0, -1, tol, True, 1.0, per_query=True, f32=f32)
+    culled = cull_mask(q, is_vf, tol, 0.0, f32)
     assert culled.any() and (~culled).any()                    # the sample straddles the bound
     assert not np.any(culled & (tpq < 1))

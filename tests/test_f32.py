@@ -301,7 +301,7 @@ def test_gpu_float_pipeline_matches_reference_cuda_float_build(ctx32, orc, scene
     st = ctx32.stats()
     meta = json.load(open(os.path.join(GOLD, "ref_cuda_f32_meta.json")))
     assert st["n_pairs"] == [meta["broad_c1"]["n_vf"], meta["broad_c1"]["n_ee"]]
-    assert st["n_culled"] == [0, 0]            # the cull is a double-build device: off in float
+    assert min(st["n_culled"]) > 0.8 * min(st["n_pairs"])     # the float cull does its job
     t2, (vf_ids, vf_t), (ee_ids, ee_t) = ctx32.ccd_collisions()
     assert t2 == toi
     nv = int(z["n_vf_hits"])
@@ -313,6 +313,41 @@ def test_gpu_float_pipeline_matches_reference_cuda_float_build(ctx32, orc, scene
     # the IPC wrapper stays consistent with it
     t3 = ctx32.ipc_ccd_strategy()
     assert is_float_valued(t3) and (t3 == toi or toi < 1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kw", [dict(ms=0.0, tol=1e-6), dict(ms=1e-4, tol=1e-6),
+                                dict(ms=0.0, tol=1e-3), dict(ms=1e-6, tol=1e-5)])
+def test_gpu_float_cull_changes_no_result(ctx32, orc, torch_cuda, scene_c1, kw):
+    """The float variant of the separating-axis cull: every per-query TOI equals the float
+    solver's own (cull off), also with a minimum separation or a tolerance far larger than the
+    gaps it tests against."""
+    s = scene_c1
+    ctx32.upload_mesh(s["V0"], s["V1"], s["E"], s["F"])
+    ctx32.build_boxes(kw["ms"])
+    saved = os.environ.get("SCCD_NP_CULL")
+    try:
+        for kind in (0, 1):
+            pairs = ctx32.broad_phase(kind)
+            q = orc.gather_queries(s, np.ascontiguousarray(pairs), kind == 0)
+            os.environ.pop("SCCD_NP_CULL", None)
+            ctx32.reset_stats()
+            toi1, tpq1 = _narrow_gpu(ctx32, torch_cuda, kind, q, max_iter=-1,
+                                     allow_zero_toi=True, **kw)
+            culled = ctx32.stats()["n_culled"][kind]
+            os.environ["SCCD_NP_CULL"] = "0"
+            ctx32.reset_stats()
+            toi0, tpq0 = _narrow_gpu(ctx32, torch_cuda, kind, q, max_iter=-1,
+                                     allow_zero_toi=True, **kw)
+            assert ctx32.stats()["n_culled"][kind] == 0
+            assert np.array_equal(tpq0, tpq1) and toi0 == toi1
+            if kw["ms"] == 0.0 and kw["tol"] == 1e-6:
+                assert culled > 0.8 * len(q)
+    finally:
+        if saved is None:
+            os.environ.pop("SCCD_NP_CULL", None)
+        else:
+            os.environ["SCCD_NP_CULL"] = saved
 
 
 @pytest.mark.gpu

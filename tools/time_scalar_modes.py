@@ -2,9 +2,9 @@
 
   python tools/time_scalar_modes.py [workload] [steps]
 
-The float mode (the reference's SCALABLE_CCD_USE_DOUBLE=OFF build) runs the lane-per-tree
-solver on every candidate pair: no separating-axis cull, no warp-cooperative kernel -- it is
-there for result parity with the reference's float build, not tuned."""
+The float mode (the reference's SCALABLE_CCD_USE_DOUBLE=OFF build) runs the separating-axis cull
+(float filters) and the lane-per-tree float solver; the warp-cooperative kernel is double only.
+SCCD_NP_CULL=0 in the environment switches the cull off in both modes."""
 import json
 import os
 import sys
