@@ -370,6 +370,22 @@ def main():
         rank_stage_ms = gathered
     e2e_ms, toi2, _, _ = timed(step_e2e, args.steps, 1)
     assert toi == toi2, (toi, toi2)
+    # what a simulator with a fixed topology pays per step (sccd_update_vertices: only the two
+    # vertex frames cross PCIe).  Extra information; the contract's e2e is the line above.
+    e2e_v = None
+    if world == 1:
+        try:
+            def step_e2e_vertices():
+                ctx.update_vertices(pinned["V0"].data_ptr(), pinned["V1"].data_ptr(), nV=nV,
+                                    host=True)
+                return ctx.ccd(**PARAMS)
+            v_ms, toi3, _, _ = timed(step_e2e_vertices, args.steps, 1)
+            if toi3 == toi:
+                e2e_v = {"value": v_ms, "unit": UNIT, "h2d_bytes_per_step": 2 * 24 * nV,
+                         "d2h_bytes_per_step": 8,
+                         "note": "pinned vertex frames -> sccd_update_vertices + sccd_ccd"}
+        except Exception as exc:  # never let the extra arm cost the bench line
+            e2e_v = {"error": repr(exc)[:200]}
 
     def avg(key, idx=None):
         vals = [s[key] if idx is None else s[key][idx] for s in stats]
@@ -451,6 +467,7 @@ def main():
                 "h2d_bytes_per_step": 2 * 24 * nV + 8 * nE + 12 * nF, "d2h_bytes_per_step": 8,
                 "note": ("whole job: each rank copies 1/N of the mesh H2D, NCCL all-gather of the "
                          "slices" if world > 1 else "pinned host mesh -> sccd_ccd_host")},
+        "e2e_vertices_only": e2e_v,
         "gpu_launches": int(avg("n_launches")) * args.steps,
         "roofline": roofline, "roofline_fp64": fp64,
         "toi": toi, "n_pairs": n_pairs,

@@ -150,6 +150,14 @@ int sccd_upload_mesh(
     sccd_ctx* ctx, const double* V0, const double* V1, int64_t nV, const int32_t* E,
     int64_t nE, const int32_t* F, int64_t nF, int on_device);
 
+/* Frame-to-frame reuse: new vertex positions for the mesh of the last
+ * sccd_upload_mesh -- same vertex count, E and F stay where that call put them (on the device),
+ * so a simulation step moves 48 B per vertex instead of the whole mesh.  The reference has no
+ * such entry: its ccd() uploads all four matrices on every call (cuda/ccd.cu:103-106).
+ * on_device as in sccd_upload_mesh.  Boxes have to be rebuilt (the pipeline calls do that). */
+int sccd_update_vertices(
+    sccd_ctx* ctx, const double* V0, const double* V1, int64_t nV, int on_device);
+
 /* build_vertex_boxes + build_edge_boxes + build_face_boxes + the three DeviceAABBs
  * constructors (cuda/broad_phase/aabb.cu:75-229), on the device: boxes are built
  * from the uploaded mesh, keyed on min.x and radix-sorted (vertices+faces as one

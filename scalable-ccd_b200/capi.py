@@ -27,7 +27,7 @@ SYMBOLS = [
     "sccd_set_max_pairs_per_chunk", "sccd_set_queue_capacity", "sccd_set_grid_cells",
     "sccd_set_shard", "sccd_set_scalar_type",
     "sccd_build_vertex_boxes", "sccd_build_element_boxes",
-    "sccd_upload_mesh", "sccd_build_boxes", "sccd_get_boxes", "sccd_set_boxes",
+    "sccd_upload_mesh", "sccd_update_vertices", "sccd_build_boxes", "sccd_get_boxes", "sccd_set_boxes",
     "sccd_broad_phase_begin",
     "sccd_broad_phase_partial", "sccd_broad_phase_is_complete", "sccd_broad_phase",
     "sccd_narrow_phase", "sccd_narrow_phase_queries", "sccd_ccd", "sccd_ccd_collisions",
@@ -192,6 +192,23 @@ class Context:
             self._h, _ptr(V0), _ptr(V1), C.c_int64(nV), _ptr(E), C.c_int64(nE), _ptr(F),
             C.c_int64(nF), C.c_int(on_dev)))
         self.nV, self.nE, self.nF = nV, nE, nF
+
+    def update_vertices(self, V0, V1, nV=None, host=False):
+        """New positions for the uploaded mesh (same topology): host numpy arrays (column-major
+        float64), or raw pointers with nV given -- device pointers unless host=True."""
+        if nV is None:
+            for a in (V0, V1):
+                if a.ndim != 2 or a.shape[1] != 3 or not a.flags.f_contiguous \
+                        or a.dtype != np.float64:
+                    raise ValueError("V0/V1 must be (n, 3) column-major float64")
+            if V0.shape != V1.shape:
+                raise ValueError("V0 and V1 must have the same shape")
+            nV, on_dev = V0.shape[0], 0
+            self._keep_v = [V0, V1]
+        else:
+            on_dev = 0 if host else 1
+        self._chk(self.L.sccd_update_vertices(
+            self._h, _ptr(V0), _ptr(V1), C.c_int64(nV), C.c_int(on_dev)))
 
     def build_boxes(self, inflation_radius: float = 0.0):
         self._chk(self.L.sccd_build_boxes(self._h, C.c_double(inflation_radius)))

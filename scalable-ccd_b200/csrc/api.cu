@@ -317,6 +317,31 @@ void upload_mesh(
     c->runs[0].bp_kind = c->runs[1].bp_kind = -1;
 }
 
+// Frame-to-frame: same topology (E, F stay where the last upload put them), new positions.
+void update_vertices(sccd_ctx* c, const double* V0, const double* V1, int64_t nV, bool on_device)
+{
+    if (!c->have_mesh)
+        throw std::logic_error("update_vertices: no mesh uploaded");
+    if (nV != c->nV)
+        throw std::invalid_argument("update_vertices: vertex count differs from the uploaded mesh");
+    if (nV && (!V0 || !V1))
+        throw std::invalid_argument("update_vertices: null pointer");
+    if (on_device) {
+        c->dV0 = V0;
+        c->dV1 = V1;
+    } else {
+        const size_t vb = sizeof(double) * 3 * (size_t)nV;
+        c->bV0.reserve(vb + 16);
+        c->bV1.reserve(vb + 16);
+        SCCD_CUDA(cudaMemcpyAsync(c->bV0.ptr, V0, vb, cudaMemcpyHostToDevice, c->stream));
+        SCCD_CUDA(cudaMemcpyAsync(c->bV1.ptr, V1, vb, cudaMemcpyHostToDevice, c->stream));
+        c->dV0 = c->bV0.as<double>();
+        c->dV1 = c->bV1.as<double>();
+    }
+    c->have_boxes = false;
+    c->runs[0].bp_kind = c->runs[1].bp_kind = -1;
+}
+
 void prepare_list(sccd_ctx* c, int which, int n, bool two_lists)
 {
     auto& L = c->lists[which];
@@ -1334,6 +1359,15 @@ int sccd_upload_mesh(
 {
     return guarded(ctx, [&] {
         upload_mesh(ctx, V0, V1, nV, E, nE, F, nF, on_device != 0);
+        return SCCD_OK;
+    });
+}
+
+int sccd_update_vertices(
+    sccd_ctx* ctx, const double* V0, const double* V1, int64_t nV, int on_device)
+{
+    return guarded(ctx, [&] {
+        update_vertices(ctx, V0, V1, nV, on_device != 0);
         return SCCD_OK;
     });
 }

@@ -358,7 +358,7 @@ struct NarrowInput {
 // work on (path deeper than the lane state can track): run launch_narrow_extra_round until
 // it is zero.
 // f32: the reference's float build (SCALABLE_CCD_USE_DOUBLE off) -- float arithmetic on the
-// same (float-valued) double buffers; cull with the float filters, lane-per-tree kernel only
+// same (float-valued) double buffers; cull with the float filters, both solver kernels in float
 void launch_narrow_phase(
     bool is_vf, bool f32, const NarrowInput& in, const NarrowParams& p, NarrowCounters* counters,
     double* g_toi, WorkItem* items0, WorkItem* items1, unsigned long long item_cap, double* toi_per_query,

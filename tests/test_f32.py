@@ -351,6 +351,38 @@ def test_gpu_float_cull_changes_no_result(ctx32, orc, torch_cuda, scene_c1, kw):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("flags", [1 << 24, 4 | (3 << 8) | (2 << 16) | (1 << 25), 1 << 28])
+def test_gpu_float_scheduling_variants_change_no_result(ctx32, orc, sccd, torch_cuda, scene_c1,
+                                                         flags):
+    """Lane-per-tree only / tiny budgets / small cooperative limit (SCCD_NP_FLAGS, see
+    tests/test_gpu_parity.py VARIANTS): the float kernels return the same per-query TOIs
+    however the trees are cut and whichever of the two kernels walks them."""
+    s = scene_c1
+    ctx32.upload_mesh(s["V0"], s["V1"], s["E"], s["F"])
+    ctx32.build_boxes(0.0)
+    ee_q, vf_q = sccd.scenes.queries_c5(1500, seed=4)
+    sel = orc.tractable(vf_q, True, 0.0, 1e-6, f32=True)
+    saved = os.environ.get("SCCD_NP_FLAGS")
+    try:
+        for kind in (0, 1):
+            pairs = ctx32.broad_phase(kind)
+            qs = [orc.gather_queries(s, np.ascontiguousarray(pairs), kind == 0)]
+            if kind == 0:
+                qs.append(vf_q[sel])
+            for q in qs:
+                os.environ.pop("SCCD_NP_FLAGS", None)
+                toi1, tpq1 = _narrow_gpu(ctx32, torch_cuda, kind, q)
+                os.environ["SCCD_NP_FLAGS"] = str(flags)
+                toi2, tpq2 = _narrow_gpu(ctx32, torch_cuda, kind, q)
+                assert np.array_equal(tpq1, tpq2) and toi1 == toi2
+    finally:
+        if saved is None:
+            os.environ.pop("SCCD_NP_FLAGS", None)
+        else:
+            os.environ["SCCD_NP_FLAGS"] = saved
+
+
+@pytest.mark.gpu
 def test_gpu_scalar_type_switch_rebuilds_and_double_is_untouched(ctx, sccd, orc, scene_small):
     s = scene_small
     ctx.upload_mesh(s["V0"], s["V1"], s["E"], s["F"])

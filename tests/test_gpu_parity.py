@@ -496,3 +496,33 @@ def test_sharded_driver_on_one_gpu(sccd, orc, scene_small, torch_cuda):
     sh.profile = True
     assert sh.ccd() == want and "ms" in sh.last
     c.close()
+
+
+def test_update_vertices_equals_a_fresh_upload(ctx, sccd, orc, scene_small):
+    """Frame-to-frame reuse: new positions for the uploaded topology give exactly what a
+    fresh upload of the whole mesh gives (host arrays and device pointers)."""
+    import torch
+    s = scene_small
+    s2 = sccd.scenes.cloth_on_sphere(31, seed=8, sphere="uv")      # same topology, other frame
+    assert np.array_equal(s["E"], s2["E"]) and np.array_equal(s["F"], s2["F"])
+    want = orc.ccd(s2)
+    ctx.upload_mesh(s["V0"], s["V1"], s["E"], s["F"])
+    assert ctx.ccd() == orc.ccd(s)["toi"]
+    ctx.update_vertices(s2["V0"], s2["V1"])
+    assert ctx.ccd() == want["toi"]
+    assert ctx.stats()["n_pairs"] == [len(want["vf"]), len(want["ee"])]
+    assert np.array_equal(orc.canonical(ctx.broad_phase(0)), want["vf"])
+    # device pointers: back to the first frame
+    d0 = torch.from_numpy(np.ascontiguousarray(s["V0"].T)).cuda()   # column-major bytes
+    d1 = torch.from_numpy(np.ascontiguousarray(s["V1"].T)).cuda()
+    ctx.update_vertices(d0.data_ptr(), d1.data_ptr(), nV=s["V0"].shape[0])
+    assert ctx.ccd() == orc.ccd(s)["toi"]
+    with pytest.raises(sccd.SccdError) as e:
+        ctx.update_vertices(s["V0"][:-1].copy(order="F"), s["V1"][:-1].copy(order="F"))
+    assert e.value.code == sccd.capi.ERR_ARG
+    fresh = sccd.Context(0)
+    with pytest.raises(sccd.SccdError) as e:
+        fresh.update_vertices(s["V0"], s["V1"])
+    assert e.value.code == sccd.capi.ERR_STATE
+    fresh.close()
+    ctx.upload_mesh(s["V0"], s["V1"], s["E"], s["F"])               # leave host-owned buffers behind
