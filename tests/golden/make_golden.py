@@ -56,7 +56,9 @@ NARROW_CASES = [  # (name, ms, max_iter, tol, allow_zero_toi)
 def make_cpu(out, f32=False):
     sfx = "_f32" if f32 else ""
     fix = {}
-    for name, s in (("c1", scenes.scene_c1()), ("small", small_scene())):
+    for name, s in (("c1", scenes.scene_c1()), ("small", small_scene()),
+                    ("pile", scenes.blob_pile(60, seed=5)),               # configs 3 / 4 in small
+                    ("slab", scenes.blob_pile(60, seed=6, slab=True))):
         r = orc.ref_cpu_broad_phase(s, f32=f32)
         vf, ee = orc.canonical(r["vf"]), orc.canonical(r["ee"])
         assert len(vf) == r["n_vf"] and len(ee) == r["n_ee"], "reference emitted duplicates"

@@ -36,9 +36,11 @@ def is_float_valued(a):
 
 
 # ------------------------------------------------------------------------------- CPU
-@pytest.mark.parametrize("name", ["small", "c1"])
-def test_float_oracle_broad_phase_matches_reference_golden(orc, scene_c1, scene_small, gold_f32, name):
-    s = {"small": scene_small, "c1": scene_c1}[name]
+@pytest.mark.parametrize("name", ["small", "c1", "pile", "slab"])
+def test_float_oracle_broad_phase_matches_reference_golden(orc, sccd, scene_c1, scene_small,
+                                                           gold_f32, name):
+    from test_oracle import golden_scene
+    s = golden_scene(sccd, scene_c1, scene_small, name)
     g = gold_f32[name]
     vb, eb, fb = orc.build_boxes(s, f32=True)
     assert sha(vb, eb, fb) == g["boxes_sha256"]                      # boxes bit-exact

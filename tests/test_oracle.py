@@ -34,10 +34,21 @@ def test_scene_generators_are_stable(scene_c1, scene_small, gold_cpu):
         == gold_cpu["c1"]["sizes"]
 
 
-@pytest.mark.parametrize("name", ["small", "c1"])
-def test_oracle_broad_phase_matches_reference_golden(orc, scene_c1, scene_small, gold_cpu, name):
-    s = {"small": scene_small, "c1": scene_c1}[name]
+def golden_scene(sccd, scene_c1, scene_small, name):
+    """The scenes the reference-CPU goldens were frozen on (tests/golden/make_golden.py)."""
+    if name == "pile":      # configs 3 / 4 in small: rigid blob instances, heavy-tailed pile
+        return sccd.scenes.blob_pile(60, seed=5)
+    if name == "slab":
+        return sccd.scenes.blob_pile(60, seed=6, slab=True)
+    return {"small": scene_small, "c1": scene_c1}[name]
+
+
+@pytest.mark.parametrize("name", ["small", "c1", "pile", "slab"])
+def test_oracle_broad_phase_matches_reference_golden(orc, sccd, scene_c1, scene_small, gold_cpu,
+                                                     name):
+    s = golden_scene(sccd, scene_c1, scene_small, name)
     g = gold_cpu[name]
+    assert scene_hash(s) == g["scene_sha256"]
     vb, eb, fb = orc.build_boxes(s)
     assert sha(vb, eb, fb) == g["boxes_sha256"]          # boxes bit-exact
     vf, ax_vf = orc.sort_and_sweep_two_lists(vb, fb, 0)
