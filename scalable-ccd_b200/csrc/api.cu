@@ -948,6 +948,11 @@ void narrow_enqueue(
     P.use_ms = ms > 0 ? 1 : 0;
     {
         const char* f = getenv("SCCD_NP_FLAGS");
+        // (SCCD_NP_FLAGS_EE: the same knobs for the edge-edge pass alone -- it inherits the
+        // earliest toi of the vertex-face pass and may want other budgets)
+        const char* fe = kind == SCCD_EE ? getenv("SCCD_NP_FLAGS_EE") : nullptr;
+        if (fe)
+            f = fe;
         P.flags = f ? (int)strtoll(f, nullptr, 0) : 0;
         const char* d = getenv("SCCD_NP_DEPTH"); // test hook: exercise the "path too deep" route
         P.max_depth = d ? std::min(128, std::max(2, atoi(d))) : 128;

@@ -2,6 +2,7 @@
 ccd() step time and per-stage device times for each flag value given on the command line.
 
   python tools/time_np_flags.py c2 0 $((2<<28)) $((1<<28))
+  SCCD_NP_FLAGS_EE=$((24<<8)) python tools/time_np_flags.py c2 0     # edge-edge pass alone
 
 Bits 28..30 = log2(cooperative limit) - 13: round 0 goes to the warp-cooperative kernel when at
 most limit/2 queries survive the cull.  The edge-edge pass of a cloth scene runs after the
