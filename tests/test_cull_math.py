@@ -78,6 +78,29 @@ def test_culled_mesh_queries_are_misses(orc, scene_c1, tol, ms, f32):
 
 
 @pytest.mark.parametrize("f32", [False, True])
+@pytest.mark.parametrize("slab", [False, True])
+@pytest.mark.parametrize("tol,ms", [(1e-6, 0.0), (1e-4, 1e-4)])
+def test_culled_rigid_body_queries_are_misses(orc, sccd, tol, ms, slab, f32):
+    """Configs 3 / 4 in small: rotating, translating rigid blobs -- other L_t / L_u / L_v ratios
+    than a falling cloth (the edge-edge acceptance width depends on them)."""
+    s = sccd.scenes.blob_pile(60, seed=6 if slab else 5, slab=slab)
+    vb, eb, fb = orc.build_boxes(s, ms, f32=f32)
+    vf, _ = orc.sort_and_sweep_two_lists(vb, fb, 0, f32=f32)
+    ee, _ = orc.sort_and_sweep(eb, 0, f32=f32)
+    n_culled = 0
+    for pairs, is_vf in ((orc.canonical(vf), True), (orc.canonical(ee), False)):
+        q = orc.gather_queries(s, pairs, is_vf)
+        keep = orc.tractable(q, is_vf, ms, tol, f32=f32)
+        q = q[keep]
+        _, tpq, _ = orc.narrow_phase(q, is_vf, ms, -1, tol, True, 1.0, per_query=True, f32=f32)
+        culled = cull_mask(q, is_vf, tol, ms, f32)
+        assert not np.any(culled & (tpq < 1)), "the cull dropped a query the root finder reports"
+        assert (tpq < 1).any()                    # the scene has real contacts
+        n_culled += int(culled.sum())
+    assert n_culled > 0
+
+
+@pytest.mark.parametrize("f32", [False, True])
 @pytest.mark.parametrize("tol,ms", [(1e-6, 0.0), (1e-9, 0.0), (1e-6, 1e-8), (1e-3, 0.0)])
 def test_culled_adversarial_queries_are_misses(orc, sccd, tol, ms, f32):
     ee, vf = sccd.scenes.queries_c5(3000 if not f32 else 1200, seed=4)
