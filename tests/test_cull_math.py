@@ -67,6 +67,9 @@ def test_culled_mesh_queries_are_misses(orc, scene_c1, tol, ms, f32):
     s = scene_c1
     if f32 and ms == 1e-3:
         pytest.skip("float build with ms = 1e-3: >1e8 box checks on the CPU")
+    if f32 and tol == 1e-9:
+        pytest.skip("tol = 1e-9 is below the float resolution: the float cull keeps every query "
+                    "(scale test) and the solver needs 90 s on the CPU")
     r = orc.ccd(s, f32=f32, per_query=False)        # the candidate pairs of that scalar type
     for pairs, is_vf in ((r["vf"], True), (r["ee"], False)):
         q = orc.gather_queries(s, np.ascontiguousarray(pairs), is_vf)
