@@ -52,3 +52,26 @@ def test_product_does_not_import_oracle():
                 assert "oracle" not in text.replace("oracle/", "").lower() or f == "__init__.py" \
                     or "import oracle" not in text and "from oracle" not in text, f
                 assert "from oracle" not in text and "import oracle" not in text, f
+
+
+def test_header_is_plain_c99_and_links_from_c(sccd, tmp_path):
+    """include/sccd.h is the drop-in boundary: plain C (no C++-isms), every entry point
+    callable from a C translation unit linked against the library."""
+    import subprocess
+    sccd.capi.load()
+    src = tmp_path / "c_abi.c"
+    calls = "\n".join(f"    p[{i}] = (void*)&{name};" for i, name in enumerate(header_symbols()))
+    src.write_text(
+        '#include "sccd.h"\n#include <stdio.h>\n'
+        f"int main(void) {{\n    void* p[{len(header_symbols())}];\n{calls}\n"
+        '    printf("%s %d\\n", sccd_version(), (int)(sizeof(p) / sizeof(p[0])));\n'
+        "    return p[0] ? 0 : 1;\n}\n")
+    exe = tmp_path / "c_abi"
+    libdir = os.path.join(ROOT, "scalable-ccd_b200")
+    subprocess.check_call(
+        ["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror",
+         "-Wno-pedantic",  # (function pointer -> void* is an extension; the check is about the header)
+         f"-I{ROOT}/include", str(src), "-o", str(exe), f"-L{libdir}", "-lsccd_b200",
+         f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "sm_100a" in out.stdout, out.stdout + out.stderr
