@@ -132,6 +132,32 @@ int sccd_set_grid_cells(sccd_ctx* ctx, int max_cells);
  * exact in a double.  Boxes have to be rebuilt after a change. */
 int sccd_set_scalar_type(sccd_ctx* ctx, int type);
 
+/* Tuning and test knobs (the reference has none of them; its equivalents are compile-time
+ * constants).  Initial values come from the SCCD_* environment variables read once in
+ * sccd_create; nothing on the hot path reads the environment.  SCCD_ERR_ARG for an unknown
+ * option or a value out of range. */
+#define SCCD_OPT_NARROW_CULL 1      /* 1 (default) / 0: separating-axis cull before the solver  */
+#define SCCD_OPT_NARROW_FLAGS 2     /* narrow-phase scheduling knobs (budgets, refill, kernel
+                                       choice; see csrc/narrow.cu); results never depend on it */
+#define SCCD_OPT_NARROW_FLAGS_EE 3  /* the same for the edge-edge pass alone; < 0 = follow (2)  */
+#define SCCD_OPT_NARROW_MAX_DEPTH 4 /* bisection levels a walk tracks before handing on, 2..128 */
+#define SCCD_OPT_MAX_ITER_MODE 5    /* a query that reaches max_iter >= 0:
+                                       0 (default) its remaining boxes are ACCEPTED at their
+                                         t_lo -- never later than the exact answer;
+                                       1 they are DROPPED, as in the reference
+                                         (root_finder.cu:303-305) -- may miss a collision      */
+#define SCCD_OPT_KEY_STEPS 6        /* log2 of the major-axis quantisation steps per record     */
+#define SCCD_OPT_GRID_SCALE_MILLI 7 /* cell edge in mean box extents, x 1000 (default 3000)     */
+#define SCCD_OPT_GRID_REPL_MILLI 8  /* records per box above which the grid is coarsened, x1000 */
+#define SCCD_OPT_SWEEP_AXIS 9       /* axis the mesh pipeline sorts and sweeps along: 0 (default,
+                                       the reference's GPU path, aabb.cu:86), 1, 2, or -1 = the
+                                       axis sort_and_sweep would hand back for the NEXT call --
+                                       argmax of the box-centre variance of the previous build
+                                       (sort_and_sweep.cpp:176-195).  The overlap set and every
+                                       TOI are independent of it.                               */
+int sccd_set_option(sccd_ctx* ctx, int option, int64_t value);
+int sccd_get_option(const sccd_ctx* ctx, int option, int64_t* value);
+
 /* Multi-GPU sharding: this context makes, sorts and sweeps only the records of the rank-th of
  * `world` contiguous (y, z) cell ranges of each list (ranges balanced by record count; every
  * rank derives the same ranges from its own copy of the boxes, so there is no exchange) and
@@ -246,6 +272,14 @@ int sccd_narrow_phase_queries(
     sccd_ctx* ctx, int kind, const double* queries, int64_t n, int on_device, double ms,
     int max_iter, double tol, int allow_zero_toi, double* toi_inout, double* d_toi_per_query);
 
+/* Per-query box counters of the most recent sccd_narrow_phase / sccd_narrow_phase_queries call
+ * that ran with max_iter >= 0: the reference's CCDData::nbr_checks (ccd_data.cuh:8-18,
+ * root_finder.cu:288-289).  *d_checks: device array of *n counters owned by the context, valid
+ * until its next narrow-phase call (NULL / 0 if the last call had max_iter < 0).  A query can
+ * only have been cut short by the cap if its counter exceeds max_iter + 1; the TOI of every
+ * other query is exactly the uncapped answer. */
+int sccd_narrow_phase_checks(sccd_ctx* ctx, const uint32_t** d_checks, int64_t* n);
+
 /* ---- pipelines ------------------------------------------------------------------ */
 
 /* ccd() without the upload (cuda/ccd.cu:108-146): boxes -> VF broad+narrow ->
@@ -260,6 +294,13 @@ int sccd_ccd(
 int sccd_ccd_collisions(
     sccd_ctx* ctx, double min_distance, int max_iter, double tol, int allow_zero_toi,
     double* toi, sccd_pair* ids, double* tois, int64_t cap, int64_t* n_vf, int64_t* n_ee);
+
+/* The collisions of the most recent sccd_ccd_collisions on this context, without running
+ * anything again: call sccd_ccd_collisions with cap = 0 to learn the counts, then fetch.
+ * (copy_out_collisions, cuda/narrow_phase/narrow_phase.cu:84-103, hands the reference's caller
+ * one vector after one pass; this keeps it one pass here as well.) */
+int sccd_get_collisions(
+    sccd_ctx* ctx, sccd_pair* ids, double* tois, int64_t cap, int64_t* n_vf, int64_t* n_ee);
 
 /* Whole ccd() including the host->device upload (cuda/ccd.cuh:26-38). */
 int sccd_ccd_host(

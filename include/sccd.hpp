@@ -118,9 +118,7 @@ namespace cuda {
             nullptr, nullptr, 0, &nvf, &nee));
         std::vector<sccd_pair> ids((size_t)(nvf + nee));
         std::vector<double> tois(ids.size());
-        c.check(sccd_ccd_collisions(
-            c.h, minimum_separation_distance, max_iterations, tolerance, allow_zero_toi, &toi,
-            ids.data(), tois.data(), (int64_t)ids.size(), &nvf, &nee));
+        c.check(sccd_get_collisions(c.h, ids.data(), tois.data(), (int64_t)ids.size(), &nvf, &nee));
         for (size_t i = 0; i < ids.size(); i++)
             collisions.emplace_back(ids[i].a, ids[i].b, (Scalar)tois[i]);
         return (Scalar)toi;

@@ -17,6 +17,8 @@ LIB_PATH = os.path.join(HERE, "libsccd_b200.so")
 VF, EE, BOXES = 0, 1, 2
 F64, F32 = 0, 1  # sccd_set_scalar_type: the reference's SCALABLE_CCD_USE_DOUBLE switch
 OK, ERR_CUDA, ERR_ARG, ERR_STATE, ERR_MEMORY = 0, -1, -2, -3, -4
+(OPT_NARROW_CULL, OPT_NARROW_FLAGS, OPT_NARROW_FLAGS_EE, OPT_NARROW_MAX_DEPTH, OPT_MAX_ITER_MODE,
+ OPT_KEY_STEPS, OPT_GRID_SCALE_MILLI, OPT_GRID_REPL_MILLI, OPT_SWEEP_AXIS) = range(1, 10)
 
 AABB_DTYPE = np.dtype(
     [("min", np.float64, 3), ("max", np.float64, 3), ("vids", np.int32, 3), ("elem", np.int32)])
@@ -31,6 +33,7 @@ SYMBOLS = [
     "sccd_broad_phase_begin",
     "sccd_broad_phase_partial", "sccd_broad_phase_is_complete", "sccd_broad_phase",
     "sccd_narrow_phase", "sccd_narrow_phase_queries", "sccd_ccd", "sccd_ccd_collisions",
+    "sccd_get_collisions", "sccd_set_option", "sccd_get_option", "sccd_narrow_phase_checks",
     "sccd_ccd_host", "sccd_ipc_ccd_strategy", "sccd_get_stats", "sccd_reset_stats",
     "sccd_synchronize", "sccd_measure_fp64_peak",
     "sccd_version",
@@ -138,6 +141,15 @@ class Context:
 
     def set_shard(self, rank: int, world: int):
         self._chk(self.L.sccd_set_shard(self._h, C.c_int(rank), C.c_int(world)))
+
+    def set_option(self, option: int, value: int):
+        """sccd_set_option: OPT_* constants of this module."""
+        self._chk(self.L.sccd_set_option(self._h, C.c_int(option), C.c_int64(value)))
+
+    def get_option(self, option: int) -> int:
+        v = C.c_int64(0)
+        self._chk(self.L.sccd_get_option(self._h, C.c_int(option), C.byref(v)))
+        return v.value
 
     def set_scalar_type(self, scalar: int):
         """F64 (default) or F32 = the reference built with SCALABLE_CCD_USE_DOUBLE=OFF."""
@@ -287,6 +299,13 @@ class Context:
             C.byref(t), C.c_void_p(d_toi_per_query)))
         return t.value
 
+    def narrow_phase_checks(self):
+        """-> (device pointer, n): per-query box counters of the last capped narrow phase."""
+        p = C.c_void_p(0)
+        n = C.c_int64(0)
+        self._chk(self.L.sccd_narrow_phase_checks(self._h, C.byref(p), C.byref(n)))
+        return (p.value or 0), n.value
+
     # ---- pipelines
     def ccd(self, ms=0.0, max_iter=-1, tol=1e-6, allow_zero_toi=True) -> float:
         t = C.c_double(1.0)
@@ -318,10 +337,8 @@ class Context:
         k = nvf.value + nee.value
         ids = np.empty((max(k, 1), 2), np.int32)
         tois = np.empty(max(k, 1), np.float64)
-        self._chk(self.L.sccd_ccd_collisions(
-            self._h, C.c_double(ms), C.c_int(max_iter), C.c_double(tol),
-            C.c_int(int(allow_zero_toi)), C.byref(t), _ptr(ids), _ptr(tois), C.c_int64(k),
-            C.byref(nvf), C.byref(nee)))
+        self._chk(self.L.sccd_get_collisions(   # one pipeline pass: fetch what it kept
+            self._h, _ptr(ids), _ptr(tois), C.c_int64(k), C.byref(nvf), C.byref(nee)))
         a = nvf.value
         return t.value, (ids[:a], tois[:a]), (ids[a:k], tois[a:k])
 

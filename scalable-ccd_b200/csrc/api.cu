@@ -86,6 +86,8 @@ struct sccd_ctx {
         SortedList sorted;
         BoxArrays unsorted;
         int n_boxes = 0;
+        int axis = 0;      // axis the records of this list are rotated to / swept along
+        int next_axis = 0; // variance argmax of the last build (sort_and_sweep.cpp:176-195)
         int built_rank = 0, built_world = 1; // sharding the sorted records were made for
         // sort_list_begin -> sort_list_finish hand-over
         GridParams g_try;
@@ -107,10 +109,24 @@ struct sccd_ctx {
         unsigned long long splits[2 * 16 + 2];
     };
     ListHost* h_lists = nullptr; // [3]
+    DevBuf b_flags;            // [0]: an E / F entry is not a vertex index (box kernels)
+    int* h_flags = nullptr;    // pinned copy
     int grid_max_cells = -1;   // < 0: choose automatically; 1 forces the plain 1-axis sweep
     // tuning knobs (env SCCD_GRID_SCALE / SCCD_GRID_REPL): cell edge in mean box extents, and
     // the replication (records per box) above which the grid is coarsened
     double grid_scale = 3.0, grid_repl = 2.5;
+    // sccd_set_option (initial values from the SCCD_* environment variables, read ONCE in
+    // sccd_create; nothing on the hot path calls getenv)
+    struct Options {
+        int np_cull = 1;        // separating-axis cull in front of the solver
+        int np_flags = 0;       // narrow-phase scheduling knobs (narrow.cu)
+        int np_flags_ee = -1;   // the same for the edge-edge pass alone (< 0: follow np_flags)
+        int np_depth = 128;     // levels a walk tracks before handing on
+        int cap_drops = 0;      // max_iter reached: 0 accept at t_lo, 1 drop (reference)
+        int key_steps = 3;      // log2 of the x quantisation steps per record of a cell
+        int sweep_axis = 0;     // 0/1/2, or -1: variance argmax of the previous build
+    } opt;
+    int next_axis = 0;          // argmax of the box-centre variance of the last build
 
     // Run state (broad-phase cursor, pair / staging buffers, narrow-phase lists and counters)
     // and the stream its work is enqueued on.  Broad and narrow phase are split in an enqueue
@@ -127,6 +143,7 @@ struct sccd_ctx {
         DevBuf b_counters, b_items[2], b_toi_q, b_checks_q, b_queries, b_surv;
         NarrowCounters* h_counters = nullptr; // pinned
         unsigned long long item_cap = 0; // capacity of each of the two hand-on lists
+        long long checks_n = 0;          // queries of the last batch that counted its checks
         // narrow_enqueue -> narrow_finish hand-over
         struct Pending {
             bool active = false;
@@ -141,6 +158,11 @@ struct sccd_ctx {
     Run* cur = &runs[0];
     DevBuf b_gtoi; // earliest toi shared by the two lists of a pipeline call
     double* h_gtoi = nullptr; // pinned
+
+    // collisions of the last sccd_ccd_collisions (fetched by sccd_get_collisions)
+    std::vector<sccd_pair> coll_ids;
+    std::vector<double> coll_toi;
+    int64_t coll_n[2] = { 0, 0 };
 
     sccd_stats stats {};
     LaunchCounter lc;
@@ -174,6 +196,8 @@ struct sccd_ctx {
             cudaEventDestroy(ev_vf_done);
         if (h_lists)
             cudaFreeHost(h_lists);
+        if (h_flags)
+            cudaFreeHost(h_flags);
         for (auto& e : ev)
             if (e)
                 cudaEventDestroy(e);
@@ -356,7 +380,7 @@ void prepare_list(sccd_ctx* c, int which, int n, bool two_lists)
 
 // Choose the (y, z) cell grid of a list from its box statistics: cells about twice the mean
 // box extent (so a box touches ~1.5 cells per axis), at most 1024 per axis / 2^20 in total.
-GridParams choose_grid(const double st[6], int n, int max_cells, double scale)
+GridParams choose_grid(const double* st, int n, int max_cells, double scale)
 {
     GridParams g;
     if (n <= 0 || max_cells == 1)
@@ -551,8 +575,7 @@ void sort_list_finish(
     {
         const int x_max = 32 - kKeyFlagBits - cell_bits;
         const double per_cell = (double)m_total / (double)((long long)g.sy * g.sz);
-        // tuning knob (env SCCD_KEY_STEPS): log2 of the quantisation steps per record
-        static const int steps = getenv("SCCD_KEY_STEPS") ? atoi(getenv("SCCD_KEY_STEPS")) : 3;
+        const int steps = c->opt.key_steps; // log2 of the quantisation steps per record
         int want = steps;
         while (want < x_max && (double)(1ll << (want - steps)) < per_cell)
             want++;
@@ -632,16 +655,44 @@ void build_boxes(sccd_ctx* c, double inflation_radius)
         : std::nextafter(inflation_radius, DBL_MAX);
     auto& LV = c->lists[0];
     auto& LE = c->lists[1];
+    // SCCD_OPT_SWEEP_AXIS: a fixed axis, or (-1) the axis the previous build handed back
+    LV.axis = c->opt.sweep_axis >= 0 ? c->opt.sweep_axis : LV.next_axis;
+    LE.axis = c->opt.sweep_axis >= 0 ? c->opt.sweep_axis : LE.next_axis;
+    int* d_bad = (int*)c->b_flags.reserve(64);
+    if (!c->h_flags)
+        SCCD_CUDA(cudaMallocHost((void**)&c->h_flags, 64));
+    SCCD_CUDA(cudaMemsetAsync(d_bad, 0, 4, c->stream));
     const size_t kt_boxes = kt_begin(c, &c->stats.ms_k_boxes);
     launch_mesh_boxes(
         c->dV0, c->dV1, nV, radius_up, c->f32, c->b_vtab.as<VertexRec>(), c->b_vbox.as<double>(),
-        c->dE, nE, c->dF, nF, LE.unsorted, LV.unsorted, c->stream, c->lc);
+        c->dE, nE, c->dF, nF, LE.unsorted, LV.unsorted, LE.axis, LV.axis, d_bad, c->stream, c->lc);
     kt_end(c, kt_boxes);
     record(c, EV_BUILD);
     // sync 1: statistics of both lists; sync 2: record counts of both lists
     list_stats(c, 0);
     list_stats(c, 1);
+    SCCD_CUDA(cudaMemcpyAsync(c->h_flags, d_bad, 4, cudaMemcpyDeviceToHost, c->stream));
     SCCD_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->h_flags[0]) // the reference would read out of bounds (aabb.cu:199-226)
+        throw std::invalid_argument("build_boxes: an edge / face refers to a vertex that does not exist");
+    for (int which = 0; which < 2; which++) {
+        // next sweep axis = argmax of the variance of the box centres, as sort_and_sweep hands
+        // it back (sort_and_sweep.cpp:176-195); here over the sampled boxes of the statistics
+        auto& L = c->lists[which];
+        const double* st = list_host(c, which).stats;
+        const int stride = std::min(16, std::max(1, L.n_boxes >> 18));
+        const double ns = (double)((L.n_boxes + stride - 1) / stride);
+        double var[3] = { 0, 0, 0 }; // in the caller's axes
+        for (int k = 0; k < 3; k++)
+            var[(L.axis + k) % 3] = ns > 0 ? st[11 + k] - st[8 + k] * st[8 + k] / ns : 0.0;
+        int best = 0;
+        if (var[1] > var[0])
+            best = 1;
+        if (var[2] > var[best])
+            best = 2;
+        L.next_axis = L.n_boxes > 0 ? best : L.axis;
+    }
+    c->next_axis = LV.next_axis;
     sort_list_begin(c, 0);
     sort_list_begin(c, 1);
     SCCD_CUDA(cudaStreamSynchronize(c->stream));
@@ -946,32 +997,25 @@ void narrow_enqueue(
     P.max_iter = max_iter;
     P.allow_zero_toi = allow_zero_toi ? 1 : 0;
     P.use_ms = ms > 0 ? 1 : 0;
-    {
-        const char* f = getenv("SCCD_NP_FLAGS");
-        // (SCCD_NP_FLAGS_EE: the same knobs for the edge-edge pass alone -- it inherits the
-        // earliest toi of the vertex-face pass and may want other budgets)
-        const char* fe = kind == SCCD_EE ? getenv("SCCD_NP_FLAGS_EE") : nullptr;
-        if (fe)
-            f = fe;
-        P.flags = f ? (int)strtoll(f, nullptr, 0) : 0;
-        const char* d = getenv("SCCD_NP_DEPTH"); // test hook: exercise the "path too deep" route
-        P.max_depth = d ? std::min(128, std::max(2, atoi(d))) : 128;
-    }
+    // (the edge-edge pass inherits the earliest toi of the vertex-face pass and may want other
+    // budgets: SCCD_OPT_NARROW_FLAGS_EE)
+    P.flags = (kind == SCCD_EE && c->opt.np_flags_ee >= 0) ? c->opt.np_flags_ee : c->opt.np_flags;
+    P.max_depth = c->opt.np_depth;
+    P.cap_drops = c->opt.cap_drops;
     SCCD_CUDA(cudaMemsetAsync(R.b_counters.ptr, 0, sizeof(NarrowCounters), st));
     if (d_toi_per_query)
         launch_fill_f64(d_toi_per_query, in.n, INFINITY, st, c->lc);
     unsigned int* checks = nullptr;
+    R.checks_n = 0;
     if (max_iter >= 0) {
         checks = (unsigned int*)R.b_checks_q.reserve((size_t)in.n * 4);
         SCCD_CUDA(cudaMemsetAsync(checks, 0, (size_t)in.n * 4, st));
+        R.checks_n = in.n;
     }
     // separating-axis cull in front of the solver (SCCD_NP_CULL=0 switches it off: A/B, tests)
     uint32_t* survivors = nullptr;
-    {
-        const char* e = getenv("SCCD_NP_CULL");
-        if (!e || atoi(e) != 0)
-            survivors = (uint32_t*)R.b_surv.reserve((size_t)in.n * 4);
-    }
+    if (c->opt.np_cull)
+        survivors = (uint32_t*)R.b_surv.reserve((size_t)in.n * 4);
     const size_t kt = kt_begin(c, &c->stats.ms_k_narrow[kind]);
     launch_narrow_phase(
         kind == SCCD_VF, c->f32, in, P, R.b_counters.as<NarrowCounters>(), d_gtoi,
@@ -1021,6 +1065,8 @@ void narrow_finish(sccd_ctx* c, double* d_gtoi)
     c->stats.n_capped[kind] += (int64_t)r.capped;
     if (r.overflow)
         c->stats.queue_overflow = 1;
+    if (r.bad_input)
+        throw std::invalid_argument("narrow_phase: a pair refers to an element that is not in the mesh");
     if (r.overflow == 2)
         throw std::runtime_error(
             "narrow phase: item list too small to hand on a sub-tree deeper than 128 levels; "
@@ -1068,6 +1114,7 @@ NarrowInput mesh_input(sccd_ctx* c, const sccd_pair* d_pairs, int64_t n)
     in.vtab = c->b_vtab.as<VertexRec>();
     in.E = c->dE;
     in.F = c->dF;
+    in.nV = c->nV;
     in.nE = c->nE;
     in.nF = c->nF;
     in.pairs = d_pairs;
@@ -1269,10 +1316,24 @@ int sccd_create(int device, void* stream, sccd_ctx** out)
         if (prop.major != 10)
             throw CudaError("sccd: this library is built for sm_100a (B200) only");
         c->num_sms = prop.multiProcessorCount;
+        // initial option values; afterwards only sccd_set_option changes them
         if (const char* e = getenv("SCCD_GRID_SCALE"))
             c->grid_scale = std::min(64.0, std::max(0.25, atof(e)));
         if (const char* e = getenv("SCCD_GRID_REPL"))
             c->grid_repl = std::min(16.0, std::max(1.0, atof(e)));
+        if (const char* e = getenv("SCCD_NP_FLAGS"))
+            c->opt.np_flags = (int)strtoll(e, nullptr, 0);
+        if (const char* e = getenv("SCCD_NP_FLAGS_EE"))
+            c->opt.np_flags_ee = (int)strtoll(e, nullptr, 0);
+        if (const char* e = getenv("SCCD_NP_DEPTH"))
+            c->opt.np_depth = std::min(128, std::max(2, atoi(e)));
+        if (const char* e = getenv("SCCD_NP_CULL"))
+            c->opt.np_cull = atoi(e) != 0;
+        if (const char* e = getenv("SCCD_KEY_STEPS"))
+            c->opt.key_steps = std::min(16, std::max(0, atoi(e)));
+        if (const char* e = getenv("SCCD_SWEEP_AXIS"))
+            c->opt.sweep_axis = std::min(2, std::max(-1, atoi(e)));
+        narrow_init_device();
         for (auto& e : c->ev)
             SCCD_CUDA(cudaEventCreate(&e));
         c->runs[0].stream = c->stream;
@@ -1344,6 +1405,76 @@ int sccd_set_scalar_type(sccd_ctx* ctx, int type)
         ctx->f32 = type == SCCD_F32;
         ctx->have_boxes = false; // boxes and the vertex table depend on the scalar type
         ctx->runs[0].bp_kind = ctx->runs[1].bp_kind = -1;
+    }
+    return SCCD_OK;
+}
+
+int sccd_set_option(sccd_ctx* ctx, int option, int64_t value)
+{
+    if (!ctx)
+        return SCCD_ERR_ARG;
+    auto& o = ctx->opt;
+    switch (option) {
+    case SCCD_OPT_NARROW_CULL: o.np_cull = value != 0; break;
+    case SCCD_OPT_NARROW_FLAGS: o.np_flags = (int)value; break;
+    case SCCD_OPT_NARROW_FLAGS_EE: o.np_flags_ee = (int)value; break;
+    case SCCD_OPT_NARROW_MAX_DEPTH:
+        if (value < 2 || value > 128)
+            return SCCD_ERR_ARG;
+        o.np_depth = (int)value;
+        break;
+    case SCCD_OPT_MAX_ITER_MODE:
+        if (value != 0 && value != 1)
+            return SCCD_ERR_ARG;
+        o.cap_drops = (int)value;
+        break;
+    case SCCD_OPT_KEY_STEPS:
+        if (value < 0 || value > 16)
+            return SCCD_ERR_ARG;
+        o.key_steps = (int)value;
+        break;
+    case SCCD_OPT_GRID_SCALE_MILLI:
+        if (value < 250 || value > 64000)
+            return SCCD_ERR_ARG;
+        ctx->grid_scale = (double)value / 1000.0;
+        break;
+    case SCCD_OPT_GRID_REPL_MILLI:
+        if (value < 1000 || value > 16000)
+            return SCCD_ERR_ARG;
+        ctx->grid_repl = (double)value / 1000.0;
+        break;
+    case SCCD_OPT_SWEEP_AXIS:
+        if (value < -1 || value > 2)
+            return SCCD_ERR_ARG;
+        if (o.sweep_axis != (int)value) {
+            o.sweep_axis = (int)value;
+            ctx->have_boxes = false;
+            ctx->runs[0].bp_kind = ctx->runs[1].bp_kind = -1;
+        }
+        break;
+    default:
+        ctx->error = "set_option: unknown option";
+        return SCCD_ERR_ARG;
+    }
+    return SCCD_OK;
+}
+
+int sccd_get_option(const sccd_ctx* ctx, int option, int64_t* value)
+{
+    if (!ctx || !value)
+        return SCCD_ERR_ARG;
+    const auto& o = ctx->opt;
+    switch (option) {
+    case SCCD_OPT_NARROW_CULL: *value = o.np_cull; break;
+    case SCCD_OPT_NARROW_FLAGS: *value = o.np_flags; break;
+    case SCCD_OPT_NARROW_FLAGS_EE: *value = o.np_flags_ee; break;
+    case SCCD_OPT_NARROW_MAX_DEPTH: *value = o.np_depth; break;
+    case SCCD_OPT_MAX_ITER_MODE: *value = o.cap_drops; break;
+    case SCCD_OPT_KEY_STEPS: *value = o.key_steps; break;
+    case SCCD_OPT_GRID_SCALE_MILLI: *value = (int64_t)std::llround(ctx->grid_scale * 1000.0); break;
+    case SCCD_OPT_GRID_REPL_MILLI: *value = (int64_t)std::llround(ctx->grid_repl * 1000.0); break;
+    case SCCD_OPT_SWEEP_AXIS: *value = o.sweep_axis; break;
+    default: return SCCD_ERR_ARG;
     }
     return SCCD_OK;
 }
@@ -1466,13 +1597,15 @@ int sccd_get_boxes(sccd_ctx* ctx, int which, sccd_aabb* out)
         SCCD_CUDA(cudaMemcpy(x.data(), U.x + off, sizeof(double2) * n, cudaMemcpyDeviceToHost));
         SCCD_CUDA(cudaMemcpy(yz.data(), U.yz + off, sizeof(double4) * n, cudaMemcpyDeviceToHost));
         SCCD_CUDA(cudaMemcpy(id.data(), U.id + off, sizeof(int4) * n, cudaMemcpyDeviceToHost));
+        // records are rotated to (axis, axis + 1, axis + 2) mod 3
+        const int ax = ctx->lists[which == 1 ? 1 : 0].axis, ay = (ax + 1) % 3, az = (ax + 2) % 3;
         for (int i = 0; i < n; i++) {
-            out[i].min[0] = x[i].x;
-            out[i].max[0] = x[i].y;
-            out[i].min[1] = yz[i].x;
-            out[i].min[2] = yz[i].y;
-            out[i].max[1] = yz[i].z;
-            out[i].max[2] = yz[i].w;
+            out[i].min[ax] = x[i].x;
+            out[i].max[ax] = x[i].y;
+            out[i].min[ay] = yz[i].x;
+            out[i].min[az] = yz[i].y;
+            out[i].max[ay] = yz[i].z;
+            out[i].max[az] = yz[i].w;
             out[i].vertex_ids[0] = id[i].x;
             out[i].vertex_ids[1] = id[i].y;
             out[i].vertex_ids[2] = id[i].z;
@@ -1591,6 +1724,16 @@ int sccd_narrow_phase_queries(
     });
 }
 
+int sccd_narrow_phase_checks(sccd_ctx* ctx, const uint32_t** d_checks, int64_t* n)
+{
+    if (!ctx || !d_checks || !n)
+        return SCCD_ERR_ARG;
+    const auto& R = ctx->runs[0];
+    *d_checks = R.checks_n > 0 ? R.b_checks_q.as<uint32_t>() : nullptr;
+    *n = R.checks_n;
+    return SCCD_OK;
+}
+
 int sccd_ccd(
     sccd_ctx* ctx, double min_distance, int max_iter, double tol, int allow_zero_toi, double* toi)
 {
@@ -1611,9 +1754,12 @@ int sccd_ccd_collisions(
     return guarded(ctx, [&] {
         if (!toi)
             throw std::invalid_argument("ccd_collisions: null toi");
-        std::vector<sccd_pair> cid;
-        std::vector<double> ct;
-        int64_t nc[2] = { 0, 0 };
+        std::vector<sccd_pair>& cid = ctx->coll_ids;
+        std::vector<double>& ct = ctx->coll_toi;
+        int64_t* nc = ctx->coll_n;
+        cid.clear();
+        ct.clear();
+        nc[0] = nc[1] = 0;
         run_pipeline(
             ctx, min_distance, max_iter, tol, allow_zero_toi != 0, false, toi, true, &cid, &ct, nc);
         const int64_t k = std::min<int64_t>(cap, (int64_t)cid.size());
@@ -1627,6 +1773,23 @@ int sccd_ccd_collisions(
             *n_ee = nc[1];
         return SCCD_OK;
     });
+}
+
+int sccd_get_collisions(
+    sccd_ctx* ctx, sccd_pair* ids, double* tois, int64_t cap, int64_t* n_vf, int64_t* n_ee)
+{
+    if (!ctx || cap < 0)
+        return SCCD_ERR_ARG;
+    const int64_t k = std::min<int64_t>(cap, (int64_t)ctx->coll_ids.size());
+    if (ids && k > 0)
+        std::memcpy(ids, ctx->coll_ids.data(), (size_t)k * sizeof(sccd_pair));
+    if (tois && k > 0)
+        std::memcpy(tois, ctx->coll_toi.data(), (size_t)k * 8);
+    if (n_vf)
+        *n_vf = ctx->coll_n[0];
+    if (n_ee)
+        *n_ee = ctx->coll_n[1];
+    return SCCD_OK;
 }
 
 int sccd_ccd_host(

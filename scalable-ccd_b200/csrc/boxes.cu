@@ -22,11 +22,20 @@ __device__ __forceinline__ double next_up(double x) { return nextafter(x, DBL_MA
 __device__ __forceinline__ float next_down(float x) { return nextafterf(x, -FLT_MAX); }
 __device__ __forceinline__ float next_up(float x) { return nextafterf(x, FLT_MAX); }
 
-__device__ __forceinline__ void store_record(
-    const BoxArrays& out, int k, const double lo[3], const double hi[3], int4 id)
+// The sweep runs along the FIRST coordinate of a record: a list swept along `axis` stores its
+// boxes with the axes rotated to (axis, axis + 1, axis + 2) mod 3 (SCCD_OPT_SWEEP_AXIS; the
+// reference's GPU path always sorts on x, aabb.cu:86, its CPU path on the caller's axis,
+// sort_and_sweep.cpp:78-116).  The overlap set does not depend on it.
+__device__ __forceinline__ double pick_axis(const double v[3], int a)
 {
-    out.x[k] = make_double2(lo[0], hi[0]);
-    out.yz[k] = make_double4(lo[1], lo[2], hi[1], hi[2]);
+    return a == 0 ? v[0] : (a == 1 ? v[1] : v[2]);
+}
+__device__ __forceinline__ void store_record(
+    const BoxArrays& out, int k, const double lo[3], const double hi[3], int4 id, int axis)
+{
+    const int ay = axis == 2 ? 0 : axis + 1, az = axis == 0 ? 2 : axis - 1;
+    out.x[k] = make_double2(pick_axis(lo, axis), pick_axis(hi, axis));
+    out.yz[k] = make_double4(pick_axis(lo, ay), pick_axis(lo, az), pick_axis(hi, ay), pick_axis(hi, az));
     out.id[k] = id;
 }
 
@@ -39,7 +48,7 @@ __device__ __forceinline__ void store_record(
 template <bool F32>
 __global__ void __launch_bounds__(kThreads) vertex_boxes_kernel(
     const double* __restrict__ V0, const double* __restrict__ V1, int nV, double radius_up,
-    VertexRec* __restrict__ vtab, double* __restrict__ vbox, BoxArrays vf)
+    VertexRec* __restrict__ vtab, double* __restrict__ vbox, BoxArrays vf, int axis_vf)
 {
     const int i = blockIdx.x * kThreads + threadIdx.x;
     if (i >= nV)
@@ -83,7 +92,7 @@ __global__ void __launch_bounds__(kThreads) vertex_boxes_kernel(
     vb[2] = make_double2(hi[1], hi[2]);
     // aabb.cu:180-181 ids; element id flipped because vertices are list A of the
     // vertex-face sweep (broad_phase.cu:20-26).
-    store_record(vf, i, lo, hi, make_int4(i, -i - 1, -i - 1, -i - 1));
+    store_record(vf, i, lo, hi, make_int4(i, -i - 1, -i - 1, -i - 1), axis_vf);
 }
 
 __device__ __forceinline__ void load_vbox(
@@ -102,12 +111,20 @@ __device__ __forceinline__ void load_vbox(
 // aabb.cu:186-229 build_edge_boxes / build_face_boxes (union of vertex boxes).
 __global__ void __launch_bounds__(kThreads) element_boxes_kernel(
     const double* __restrict__ vbox, const int32_t* __restrict__ E, int nE,
-    const int32_t* __restrict__ F, int nF, int nV, BoxArrays eb, BoxArrays vf)
+    const int32_t* __restrict__ F, int nF, int nV, BoxArrays eb, BoxArrays vf, int axis_e,
+    int axis_vf, int* __restrict__ bad)
 {
     const int t = blockIdx.x * kThreads + threadIdx.x;
     if (t < nE) {
         const int e0 = E[t], e1 = E[t + (size_t)nE];
         double lo[3], hi[3], lo1[3], hi1[3];
+        if ((unsigned)e0 >= (unsigned)nV || (unsigned)e1 >= (unsigned)nV) {
+            // the reference would index out of bounds; reported as SCCD_ERR_ARG by build_boxes
+            *bad = 1;
+            const double z[3] = { 0.0, 0.0, 0.0 };
+            store_record(eb, t, z, z, make_int4(0, 0, -1, t), axis_e);
+            return;
+        }
         load_vbox(vbox, e0, lo, hi);
         load_vbox(vbox, e1, lo1, hi1);
 #pragma unroll
@@ -115,11 +132,18 @@ __global__ void __launch_bounds__(kThreads) element_boxes_kernel(
             lo[k] = fmin(lo[k], lo1[k]);
             hi[k] = fmax(hi[k], hi1[k]);
         }
-        store_record(eb, t, lo, hi, make_int4(e0, e1, -e0 - 1, t));
+        store_record(eb, t, lo, hi, make_int4(e0, e1, -e0 - 1, t), axis_e);
     } else if (t < nE + nF) {
         const int f = t - nE;
         const int f0 = F[f], f1 = F[f + (size_t)nF], f2 = F[f + (size_t)2 * nF];
         double lo[3], hi[3], lo1[3], hi1[3], lo2[3], hi2[3];
+        if ((unsigned)f0 >= (unsigned)nV || (unsigned)f1 >= (unsigned)nV
+            || (unsigned)f2 >= (unsigned)nV) {
+            *bad = 1;
+            const double z[3] = { 0.0, 0.0, 0.0 };
+            store_record(vf, nV + f, z, z, make_int4(0, 0, 0, f), axis_vf);
+            return;
+        }
         load_vbox(vbox, f0, lo, hi);
         load_vbox(vbox, f1, lo1, hi1);
         load_vbox(vbox, f2, lo2, hi2);
@@ -128,7 +152,7 @@ __global__ void __launch_bounds__(kThreads) element_boxes_kernel(
             lo[k] = fmin(fmin(lo[k], lo1[k]), lo2[k]);
             hi[k] = fmax(fmax(hi[k], hi1[k]), hi2[k]);
         }
-        store_record(vf, nV + f, lo, hi, make_int4(f0, f1, f2, f));
+        store_record(vf, nV + f, lo, hi, make_int4(f0, f1, f2, f), axis_vf);
     }
 }
 
@@ -273,22 +297,22 @@ void launch_element_aabbs(
 void launch_mesh_boxes(
     const double* V0, const double* V1, int nV, double radius_up, bool f32, VertexRec* vtab,
     double* vbox, const int32_t* E, int nE, const int32_t* F, int nF, BoxArrays e_unsorted,
-    BoxArrays vf_unsorted, cudaStream_t s, LaunchCounter& lc)
+    BoxArrays vf_unsorted, int axis_e, int axis_vf, int* bad, cudaStream_t s, LaunchCounter& lc)
 {
     if (nV > 0) {
         const int grid = (nV + kThreads - 1) / kThreads;
         if (f32)
             vertex_boxes_kernel<true><<<grid, kThreads, 0, s>>>(
-                V0, V1, nV, radius_up, vtab, vbox, vf_unsorted);
+                V0, V1, nV, radius_up, vtab, vbox, vf_unsorted, axis_vf);
         else
             vertex_boxes_kernel<false><<<grid, kThreads, 0, s>>>(
-                V0, V1, nV, radius_up, vtab, vbox, vf_unsorted);
+                V0, V1, nV, radius_up, vtab, vbox, vf_unsorted, axis_vf);
         SCCD_CUDA(cudaGetLastError());
         lc.n++;
     }
     if (nE + nF > 0) {
         element_boxes_kernel<<<(nE + nF + kThreads - 1) / kThreads, kThreads, 0, s>>>(
-            vbox, E, nE, F, nF, nV, e_unsorted, vf_unsorted);
+            vbox, E, nE, F, nF, nV, e_unsorted, vf_unsorted, axis_e, axis_vf, bad);
         SCCD_CUDA(cudaGetLastError());
         lc.n++;
     }

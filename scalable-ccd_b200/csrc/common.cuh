@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <stdexcept>
@@ -32,9 +33,10 @@ inline void check(cudaError_t e, const char* what, const char* file, int line)
 // ---- grow-only device buffer (kept across calls: frame-to-frame reuse) -----------
 // bumped by every (re)allocation: lets the context reuse its last cudaMemGetInfo() answer
 // (the call takes milliseconds once gigabytes are mapped) while nothing was allocated
-inline unsigned long long& alloc_epoch()
+// (process-wide and atomic: contexts on different threads allocate concurrently)
+inline std::atomic<unsigned long long>& alloc_epoch()
 {
-    static unsigned long long e = 0;
+    static std::atomic<unsigned long long> e { 0 };
     return e;
 }
 
@@ -64,7 +66,7 @@ struct DevBuf {
                 SCCD_CUDA(cudaMalloc(&ptr, want));
             }
             cap = want;
-            alloc_epoch()++;
+            alloc_epoch().fetch_add(1, std::memory_order_relaxed);
         }
         return ptr;
     }
@@ -159,17 +161,22 @@ struct SortedList {
     PrefilterArrays pf; // sorted prefilter view
 };
 
-constexpr int kNumStats = 8;
+constexpr int kNumStats = 14;
 #ifdef __CUDACC__
 // Box statistics of a list (grid choice): r[0..7] = {min ymin, max ymax, min zmin, max zmax,
-// sum (ymax-ymin), sum (zmax-zmin), min xmin, max xmax}.  Fixed reduction trees everywhere, so
-// the sums -- and with them the chosen grid -- are deterministic.
+// sum (ymax-ymin), sum (zmax-zmin), min xmin, max xmax, sum c_x, sum c_y, sum c_z, sum c_x^2,
+// sum c_y^2, sum c_z^2} with c = box centre (the variance that picks the next sweep axis,
+// sort_and_sweep.cpp:176-195; axes in the record's rotated order).  Fixed reduction trees
+// everywhere, so the sums -- and with them the chosen grid -- are deterministic.
 __device__ __forceinline__ void stats_identity(double r[kNumStats])
 {
     r[0] = 1.7976931348623157e308, r[1] = -1.7976931348623157e308;
     r[2] = 1.7976931348623157e308, r[3] = -1.7976931348623157e308;
     r[4] = 0.0, r[5] = 0.0;
     r[6] = 1.7976931348623157e308, r[7] = -1.7976931348623157e308;
+#pragma unroll
+    for (int k = 8; k < kNumStats; k++)
+        r[k] = 0.0;
 }
 __device__ __forceinline__ void stats_merge(double r[kNumStats], const double o[kNumStats])
 {
@@ -181,12 +188,21 @@ __device__ __forceinline__ void stats_merge(double r[kNumStats], const double o[
     r[5] += o[5];
     r[6] = fmin(r[6], o[6]);
     r[7] = fmax(r[7], o[7]);
+#pragma unroll
+    for (int k = 8; k < kNumStats; k++)
+        r[k] += o[k];
 }
 __device__ __forceinline__ void stats_of_box(
     double r[kNumStats], const double lo[3], const double hi[3])
 {
     r[0] = lo[1], r[1] = hi[1], r[2] = lo[2], r[3] = hi[2];
     r[4] = hi[1] - lo[1], r[5] = hi[2] - lo[2], r[6] = lo[0], r[7] = hi[0];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const double c = (lo[k] + hi[k]) / 2; // sort_and_sweep.cpp:180
+        r[8 + k] = c;
+        r[11 + k] = c * c;
+    }
 }
 // block reduction (blockDim.x = 32 * warps <= 1024); the result is valid on thread 0.
 // red: shared scratch of 32 * kNumStats doubles.
@@ -229,7 +245,8 @@ struct NarrowParams {
     int allow_zero_toi;
     int use_ms;     // ms > 0 (selects the error filter, root_finder.cu:95-122)
     int flags;      // debug knobs (SCCD_NP_FLAGS env), see narrow.cu
-    int max_depth;  // levels a walk may track before handing on (<= 128; SCCD_NP_DEPTH env)
+    int max_depth;  // levels a walk may track before handing on (<= 128)
+    int cap_drops;  // max_iter reached: 0 = accept the box at t_lo (conservative), 1 = drop it
 };
 
 // A pending sub-box of a query, handed from one round of the narrow phase to the next
@@ -252,9 +269,15 @@ struct alignas(128) NarrowCounters {
     alignas(128) unsigned long long next[kNarrowRounds];      // next unclaimed work index
     alignas(128) unsigned long long n_items[kNarrowRounds + 1]; // [r] = items round r reads
     alignas(128) int overflow;                        // an item list was full (work kept local)
+    int bad_input;                                    // a pair id is no element of the mesh
     unsigned long long box_checks;
     unsigned long long donated;
     unsigned long long capped;
+    // Longest-first claim order (flag bit 23): the cull writes survivors whose swept hulls overlap
+    // (likely real contacts = deep trees) from the front of the survivor list and the others
+    // from its back, so that round 0 claims the long trees first.  n_items[0] stays the total.
+    alignas(128) unsigned long long n_front; // survivors written at [0, n_front)
+    alignas(128) unsigned long long n_back;  // survivors written at [n - n_back, n)
 };
 
 // ---- kernel launchers (defined in the .cu files) -----------------------------------
@@ -267,7 +290,9 @@ struct LaunchCounter {
 void launch_mesh_boxes(
     const double* V0, const double* V1, int nV, double radius_up, bool f32, VertexRec* vtab,
     double* vbox /* 6*nV: min xyz, max xyz */, const int32_t* E, int nE, const int32_t* F,
-    int nF, BoxArrays e_unsorted, BoxArrays vf_unsorted, cudaStream_t s, LaunchCounter& lc);
+    int nF, BoxArrays e_unsorted, BoxArrays vf_unsorted, int axis_e, int axis_vf,
+    int* bad /* device flag: set when an E / F entry is not a vertex index */, cudaStream_t s,
+    LaunchCounter& lc);
 
 // the reference's box builders by name, on caller-made AoS arrays (aabb.cuh:150-188)
 void launch_vertex_aabbs(
@@ -342,12 +367,16 @@ void launch_find_chunk_end(
     const unsigned long long* offsets, int lo, int hi, unsigned long long budget,
     int* d_out, cudaStream_t s, LaunchCounter& lc);
 
+// once per context (sccd_create): opts the solver kernels in to their dynamic shared memory on
+// the current device (cudaFuncSetAttribute is per device and idempotent)
+void narrow_init_device();
+
 struct NarrowInput {
     // mesh mode
     const VertexRec* vtab = nullptr;
     const int32_t* E = nullptr;
     const int32_t* F = nullptr;
-    int nE = 0, nF = 0;
+    int nV = 0, nE = 0, nF = 0;
     const sccd_pair* pairs = nullptr;
     // direct mode (n x 24 doubles)
     const double* queries = nullptr;

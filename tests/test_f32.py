@@ -320,24 +320,24 @@ def test_gpu_float_pipeline_matches_reference_cuda_float_build(ctx32, orc, scene
 @pytest.mark.gpu
 @pytest.mark.parametrize("kw", [dict(ms=0.0, tol=1e-6), dict(ms=1e-4, tol=1e-6),
                                 dict(ms=0.0, tol=1e-3), dict(ms=1e-6, tol=1e-5)])
-def test_gpu_float_cull_changes_no_result(ctx32, orc, torch_cuda, scene_c1, kw):
+def test_gpu_float_cull_changes_no_result(ctx32, sccd, orc, torch_cuda, scene_c1, kw):
     """The float variant of the separating-axis cull: every per-query TOI equals the float
     solver's own (cull off), also with a minimum separation or a tolerance far larger than the
     gaps it tests against."""
     s = scene_c1
     ctx32.upload_mesh(s["V0"], s["V1"], s["E"], s["F"])
     ctx32.build_boxes(kw["ms"])
-    saved = os.environ.get("SCCD_NP_CULL")
+    OPT = sccd.capi.OPT_NARROW_CULL
     try:
         for kind in (0, 1):
             pairs = ctx32.broad_phase(kind)
             q = orc.gather_queries(s, np.ascontiguousarray(pairs), kind == 0)
-            os.environ.pop("SCCD_NP_CULL", None)
+            ctx32.set_option(OPT, 1)
             ctx32.reset_stats()
             toi1, tpq1 = _narrow_gpu(ctx32, torch_cuda, kind, q, max_iter=-1,
                                      allow_zero_toi=True, **kw)
             culled = ctx32.stats()["n_culled"][kind]
-            os.environ["SCCD_NP_CULL"] = "0"
+            ctx32.set_option(OPT, 0)
             ctx32.reset_stats()
             toi0, tpq0 = _narrow_gpu(ctx32, torch_cuda, kind, q, max_iter=-1,
                                      allow_zero_toi=True, **kw)
@@ -346,17 +346,14 @@ def test_gpu_float_cull_changes_no_result(ctx32, orc, torch_cuda, scene_c1, kw):
             if kw["ms"] == 0.0 and kw["tol"] == 1e-6:
                 assert culled > 0.8 * len(q)
     finally:
-        if saved is None:
-            os.environ.pop("SCCD_NP_CULL", None)
-        else:
-            os.environ["SCCD_NP_CULL"] = saved
+        ctx32.set_option(OPT, 1)
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("flags", [1 << 24, 4 | (3 << 8) | (2 << 16) | (1 << 25), 1 << 28])
 def test_gpu_float_scheduling_variants_change_no_result(ctx32, orc, sccd, torch_cuda, scene_c1,
                                                          flags):
-    """Lane-per-tree only / tiny budgets / small cooperative limit (SCCD_NP_FLAGS, see
+    """Lane-per-tree only / tiny budgets / small cooperative limit (SCCD_OPT_NARROW_FLAGS, see
     tests/test_gpu_parity.py VARIANTS): the float kernels return the same per-query TOIs
     however the trees are cut and whichever of the two kernels walks them."""
     s = scene_c1
@@ -364,7 +361,7 @@ def test_gpu_float_scheduling_variants_change_no_result(ctx32, orc, sccd, torch_
     ctx32.build_boxes(0.0)
     ee_q, vf_q = sccd.scenes.queries_c5(1500, seed=4)
     sel = orc.tractable(vf_q, True, 0.0, 1e-6, f32=True)
-    saved = os.environ.get("SCCD_NP_FLAGS")
+    OPT = sccd.capi.OPT_NARROW_FLAGS
     try:
         for kind in (0, 1):
             pairs = ctx32.broad_phase(kind)
@@ -372,16 +369,13 @@ def test_gpu_float_scheduling_variants_change_no_result(ctx32, orc, sccd, torch_
             if kind == 0:
                 qs.append(vf_q[sel])
             for q in qs:
-                os.environ.pop("SCCD_NP_FLAGS", None)
+                ctx32.set_option(OPT, 0)
                 toi1, tpq1 = _narrow_gpu(ctx32, torch_cuda, kind, q)
-                os.environ["SCCD_NP_FLAGS"] = str(flags)
+                ctx32.set_option(OPT, flags)
                 toi2, tpq2 = _narrow_gpu(ctx32, torch_cuda, kind, q)
                 assert np.array_equal(tpq1, tpq2) and toi1 == toi2
     finally:
-        if saved is None:
-            os.environ.pop("SCCD_NP_FLAGS", None)
-        else:
-            os.environ["SCCD_NP_FLAGS"] = saved
+        ctx32.set_option(OPT, 0)
 
 
 @pytest.mark.gpu

@@ -165,27 +165,21 @@ def test_iteration_cap_is_conservative(ctx, orc, sccd, torch_cuda):
 
 
 @pytest.fixture
-def np_env():
-    """Sets / restores the narrow-phase debug knobs (read by the library at every batch)."""
-    saved = {k: os.environ.get(k) for k in ("SCCD_NP_FLAGS", "SCCD_NP_DEPTH", "SCCD_NP_CULL")}
+def np_env(ctx, sccd):
+    """Sets / restores the narrow-phase knobs of the shared context (sccd_set_option)."""
+    K = sccd.capi
 
     def set_(flags=None, depth=None, cull=None):
-        for k, v in (("SCCD_NP_FLAGS", flags), ("SCCD_NP_DEPTH", depth), ("SCCD_NP_CULL", cull)):
-            if v is None:
-                os.environ.pop(k, None)
-            else:
-                os.environ[k] = str(v)
+        ctx.set_option(K.OPT_NARROW_FLAGS, 0 if flags is None else flags)
+        ctx.set_option(K.OPT_NARROW_MAX_DEPTH, 128 if depth is None else depth)
+        ctx.set_option(K.OPT_NARROW_CULL, 1 if cull is None else cull)
     yield set_
-    for k, v in saved.items():
-        if v is None:
-            os.environ.pop(k, None)
-        else:
-            os.environ[k] = v
+    set_()
 
 
 # refill | first-round budget << 8 | later budget << 16 | never-cooperate << 24 |
 # log2(coop budget) - 3 << 25 | log2(coop limit) - 13 << 28
-VARIANTS = {"lane_only": 1 << 24, "tiny_budgets": 4 | (3 << 8) | (2 << 16) | (1 << 25),
+VARIANTS = {"deep_first": 1 << 23, "lane_only": 1 << 24, "tiny_budgets": 4 | (3 << 8) | (2 << 16) | (1 << 25),
             "refill_every_lane": 1, "refill_all_idle": 32, "coop_big_budget": 5 << 25,
             "coop_small_limit": 1 << 28}
 
@@ -526,3 +520,90 @@ def test_update_vertices_equals_a_fresh_upload(ctx, sccd, orc, scene_small):
     assert e.value.code == sccd.capi.ERR_STATE
     fresh.close()
     ctx.upload_mesh(s["V0"], s["V1"], s["E"], s["F"])               # leave host-owned buffers behind
+
+
+@pytest.mark.parametrize("axis", [1, 2, -1])
+def test_pipeline_sweep_axis_changes_no_result(sccd, orc, scene_c1, axis):
+    """SCCD_OPT_SWEEP_AXIS (sort_and_sweep.cpp:176-195): boxes, overlap sets and
+    every TOI are those of the x sweep."""
+    s = scene_c1
+    want = orc.ccd(s)
+    c = sccd.Context(0)
+    try:
+        c.upload_mesh(s["V0"], s["V1"], s["E"], s["F"])
+        c.set_option(sccd.capi.OPT_SWEEP_AXIS, axis)
+        assert c.get_option(sccd.capi.OPT_SWEEP_AXIS) == axis
+        for _ in range(2):       # -1: the second call sweeps along the axis the first handed back
+            assert c.ccd() == want["toi"]
+            assert c.stats()["n_pairs"] == [len(want["vf"]), len(want["ee"])]
+        vb, eb, fb = orc.build_boxes(s, 0.0)
+        for got, exp in zip(c.get_boxes(), (vb, eb, fb)):
+            assert got.tobytes() == exp.tobytes()
+        assert np.array_equal(orc.canonical(c.broad_phase(0)), want["vf"])
+        assert np.array_equal(orc.canonical(c.broad_phase(1)), want["ee"])
+        if axis == -1:
+            # the cloth lies in the xy plane: the variance argmax is x or y, never z
+            c.build_boxes(0.0)
+            assert c.broad_phase(1, want_pairs=False) == len(want["ee"])
+    finally:
+        c.close()
+
+
+def test_bad_indices_are_errors_not_faults(sccd, scene_small, torch_cuda):
+    """Out-of-range E / F entries and pair ids are SCCD_ERR_ARG (the reference would read out of
+    bounds, aabb.cu:199-226 / narrow_phase.cu:38-60); the context stays usable."""
+    s = scene_small
+    c = sccd.Context(0)
+    try:
+        E = s["E"].copy(order="F")
+        E[5, 1] = s["V0"].shape[0] + 7
+        c.upload_mesh(s["V0"], s["V1"], E, s["F"])
+        with pytest.raises(sccd.SccdError) as e:
+            c.build_boxes(0.0)
+        assert e.value.code == sccd.capi.ERR_ARG
+        F = s["F"].copy(order="F")
+        F[0, 2] = -1
+        c.upload_mesh(s["V0"], s["V1"], s["E"], F)
+        with pytest.raises(sccd.SccdError) as e:
+            c.ccd()
+        assert e.value.code == sccd.capi.ERR_ARG
+        c.upload_mesh(s["V0"], s["V1"], s["E"], s["F"])
+        good = c.ccd()
+        pairs = torch_cuda.tensor([[0, 1], [3, s["F"].shape[0]]], dtype=torch_cuda.int32, device="cuda")
+        with pytest.raises(sccd.SccdError) as e:
+            c.narrow_phase(0, pairs.data_ptr(), 2)
+        assert e.value.code == sccd.capi.ERR_ARG
+        assert c.ccd() == good
+    finally:
+        c.close()
+
+
+def test_max_iter_mode_drop_is_the_reference_rule(sccd, orc, torch_cuda):
+    """SCCD_OPT_MAX_ITER_MODE: 0 accepts the boxes of a query that reached max_iter at their t_lo
+    (never later than the exact answer); 1 drops them like the reference (root_finder.cu:303-305)
+    -- never earlier than the exact answer, may miss; queries under the cap are exact in both."""
+    ee, vf = sccd.scenes.queries_c5(4000, seed=12)
+    c = sccd.Context(0)
+    try:
+        for kind, q in ((0, vf), (1, ee)):
+            m = orc.tractable(q, kind == 0, 0.0, 1e-6)
+            q = np.ascontiguousarray(q[m])
+            _, full, _ = orc.narrow_phase(q, kind == 0)
+            out = {}
+            for mode in (0, 1):
+                c.set_option(sccd.capi.OPT_MAX_ITER_MODE, mode)
+                c.reset_stats()
+                _, tpq = _narrow_gpu(c, torch_cuda, kind, q, max_iter=40)
+                ptr, n = c.narrow_phase_checks()
+                checks = torch_cuda.as_tensor(
+                    sccd.multigpu._DevArray(ptr, (n,), "<u4"), device="cuda").cpu().numpy()
+                out[mode] = (tpq, checks <= 41, c.stats()["n_capped"][kind])
+            c.set_option(sccd.capi.OPT_MAX_ITER_MODE, 0)
+            for mode in (0, 1):
+                tpq, under, n_capped = out[mode]
+                assert n_capped > 0 and (~under).sum() >= n_capped
+                assert np.array_equal(tpq[under], full[under])
+            assert np.all(out[0][0] <= full) and np.all(out[1][0] >= full)
+            assert np.any(out[1][0] > full)          # the reference's rule does miss collisions
+    finally:
+        c.close()

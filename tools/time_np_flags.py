@@ -21,16 +21,13 @@ sccd = load_package()
 name = sys.argv[1] if len(sys.argv) > 1 else "c2"
 flag_values = [int(v, 0) for v in sys.argv[2:]] or [0]
 gen = {"small": lambda: sccd.scenes.cloth_on_sphere(31, seed=7, sphere="uv"),
-       "c1": sccd.scenes.scene_c1, "c2": sccd.scenes.scene_c2}[name]
+       "c1": sccd.scenes.scene_c1, "c2": sccd.scenes.scene_c2, "c3": sccd.scenes.scene_c3}[name]
 s = gen()
 ctx = sccd.Context(0)
 ctx.upload_mesh(s["V0"], s["V1"], s["E"], s["F"])
 out = {"workload": name}
 for fv in flag_values:
-    if fv:
-        os.environ["SCCD_NP_FLAGS"] = str(fv)
-    else:
-        os.environ.pop("SCCD_NP_FLAGS", None)
+    ctx.set_option(sccd.capi.OPT_NARROW_FLAGS, fv)
     for _ in range(2):
         toi = ctx.ccd()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
