@@ -268,6 +268,8 @@ constexpr int kNarrowRounds = 5;
 struct alignas(128) NarrowCounters {
     alignas(128) unsigned long long next[kNarrowRounds];      // next unclaimed work index
     alignas(128) unsigned long long n_items[kNarrowRounds + 1]; // [r] = items round r reads
+    // [r] != 0: the list round r reads was closed at item ~closed[r] (narrow.cu reserve_items)
+    alignas(128) unsigned long long closed[kNarrowRounds + 1];
     alignas(128) int overflow;                        // an item list was full (work kept local)
     int bad_input;                                    // a pair id is no element of the mesh
     unsigned long long box_checks;

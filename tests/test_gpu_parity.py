@@ -603,7 +603,8 @@ def test_max_iter_mode_drop_is_the_reference_rule(sccd, orc, torch_cuda):
                 tpq, under, n_capped = out[mode]
                 assert n_capped > 0 and (~under).sum() >= n_capped
                 assert np.array_equal(tpq[under], full[under])
+            # (depth-first, earliest-t-first order usually reaches the earliest root before the
+            # cap, so dropping the rest rarely loses it -- but it can; accepting never does)
             assert np.all(out[0][0] <= full) and np.all(out[1][0] >= full)
-            assert np.any(out[1][0] > full)          # the reference's rule does miss collisions
     finally:
         c.close()
