@@ -92,7 +92,25 @@ typedef struct {
     int64_t n_records[2];    /* sweep records = boxes replicated into the (y,z) cells   */
     int32_t grid_cells[2][2]; /* (sy, sz) cell grid chosen for each list                */
     int64_t n_culled[2];     /* queries answered "no collision" by the separating-axis cull */
+    /* narrow-phase load balance: items the solver rounds read (round 0 = queries that survived
+     * the cull; [5] = handed on by the last round) and the box checks of each round */
+    int64_t n_round_items[2][6];
+    int64_t n_round_checks[2][5];
+    int32_t sweep_axis[2];   /* axis each list was swept along (SCCD_OPT_SWEEP_AXIS)            */
+    int32_t next_axis[2];    /* variance argmax sort_and_sweep would hand back                  */
+    int64_t n_host_syncs;    /* host <-> device synchronisations inside the call                */
+    /* multi-GPU (sccd_ccd_sharded): records this rank sent to / received from the others   */
+    int64_t n_records_sent[2];
+    int64_t n_records_received[2];
+    float ms_exchange;       /* record exchange (NCCL send / recv), device time                 */
+    float ms_k_sort[2];      /* radix sort passes of each list                                  */
+    float ms_k_expand[2];    /* record expansion (count + scan + fill) of each list             */
+    float ms_k_cull[2];      /* separating-axis cull kernel                                     */
+    float ms_k_round[2][5];  /* solver rounds (SCCD_OPT_PROFILE only)                           */
+    float pad2_;
 } sccd_stats;
+/* sizeof(sccd_stats) of the library (binding sanity check) */
+size_t sccd_stats_size(void);
 
 /* ---- context ------------------------------------------------------------------ */
 
@@ -149,6 +167,8 @@ int sccd_set_scalar_type(sccd_ctx* ctx, int type);
 #define SCCD_OPT_KEY_STEPS 6        /* log2 of the major-axis quantisation steps per record     */
 #define SCCD_OPT_GRID_SCALE_MILLI 7 /* cell edge in mean box extents, x 1000 (default 3000)     */
 #define SCCD_OPT_GRID_REPL_MILLI 8  /* records per box above which the grid is coarsened, x1000 */
+#define SCCD_OPT_PROFILE 10         /* 1: time every solver round with its own event pair
+                                       (sccd_stats.ms_k_round); 0 (default): stage timers only */
 #define SCCD_OPT_SWEEP_AXIS 9       /* axis the mesh pipeline sorts and sweeps along: 0 (default,
                                        the reference's GPU path, aabb.cu:86), 1, 2, or -1 = the
                                        axis sort_and_sweep would hand back for the NEXT call --
@@ -166,6 +186,44 @@ int sccd_get_option(const sccd_ctx* ctx, int option, int64_t* value);
  * the whole sorted list, balanced by sweep-window length.  Takes effect at the next
  * sccd_build_boxes / sccd_set_boxes / sccd_broad_phase_begin.  rank 0 / world 1 = everything. */
 int sccd_set_shard(sccd_ctx* ctx, int rank, int world);
+
+/* ---- multi-GPU: one context (process or thread) per GPU ------------------------------ */
+/* The reference is single-GPU (its _multigpu directory is dead code that replicates every box
+ * and merges on the host, cuda/broad_phase/_multigpu/broad_phase.cu:69-116).  Here the ranks of
+ * a communicator split one ccd() call:
+ *   1. every rank makes the boxes of 1 / world of the elements and one 8-byte (key, index)
+ *      record per (box, cell);
+ *   2. records are exchanged by OWNING CELL RANGE (contiguous ranges of the (y, z) cell grid,
+ *      balanced by record count; NCCL send / recv over NVLink) -- cells are independent sweep
+ *      domains, so there is no halo;
+ *   3. the receiver sorts its records and rebuilds their exact boxes from the mesh (replicated,
+ *      48 B / vertex), sweeps them, and solves the pairs it found;
+ *   4. one all-reduce(min) of the earliest TOI.
+ * The pair lists of the ranks are disjoint and their union is the single-GPU overlap set; the
+ * TOI is the single-GPU TOI.
+ *
+ * NCCL (libnccl.so.2) is loaded at run time by sccd_comm_create, so single-GPU users need none.
+ * The caller distributes the 128-byte id of rank 0 by its own means (MPI_Bcast, a file, a
+ * torch.distributed broadcast ...).  world == 1 needs no NCCL and no id (id may be NULL). */
+#define SCCD_UNIQUE_ID_BYTES 128
+int sccd_comm_get_unique_id(void* id_out /* SCCD_UNIQUE_ID_BYTES */);
+int sccd_comm_create(sccd_ctx* ctx, const void* id, int rank, int world);
+int sccd_comm_destroy(sccd_ctx* ctx);
+
+/* ccd() over the communicator's GPUs: collective -- every rank calls it with the same
+ * arguments after uploading the SAME mesh (sccd_upload_mesh / sccd_update_vertices); every rank
+ * receives the same *toi.  sccd_get_stats afterwards reports this rank's share. */
+int sccd_ccd_sharded(
+    sccd_ctx* ctx, double min_distance, int max_iter, double tol, int allow_zero_toi,
+    double* toi);
+
+/* The same from HOST buffers: every rank holds the whole mesh on its host (the arguments are
+ * host pointers, identical content on every rank), copies only 1 / world of it over its own
+ * PCIe link, and the slices are all-gathered over NVLink. */
+int sccd_ccd_sharded_host(
+    sccd_ctx* ctx, const double* V0, const double* V1, int64_t nV, const int32_t* E, int64_t nE,
+    const int32_t* F, int64_t nF, double min_distance, int max_iter, double tol,
+    int allow_zero_toi, double* toi);
 
 /* ---- mesh + boxes --------------------------------------------------------------- */
 

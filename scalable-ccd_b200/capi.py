@@ -18,7 +18,8 @@ VF, EE, BOXES = 0, 1, 2
 F64, F32 = 0, 1  # sccd_set_scalar_type: the reference's SCALABLE_CCD_USE_DOUBLE switch
 OK, ERR_CUDA, ERR_ARG, ERR_STATE, ERR_MEMORY = 0, -1, -2, -3, -4
 (OPT_NARROW_CULL, OPT_NARROW_FLAGS, OPT_NARROW_FLAGS_EE, OPT_NARROW_MAX_DEPTH, OPT_MAX_ITER_MODE,
- OPT_KEY_STEPS, OPT_GRID_SCALE_MILLI, OPT_GRID_REPL_MILLI, OPT_SWEEP_AXIS) = range(1, 10)
+ OPT_KEY_STEPS, OPT_GRID_SCALE_MILLI, OPT_GRID_REPL_MILLI, OPT_SWEEP_AXIS, OPT_PROFILE) = range(1, 11)
+UNIQUE_ID_BYTES = 128
 
 AABB_DTYPE = np.dtype(
     [("min", np.float64, 3), ("max", np.float64, 3), ("vids", np.int32, 3), ("elem", np.int32)])
@@ -34,6 +35,8 @@ SYMBOLS = [
     "sccd_broad_phase_partial", "sccd_broad_phase_is_complete", "sccd_broad_phase",
     "sccd_narrow_phase", "sccd_narrow_phase_queries", "sccd_ccd", "sccd_ccd_collisions",
     "sccd_get_collisions", "sccd_set_option", "sccd_get_option", "sccd_narrow_phase_checks",
+    "sccd_stats_size", "sccd_comm_get_unique_id", "sccd_comm_create", "sccd_comm_destroy",
+    "sccd_ccd_sharded", "sccd_ccd_sharded_host",
     "sccd_ccd_host", "sccd_ipc_ccd_strategy", "sccd_get_stats", "sccd_reset_stats",
     "sccd_synchronize", "sccd_measure_fp64_peak",
     "sccd_version",
@@ -51,6 +54,11 @@ class Stats(C.Structure):
         ("ms_k_narrow", C.c_float * 2), ("ms_k_boxes", C.c_float), ("ms_k_gather", C.c_float),
         ("pad_", C.c_float), ("n_records", C.c_int64 * 2), ("grid_cells", (C.c_int32 * 2) * 2),
         ("n_culled", C.c_int64 * 2),
+        ("n_round_items", (C.c_int64 * 6) * 2), ("n_round_checks", (C.c_int64 * 5) * 2),
+        ("sweep_axis", C.c_int32 * 2), ("next_axis", C.c_int32 * 2), ("n_host_syncs", C.c_int64),
+        ("n_records_sent", C.c_int64 * 2), ("n_records_received", C.c_int64 * 2),
+        ("ms_exchange", C.c_float), ("ms_k_sort", C.c_float * 2), ("ms_k_expand", C.c_float * 2),
+        ("ms_k_cull", C.c_float * 2), ("ms_k_round", (C.c_float * 5) * 2), ("pad2_", C.c_float),
     ]
 
     def as_dict(self):
@@ -84,6 +92,9 @@ def load():
         L.sccd_last_error.restype = C.c_char_p
         L.sccd_version.restype = C.c_char_p
         L.sccd_destroy.restype = None
+        L.sccd_stats_size.restype = C.c_size_t
+        if L.sccd_stats_size() != C.sizeof(Stats):
+            raise RuntimeError("capi.Stats does not match sccd_stats of the library")
         _lib = L
     return _lib
 
@@ -154,6 +165,42 @@ class Context:
     def set_scalar_type(self, scalar: int):
         """F64 (default) or F32 = the reference built with SCALABLE_CCD_USE_DOUBLE=OFF."""
         self._chk(self.L.sccd_set_scalar_type(self._h, C.c_int(scalar)))
+
+    # ---- multi-GPU (one Context per rank; the caller distributes rank 0's id)
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(UNIQUE_ID_BYTES)
+        rc = load().sccd_comm_get_unique_id(buf)
+        if rc != OK:
+            raise SccdError(rc, "sccd_comm_get_unique_id failed (NCCL not loadable?)")
+        return buf.raw
+
+    def comm_create(self, unique_id, rank: int, world: int):
+        buf = C.create_string_buffer(bytes(unique_id), UNIQUE_ID_BYTES) if unique_id else None
+        self._chk(self.L.sccd_comm_create(self._h, buf, C.c_int(rank), C.c_int(world)))
+
+    def comm_destroy(self):
+        self._chk(self.L.sccd_comm_destroy(self._h))
+
+    def ccd_sharded(self, ms=0.0, max_iter=-1, tol=1e-6, allow_zero_toi=True) -> float:
+        """Collective ccd() over the communicator's ranks (mesh uploaded on every rank)."""
+        t = C.c_double(1.0)
+        self._chk(self.L.sccd_ccd_sharded(
+            self._h, C.c_double(ms), C.c_int(max_iter), C.c_double(tol),
+            C.c_int(int(allow_zero_toi)), C.byref(t)))
+        return t.value
+
+    def ccd_sharded_host(self, V0, V1, E, F, ms=0.0, max_iter=-1, tol=1e-6, allow_zero_toi=True,
+                         sizes=None) -> float:
+        """The same from HOST buffers: this rank copies 1 / world of the mesh, NCCL all-gather."""
+        nV, nE, nF = sizes if sizes is not None else (V0.shape[0], E.shape[0], F.shape[0])
+        t = C.c_double(1.0)
+        self._chk(self.L.sccd_ccd_sharded_host(
+            self._h, _ptr(V0), _ptr(V1), C.c_int64(nV), _ptr(E), C.c_int64(nE), _ptr(F),
+            C.c_int64(nF), C.c_double(ms), C.c_int(max_iter), C.c_double(tol),
+            C.c_int(int(allow_zero_toi)), C.byref(t)))
+        self.nV, self.nE, self.nF = nV, nE, nF
+        return t.value
 
     # ---- the reference's box builders by name, host arrays in and out
     def build_vertex_boxes(self, V0, V1=None, inflation_radius: float = 0.0):

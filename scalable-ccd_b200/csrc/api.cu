@@ -49,198 +49,13 @@ __global__ void find_splits_kernel(
 
 using namespace sccd;
 
-struct sccd_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    int num_sms = 148;
-    std::string error;
+#include "context.cuh"
 
-    size_t memory_limit = 0;
-    size_t mem_free = 0, mem_total = 0;   // last cudaMemGetInfo() answer ...
-    unsigned long long mem_epoch = 0;     // ... and the allocation epoch (+1) it was taken at
-    int64_t max_pairs_per_chunk = 0;
-    int64_t queue_cap = 0;
-    int rank = 0, world = 1;
-    // SCCD_F32: the reference's float build (scalar.hpp:16-18) -- inputs rounded to float, boxes
-    // by nextafterf, narrow phase in float arithmetic; every buffer stays double (float values
-    // are exact in double and compare the same)
-    bool f32 = false;
+namespace sccd {
+namespace host {
 
-    // mesh
-    int nV = 0, nE = 0, nF = 0;
-    bool have_mesh = false, have_boxes = false;
-    const double *dV0 = nullptr, *dV1 = nullptr;
-    const int32_t *dE = nullptr, *dF = nullptr;
-    DevBuf bV0, bV1, bE, bF;
-    DevBuf b_vtab, b_vbox;
-    DevBuf b_io[3]; // staging of the stand-alone box builders (sccd_build_vertex/element_boxes)
 
-    // box lists: [0] = vertex+face (two lists), [1] = edges
-    struct ListBufs {
-        DevBuf ux, uyz, uid;     // unsorted exact records (one per box)
-        DevBuf copies, offs;     // cells touched per box, and their exclusive scan
-        DevBuf keys, keys_tmp, idx, idx_out; // (key, box index) records, one per (box, cell)
-        DevBuf sx, syz, sid;     // sorted exact records
-        DevBuf pkey, preach, pyz; // sorted prefilter view
-        DevBuf sort_temp;         // radix sort scratch
-        SortedList sorted;
-        BoxArrays unsorted;
-        int n_boxes = 0;
-        int axis = 0;      // axis the records of this list are rotated to / swept along
-        int next_axis = 0; // variance argmax of the last build (sort_and_sweep.cpp:176-195)
-        int built_rank = 0, built_world = 1; // sharding the sorted records were made for
-        // sort_list_begin -> sort_list_finish hand-over
-        GridParams g_try;
-        bool try_sharded = false;
-        int try_stride = 1, attempt = 0;
-    } lists[3]; // [2] = caller-made boxes (sccd_set_boxes)
-    bool have_custom = false;
-    DevBuf b_scan_temp, b_stats, b_hist, b_splits;
-    // The edge list is sorted on a second stream, under the vertex-face sweep and narrow phase:
-    // the sort of a 1 M-box list is a dozen latency-bound launches that leave the GPU mostly
-    // idle.  ev_counts: both lists counted (main stream); ev_sorted1: edge list sorted.
-    cudaStream_t sort_stream = nullptr;
-    cudaEvent_t ev_counts = nullptr, ev_sorted1 = nullptr, ev_vf_done = nullptr;
-    bool sort1_pending = false;
-    // pinned: per list, box statistics + record count + multi-GPU cell splits
-    struct ListHost {
-        double stats[kNumStats];
-        unsigned long long m;
-        unsigned long long splits[2 * 16 + 2];
-    };
-    ListHost* h_lists = nullptr; // [3]
-    DevBuf b_flags;            // [0]: an E / F entry is not a vertex index (box kernels)
-    int* h_flags = nullptr;    // pinned copy
-    int grid_max_cells = -1;   // < 0: choose automatically; 1 forces the plain 1-axis sweep
-    // tuning knobs (env SCCD_GRID_SCALE / SCCD_GRID_REPL): cell edge in mean box extents, and
-    // the replication (records per box) above which the grid is coarsened
-    double grid_scale = 3.0, grid_repl = 2.5;
-    // sccd_set_option (initial values from the SCCD_* environment variables, read ONCE in
-    // sccd_create; nothing on the hot path calls getenv)
-    struct Options {
-        int np_cull = 1;        // separating-axis cull in front of the solver
-        int np_flags = 0;       // narrow-phase scheduling knobs (narrow.cu)
-        int np_flags_ee = -1;   // the same for the edge-edge pass alone (< 0: follow np_flags)
-        int np_depth = 128;     // levels a walk tracks before handing on
-        int cap_drops = 0;      // max_iter reached: 0 accept at t_lo, 1 drop (reference)
-        int key_steps = 3;      // log2 of the x quantisation steps per record of a cell
-        int sweep_axis = 0;     // 0/1/2, or -1: variance argmax of the previous build
-    } opt;
-    int next_axis = 0;          // argmax of the box-centre variance of the last build
 
-    // Run state (broad-phase cursor, pair / staging buffers, narrow-phase lists and counters)
-    // and the stream its work is enqueued on.  Broad and narrow phase are split in an enqueue
-    // and a finish half, so several runs on several streams can be in flight; the pipeline
-    // uses one (see run_pipeline).
-    struct Run {
-        cudaStream_t stream = nullptr;
-        int bp_kind = -1;
-        int shard_lo = 0, shard_hi = 0, bp_cursor = 0;
-        unsigned long long bp_total = 0, bp_emitted = 0;
-        DevBuf b_counts, b_offsets, b_scan, b_pairs, b_small;
-        DevBuf b_stage_pairs, b_stage_tags, b_stage_count; // count pass -> place pass
-        int* h_small = nullptr; // pinned scratch for tiny D2H results
-        DevBuf b_counters, b_items[2], b_toi_q, b_checks_q, b_queries, b_surv;
-        NarrowCounters* h_counters = nullptr; // pinned
-        unsigned long long item_cap = 0; // capacity of each of the two hand-on lists
-        long long checks_n = 0;          // queries of the last batch that counted its checks
-        // narrow_enqueue -> narrow_finish hand-over
-        struct Pending {
-            bool active = false;
-            int kind = 0;
-            NarrowInput in;
-            NarrowParams P;
-            double* d_tq = nullptr;
-            unsigned int* checks = nullptr;
-            bool culling = false;
-        } pending;
-    } runs[2]; // [1]: the edge list's broad phase + narrow phase on the sort stream (pipeline)
-    Run* cur = &runs[0];
-    DevBuf b_gtoi; // earliest toi shared by the two lists of a pipeline call
-    double* h_gtoi = nullptr; // pinned
-
-    // collisions of the last sccd_ccd_collisions (fetched by sccd_get_collisions)
-    std::vector<sccd_pair> coll_ids;
-    std::vector<double> coll_toi;
-    int64_t coll_n[2] = { 0, 0 };
-
-    sccd_stats stats {};
-    LaunchCounter lc;
-    cudaEvent_t ev[20] {};
-    bool gather_timed = false;
-    // pooled event pairs timing single kernels; resolved into stats at the end of a call
-    struct KTimer {
-        cudaEvent_t a = nullptr, b = nullptr;
-        float* dst = nullptr;
-    };
-    std::vector<KTimer> ktimers;
-    size_t kt_used = 0;
-
-    ~sccd_ctx()
-    {
-        for (auto& r : runs) {
-            if (r.h_small)
-                cudaFreeHost(r.h_small);
-            if (r.h_counters)
-                cudaFreeHost(r.h_counters);
-        }
-        if (h_gtoi)
-            cudaFreeHost(h_gtoi);
-        if (sort_stream)
-            cudaStreamDestroy(sort_stream);
-        if (ev_counts)
-            cudaEventDestroy(ev_counts);
-        if (ev_sorted1)
-            cudaEventDestroy(ev_sorted1);
-        if (ev_vf_done)
-            cudaEventDestroy(ev_vf_done);
-        if (h_lists)
-            cudaFreeHost(h_lists);
-        if (h_flags)
-            cudaFreeHost(h_flags);
-        for (auto& e : ev)
-            if (e)
-                cudaEventDestroy(e);
-        for (auto& k : ktimers) {
-            cudaEventDestroy(k.a);
-            cudaEventDestroy(k.b);
-        }
-    }
-};
-
-namespace {
-
-enum { EV_T0, EV_BUILD, EV_SORT, EV_SW0A, EV_SW0B, EV_NP0A, EV_NP0B, EV_SW1A, EV_SW1B,
-       EV_NP1A, EV_NP1B, EV_T1, EV_TMPA, EV_TMPB, EV_GA0, EV_GB0, EV_GA1, EV_GB1, EV_COUNT };
-
-void use_device(sccd_ctx* c) { SCCD_CUDA(cudaSetDevice(c->device)); }
-
-template <typename F> int guarded(sccd_ctx* c, F&& f)
-{
-    if (!c)
-        return SCCD_ERR_ARG;
-    try {
-        use_device(c);
-        c->cur = &c->runs[0]; // step-wise entry points always work on the context's own stream
-        return f();
-    } catch (const CudaError& e) {
-        c->error = e.what();
-        (void)cudaGetLastError();
-        return SCCD_ERR_CUDA;
-    } catch (const std::invalid_argument& e) {
-        c->error = e.what();
-        return SCCD_ERR_ARG;
-    } catch (const std::logic_error& e) {
-        c->error = e.what();
-        return SCCD_ERR_STATE;
-    } catch (const std::bad_alloc&) {
-        c->error = "out of host memory";
-        return SCCD_ERR_MEMORY;
-    } catch (const std::exception& e) {
-        c->error = e.what();
-        return SCCD_ERR_MEMORY;
-    }
-}
 
 void record(sccd_ctx* c, int which) { SCCD_CUDA(cudaEventRecord(c->ev[which], c->stream)); }
 float elapsed(sccd_ctx* c, int a, int b)
@@ -434,6 +249,32 @@ void regrid(GridParams& g, const double st[kNumStats])
     g.inv_hz = g.sz > 1 ? g.sz / (st[3] - st[2]) : 0.0;
 }
 
+// 32-bit key = [cell | q(x) | 3 flag bits] (common.cuh).  x gets as many bits as the digit
+// passes needed for ~8 quantisation steps per record of an average cell leave room for
+// (measured on config 2: 8 steps save a digit pass per list over 32 and add 0.01 % ties).
+// m_total: records of the whole list (all ranks); st: its box statistics.
+void key_layout(
+    GridParams& g, unsigned long long m_total, const double* st, int key_steps, int& cell_bits)
+{
+    cell_bits = 0;
+    while ((1ll << cell_bits) < (long long)g.sy * g.sz)
+        cell_bits++;
+    const int x_max = 32 - kKeyFlagBits - cell_bits;
+    const double per_cell = (double)m_total / (double)((long long)g.sy * g.sz);
+    const int steps = key_steps; // log2 of the quantisation steps per record
+    int want = steps;
+    while (want < x_max && (double)(1ll << (want - steps)) < per_cell)
+        want++;
+    want = std::min(std::max(want, 9), x_max);
+    const int passes = (cell_bits + want + 7) / 8;
+    g.x_bits = std::min(x_max, passes * 8 - cell_bits);
+    const double ext = st[7] - st[6];
+    g.x0 = st[6];
+    g.inv_hx = (ext > 0 && std::isfinite(ext)) ? std::ldexp(1.0, g.x_bits) / ext : 0.0;
+    if (!std::isfinite(g.inv_hx))
+        g.inv_hx = 0.0;
+}
+
 // enqueue the record count of grid L.g_try (and, multi-GPU, this rank's cell range)
 void sort_list_count(sccd_ctx* c, int which)
 {
@@ -556,7 +397,7 @@ void sort_list_finish(
             regrid(L.g_try, H.stats);
         }
         sort_list_count(c, which);
-        SCCD_CUDA(cudaStreamSynchronize(c->stream));
+        host_sync(c, c->stream);
     }
     const bool sharded = L.try_sharded && (long long)g.sy * g.sz > 1;
     if (sharded) {
@@ -566,28 +407,8 @@ void sort_list_finish(
     L.sorted.cell_sharded = sharded;
     if (m >= (1ull << 27))
         throw std::invalid_argument("more than 2^27 sweep records in one list");
-    // 32-bit key = [cell | q(x) | 3 flag bits] (common.cuh).  x gets as many bits as the digit
-    // passes needed for ~8 quantisation steps per record of an average cell leave room for
-    // (measured on config 2: 8 steps save a digit pass per list over 32 and add 0.01 % ties).
     int cell_bits = 0;
-    while ((1ll << cell_bits) < (long long)g.sy * g.sz)
-        cell_bits++;
-    {
-        const int x_max = 32 - kKeyFlagBits - cell_bits;
-        const double per_cell = (double)m_total / (double)((long long)g.sy * g.sz);
-        const int steps = c->opt.key_steps; // log2 of the quantisation steps per record
-        int want = steps;
-        while (want < x_max && (double)(1ll << (want - steps)) < per_cell)
-            want++;
-        want = std::min(std::max(want, 9), x_max);
-        const int passes = (cell_bits + want + 7) / 8;
-        g.x_bits = std::min(x_max, passes * 8 - cell_bits);
-        const double ext = H.stats[7] - H.stats[6];
-        g.x0 = H.stats[6];
-        g.inv_hx = (ext > 0 && std::isfinite(ext)) ? std::ldexp(1.0, g.x_bits) / ext : 0.0;
-        if (!std::isfinite(g.inv_hx))
-            g.inv_hx = 0.0;
-    }
+    key_layout(g, m_total, H.stats, c->opt.key_steps, cell_bits);
     const size_t mm = (size_t)m;
     L.keys.reserve(mm * 4);
     L.keys_tmp.reserve(mm * 4);
@@ -619,9 +440,9 @@ void sort_list_finish(
 void sort_list(sccd_ctx* c, int which, cudaEvent_t ga, cudaEvent_t gb)
 {
     list_stats(c, which);
-    SCCD_CUDA(cudaStreamSynchronize(c->stream));
+    host_sync(c, c->stream);
     sort_list_begin(c, which);
-    SCCD_CUDA(cudaStreamSynchronize(c->stream));
+    host_sync(c, c->stream);
     sort_list_finish(c, which, ga, gb);
 }
 
@@ -639,6 +460,7 @@ void build_boxes(sccd_ctx* c, double inflation_radius)
     if (!c->have_mesh)
         throw std::logic_error("build_boxes: no mesh uploaded");
     join_sort_stream(c, c->stream); // a previous build whose edge list nobody swept
+    c->sliced = false;
     const int nV = c->nV, nE = c->nE, nF = c->nF;
     const long long nVF = (long long)nV + nF;
     if (nVF >= (1ll << 27) || nE >= (1 << 27))
@@ -672,7 +494,7 @@ void build_boxes(sccd_ctx* c, double inflation_radius)
     list_stats(c, 0);
     list_stats(c, 1);
     SCCD_CUDA(cudaMemcpyAsync(c->h_flags, d_bad, 4, cudaMemcpyDeviceToHost, c->stream));
-    SCCD_CUDA(cudaStreamSynchronize(c->stream));
+    host_sync(c, c->stream);
     if (c->h_flags[0]) // the reference would read out of bounds (aabb.cu:199-226)
         throw std::invalid_argument("build_boxes: an edge / face refers to a vertex that does not exist");
     for (int which = 0; which < 2; which++) {
@@ -695,7 +517,7 @@ void build_boxes(sccd_ctx* c, double inflation_radius)
     c->next_axis = LV.next_axis;
     sort_list_begin(c, 0);
     sort_list_begin(c, 1);
-    SCCD_CUDA(cudaStreamSynchronize(c->stream));
+    host_sync(c, c->stream);
     sort_list_finish(c, 0, c->ev[EV_GA0], c->ev[EV_GB0]);
     // (if the grid of list 1 has to be coarsened, its retry runs -- and syncs -- on the main
     // stream before anything is enqueued on the sort stream)
@@ -714,6 +536,10 @@ void build_boxes(sccd_ctx* c, double inflation_radius)
     c->stats.grid_cells[0][1] = LV.sorted.grid.sz;
     c->stats.grid_cells[1][0] = LE.sorted.grid.sy;
     c->stats.grid_cells[1][1] = LE.sorted.grid.sz;
+    for (int k = 0; k < 2; k++) {
+        c->stats.sweep_axis[k] = c->lists[k].axis;
+        c->stats.next_axis[k] = c->lists[k].next_axis;
+    }
 }
 
 // stats are kept per reference pass (VF, EE); caller-made box lists report in slot 0
@@ -770,7 +596,7 @@ void set_boxes(
         SCCD_CUDA(cudaMemcpyAsync(L.unsorted.id, hid.data(), sizeof(int4) * n, cudaMemcpyHostToDevice, c->stream));
     }
     sort_list(c, 2, nullptr, nullptr);
-    SCCD_CUDA(cudaStreamSynchronize(c->stream)); // host staging vectors go out of scope
+    host_sync(c, c->stream); // host staging vectors go out of scope
     c->have_custom = true;
     c->runs[0].bp_kind = c->runs[1].bp_kind = -1;
     c->stats.n_boxes[0] = n;
@@ -801,8 +627,11 @@ void broad_phase_begin_enqueue(sccd_ctx* c, int kind)
         throw std::logic_error("Must initialize build broad phase before detecting overlaps!");
     if (kind == SCCD_EE)
         join_sort_stream(c, st); // the edge list was sorted on the sort stream
-    if (c->lists[kind].built_rank != c->rank || c->lists[kind].built_world != c->world)
+    if (c->lists[kind].built_rank != c->rank || c->lists[kind].built_world != c->world) {
+        if (c->sliced && kind != SCCD_BOXES)
+            throw std::logic_error("broad_phase: the shard changed since the sliced build");
         sort_list(c, kind, nullptr, nullptr); // sccd_set_shard changed since the list was sorted
+    }
     const SortedList& L = c->lists[kind].sorted;
     const int sk = stat_slot(kind);
     small_scratch(c);
@@ -831,7 +660,7 @@ void broad_phase_begin_enqueue(sccd_ctx* c, int kind)
         c->lc.n++;
         SCCD_CUDA(cudaMemcpyAsync(
             R.h_small, R.b_small.ptr, sizeof(int) * (c->world + 1), cudaMemcpyDeviceToHost, st));
-        SCCD_CUDA(cudaStreamSynchronize(st));
+        host_sync(c, st);
         R.shard_lo = R.h_small[c->rank];
         R.shard_hi = R.h_small[c->rank + 1];
     }
@@ -870,7 +699,7 @@ void broad_phase_begin_finish(sccd_ctx* c)
     auto& R = *c->cur;
     if (R.shard_hi - R.shard_lo <= 0)
         return;
-    SCCD_CUDA(cudaStreamSynchronize(R.stream));
+    host_sync(c, R.stream);
     unsigned long long* h = reinterpret_cast<unsigned long long*>(R.h_small);
     R.bp_total = h[0];
     c->stats.n_candidates[stat_slot(R.bp_kind)] = (int64_t)h[1];
@@ -919,7 +748,7 @@ void broad_phase_partial(sccd_ctx* c, const sccd_pair** d_pairs, int64_t* n_pair
             R.b_offsets.as<unsigned long long>(), lo, hi, budget, R.b_small.as<int>(), st, c->lc);
         SCCD_CUDA(cudaMemcpyAsync(
             R.h_small, R.b_small.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
-        SCCD_CUDA(cudaStreamSynchronize(st));
+        host_sync(c, st);
         const int e = R.h_small[0];
         if (e <= lo) // memory_handler.cpp:65-69
             throw std::runtime_error(
@@ -931,7 +760,7 @@ void broad_phase_partial(sccd_ctx* c, const sccd_pair** d_pairs, int64_t* n_pair
             &h[0], R.b_offsets.as<unsigned long long>() + e, 8, cudaMemcpyDeviceToHost, st));
         SCCD_CUDA(cudaMemcpyAsync(
             &h[1], R.b_offsets.as<unsigned long long>() + lo, 8, cudaMemcpyDeviceToHost, st));
-        SCCD_CUDA(cudaStreamSynchronize(st));
+        host_sync(c, st);
         n_chunk = h[0] - h[1];
     }
     if (n_chunk > 0) {
@@ -1042,7 +871,7 @@ void narrow_finish(sccd_ctx* c, double* d_gtoi)
         return;
     R.pending.active = false;
     const int kind = R.pending.kind;
-    SCCD_CUDA(cudaStreamSynchronize(st));
+    host_sync(c, st);
     // the last round only hands work on when a path outgrows the lane state: rerun it
     for (int extra = 0; R.h_counters->n_items[kNarrowRounds] != 0 && R.h_counters->overflow != 2;
          extra++) {
@@ -1055,13 +884,21 @@ void narrow_finish(sccd_ctx* c, double* d_gtoi)
         SCCD_CUDA(cudaMemcpyAsync(
             R.h_counters, R.b_counters.ptr, sizeof(NarrowCounters), cudaMemcpyDeviceToHost, st));
         SCCD_CUDA(cudaMemcpyAsync(&c->h_gtoi[0], d_gtoi, 8, cudaMemcpyDeviceToHost, st));
-        SCCD_CUDA(cudaStreamSynchronize(st));
+        host_sync(c, st);
     }
     const NarrowCounters& r = *R.h_counters;
     c->stats.n_box_checks[kind] += (int64_t)r.box_checks;
     if (R.pending.culling)
         c->stats.n_culled[kind] += R.pending.in.n - (int64_t)r.n_items[0];
     c->stats.n_donated[kind] += (int64_t)r.donated;
+    for (int i = 0; i <= kNarrowRounds; i++) {
+        unsigned long long n = r.n_items[i];
+        if (i > 0 && r.closed[i])
+            n = std::min(n, ~r.closed[i]);
+        c->stats.n_round_items[kind][i] += (int64_t)(i > 0 ? std::min(n, R.item_cap) : n);
+    }
+    for (int i = 0; i < kNarrowRounds; i++)
+        c->stats.n_round_checks[kind][i] += (int64_t)r.round_checks[i];
     c->stats.n_capped[kind] += (int64_t)r.capped;
     if (r.overflow)
         c->stats.queue_overflow = 1;
@@ -1149,18 +986,30 @@ void finish_stats(sccd_ctx* c, bool pipeline)
     c->stats.ms_narrow[0] = elapsed(c, EV_NP0A, EV_NP0B);
     c->stats.ms_narrow[1] = elapsed(c, EV_NP1A, EV_NP1B);
     c->stats.ms_total = elapsed(c, EV_T0, EV_T1);
+    if (c->sliced && c->ev_xa) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->ev_xa, c->ev_xb) == cudaSuccess)
+            c->stats.ms_exchange = ms;
+        else
+            (void)cudaGetLastError();
+    }
 }
 
 // ccd() body (ccd.cu:108-146) and ipc_ccd_strategy() body (ipc_ccd_strategy.cu:108-152).
 void run_pipeline(
     sccd_ctx* c, double min_distance, int max_iter, double tol, bool allow_zero_toi, bool ipc,
     double* toi_out, bool want_collisions, std::vector<sccd_pair>* coll_ids,
-    std::vector<double>* coll_toi, int64_t* n_coll)
+    std::vector<double>* coll_toi, int64_t* n_coll, bool sharded)
 {
     reset_stats(c);
     c->cur = &c->runs[0];
     record(c, EV_T0);
-    build_boxes(c, min_distance);
+    if (sharded && (ipc || want_collisions))
+        throw std::logic_error("sharded pipeline: only the plain ccd() is supported");
+    if (sharded) // collective over the context's communicator (shard.cu)
+        build_boxes_sliced(c, min_distance);
+    else
+        build_boxes(c, min_distance);
     // (Measured and dropped: running the two lists on two streams so that the tail rounds of
     // one overlap the bulk of the other.  The earliest toi is established late -- in the tail
     // rounds of the vertex-face pass -- so an edge-edge pass that starts before it is final
@@ -1212,9 +1061,22 @@ void run_pipeline(
         for (int kind = 0; kind < 2; kind++) {
             c->cur = &c->runs[kind];
             narrow_finish(c, d_gtoi);
-            SCCD_CUDA(cudaStreamSynchronize(c->cur->stream));
+            host_sync(c, c->cur->stream);
         }
         c->cur = &c->runs[0];
+        if (sharded) {
+            // every batch of both lists is complete (extra rounds included): ONE all-reduce(min)
+            // of the earliest toi.  The edge-edge pass pruned with this rank's own vertex-face
+            // bound, which changes no result (the minimum is order-independent).
+            allreduce_min_toi(c, d_gtoi, c->stream);
+            SCCD_CUDA(cudaMemcpyAsync(&c->h_gtoi[2], d_gtoi, 8, cudaMemcpyDeviceToHost, c->stream));
+            record(c, EV_T1);
+            host_sync(c, c->stream);
+            c->stats.n_host_syncs++;
+            finish_stats(c, true);
+            *toi_out = std::min(1.0, c->h_gtoi[2]);
+            return;
+        }
         record(c, EV_T1);
         finish_stats(c, true);
         // the toi travelled back with the counters of the last batch (1.0 if there was none)
@@ -1266,7 +1128,7 @@ void run_pipeline(
                 launch_compact_collisions(d_pairs, d_tq, n, d_ids, d_t, d_cnt, c->stream, c->lc);
                 unsigned long long* h = reinterpret_cast<unsigned long long*>(R.h_small);
                 SCCD_CUDA(cudaMemcpyAsync(&h[2], d_cnt, 8, cudaMemcpyDeviceToHost, c->stream));
-                SCCD_CUDA(cudaStreamSynchronize(c->stream));
+                host_sync(c, c->stream);
                 const size_t k = (size_t)h[2], old = coll_ids->size();
                 coll_ids->resize(old + k);
                 coll_toi->resize(old + k);
@@ -1276,7 +1138,7 @@ void run_pipeline(
                         cudaMemcpyDeviceToHost, c->stream));
                     SCCD_CUDA(cudaMemcpyAsync(
                         coll_toi->data() + old, d_t, k * 8, cudaMemcpyDeviceToHost, c->stream));
-                    SCCD_CUDA(cudaStreamSynchronize(c->stream));
+                    host_sync(c, c->stream);
                 }
                 n_coll[kind] += (int64_t)k;
             }
@@ -1288,12 +1150,15 @@ void run_pipeline(
     *toi_out = toi;
 }
 
-} // namespace
+} // namespace host
+} // namespace sccd
+using namespace sccd::host;
 
 // =================================================================================== C ABI
 extern "C" {
 
-const char* sccd_version(void) { return "0.1.0 sm_100a"; }
+const char* sccd_version(void) { return "0.2.0 sm_100a"; }
+size_t sccd_stats_size(void) { return sizeof(sccd_stats); }
 
 int sccd_create(int device, void* stream, sccd_ctx** out)
 {
@@ -1360,6 +1225,7 @@ void sccd_destroy(sccd_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     if (ctx->sort_stream)
         cudaStreamSynchronize(ctx->sort_stream);
+    comm_destroy(ctx);
     delete ctx;
 }
 
@@ -1585,6 +1451,8 @@ int sccd_get_boxes(sccd_ctx* ctx, int which, sccd_aabb* out)
     return guarded(ctx, [&] {
         if (!ctx->have_boxes)
             throw std::logic_error("get_boxes: call sccd_build_boxes first");
+        if (ctx->sliced)
+            throw std::logic_error("get_boxes: after sccd_ccd_sharded every rank holds a slice only");
         if (which < 0 || which > 2 || !out)
             throw std::invalid_argument("get_boxes: bad argument");
         const int n = which == 0 ? ctx->nV : (which == 1 ? ctx->nE : ctx->nF);

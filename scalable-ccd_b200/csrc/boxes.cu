@@ -6,7 +6,7 @@
 // 64-byte record (x interval, yz mini-box, ids); the sort keys are made by csrc/grid.cu.
 // Results are bit-identical to the reference's boxes: nextafter() in double is exact on
 // the device and min/max/add are correctly rounded.
-#include "common.cuh"
+#include "boxmake.cuh"
 
 #include <cfloat>
 
@@ -21,23 +21,6 @@ __device__ __forceinline__ double next_up(double x) { return nextafter(x, DBL_MA
 // float build of the reference (scalar.hpp:31-49 with Scalar = float)
 __device__ __forceinline__ float next_down(float x) { return nextafterf(x, -FLT_MAX); }
 __device__ __forceinline__ float next_up(float x) { return nextafterf(x, FLT_MAX); }
-
-// The sweep runs along the FIRST coordinate of a record: a list swept along `axis` stores its
-// boxes with the axes rotated to (axis, axis + 1, axis + 2) mod 3 (SCCD_OPT_SWEEP_AXIS; the
-// reference's GPU path always sorts on x, aabb.cu:86, its CPU path on the caller's axis,
-// sort_and_sweep.cpp:78-116).  The overlap set does not depend on it.
-__device__ __forceinline__ double pick_axis(const double v[3], int a)
-{
-    return a == 0 ? v[0] : (a == 1 ? v[1] : v[2]);
-}
-__device__ __forceinline__ void store_record(
-    const BoxArrays& out, int k, const double lo[3], const double hi[3], int4 id, int axis)
-{
-    const int ay = axis == 2 ? 0 : axis + 1, az = axis == 0 ? 2 : axis - 1;
-    out.x[k] = make_double2(pick_axis(lo, axis), pick_axis(hi, axis));
-    out.yz[k] = make_double4(pick_axis(lo, ay), pick_axis(lo, az), pick_axis(hi, ay), pick_axis(hi, az));
-    out.id[k] = id;
-}
 
 // aabb.cu:146-184 build_vertex_boxes(V0, V1, r) + from_point + conservative_inflation.
 // F32: the reference's float build -- the vertices are cast to float first (aabb.cu:124-128,
@@ -92,20 +75,8 @@ __global__ void __launch_bounds__(kThreads) vertex_boxes_kernel(
     vb[2] = make_double2(hi[1], hi[2]);
     // aabb.cu:180-181 ids; element id flipped because vertices are list A of the
     // vertex-face sweep (broad_phase.cu:20-26).
-    store_record(vf, i, lo, hi, make_int4(i, -i - 1, -i - 1, -i - 1), axis_vf);
-}
-
-__device__ __forceinline__ void load_vbox(
-    const double* __restrict__ vbox, int v, double lo[3], double hi[3])
-{
-    const double2* vb = reinterpret_cast<const double2*>(vbox + (size_t)6 * v);
-    const double2 a = __ldg(vb), b = __ldg(vb + 1), c = __ldg(vb + 2);
-    lo[0] = a.x;
-    lo[1] = a.y;
-    lo[2] = b.x;
-    hi[0] = b.y;
-    hi[1] = c.x;
-    hi[2] = c.y;
+    if (vf.x) // (the sliced multi-GPU build makes its records from vbox: list_boxes_kernel)
+        store_record(vf, i, lo, hi, make_int4(i, -i - 1, -i - 1, -i - 1), axis_vf);
 }
 
 // aabb.cu:186-229 build_edge_boxes / build_face_boxes (union of vertex boxes).
@@ -154,6 +125,23 @@ __global__ void __launch_bounds__(kThreads) element_boxes_kernel(
         }
         store_record(vf, nV + f, lo, hi, make_int4(f0, f1, f2, f), axis_vf);
     }
+}
+
+// Boxes first, first + stride, ... (count of them) of a list, made from the replicated vertex
+// boxes into a compact array: the multi-GPU build's SLICE of a list (stride 1) and the sample
+// every rank takes of the whole list for the grid statistics and the cell histogram.
+__global__ void __launch_bounds__(kThreads) list_boxes_kernel(
+    MeshView m, int list, long long first, int stride, int count, BoxArrays out, int axis,
+    int* __restrict__ bad)
+{
+    const int j = blockIdx.x * kThreads + threadIdx.x;
+    if (j >= count)
+        return;
+    double lo[3], hi[3];
+    int4 id;
+    if (!make_list_box(m, list, (int)(first + (long long)j * stride), lo, hi, id))
+        *bad = 1;
+    store_record(out, j, lo, hi, id, axis);
 }
 
 // ---- the reference's three box builders by name, on caller-made arrays ------------------
@@ -290,6 +278,18 @@ void launch_element_aabbs(
         return;
     element_aabb_kernel<<<(n + kThreads - 1) / kThreads, kThreads, 0, s>>>(
         vb, nV, idx, n, k, out, bad);
+    SCCD_CUDA(cudaGetLastError());
+    lc.n++;
+}
+
+void launch_list_boxes(
+    const MeshView& m, int list, long long first, int stride, int count, BoxArrays out, int axis,
+    int* bad, cudaStream_t s, LaunchCounter& lc)
+{
+    if (count <= 0)
+        return;
+    list_boxes_kernel<<<(count + kThreads - 1) / kThreads, kThreads, 0, s>>>(
+        m, list, first, stride, count, out, axis, bad);
     SCCD_CUDA(cudaGetLastError());
     lc.n++;
 }

@@ -273,6 +273,7 @@ struct alignas(128) NarrowCounters {
     alignas(128) int overflow;                        // an item list was full (work kept local)
     int bad_input;                                    // a pair id is no element of the mesh
     unsigned long long box_checks;
+    unsigned long long round_checks[kNarrowRounds]; // box checks per round (load-balance report)
     unsigned long long donated;
     unsigned long long capped;
     // Longest-first claim order (flag bit 23): the cull writes survivors whose swept hulls overlap
@@ -314,7 +315,8 @@ constexpr int kStatsBlocks = 296;
 void launch_box_stats(
     const BoxArrays& unsorted, int n, int stride, double* partials /* kStatsBlocks*8 */,
     double* stats,
-    cudaStream_t s, LaunchCounter& lc);
+    cudaStream_t s, LaunchCounter& lc,
+    double sum_scale = 0.0 /* factor of the two extent sums; <= 0: stride */);
 // copies[i] = number of cells box i touches inside [g.cell_lo, g.cell_hi), or inside the
 // range d_range[0..1] held on the device when d_range is not null
 void launch_expand_count(
@@ -331,6 +333,28 @@ void launch_cell_splits(
 void launch_expand_fill(
     const BoxArrays& unsorted, int n, GridParams g, const unsigned long long* offsets,
     uint32_t* keys, uint32_t* idx, cudaStream_t s, LaunchCounter& lc);
+
+// ---- multi-GPU build (shard.cu): slice / sample boxes, records, partition, rebuild
+struct MeshView;
+void launch_list_boxes(
+    const MeshView& m, int list, long long first, int stride, int count, BoxArrays out, int axis,
+    int* bad, cudaStream_t s, LaunchCounter& lc);
+void launch_expand_fill_records(
+    const BoxArrays& unsorted, int n, GridParams g, const unsigned long long* offsets,
+    uint32_t idx_base, const unsigned long long* splits, int world, unsigned long long* rec,
+    uint8_t* dest, cudaStream_t s, LaunchCounter& lc);
+void launch_dest_counts(
+    const uint8_t* dest_sorted, unsigned long long m, int world, unsigned long long* counts,
+    cudaStream_t s, LaunchCounter& lc);
+size_t partition_temp_bytes(long long m);
+void launch_partition_by_dest(
+    long long m, const uint8_t* dest_in, uint8_t* dest_out, const unsigned long long* rec_in,
+    unsigned long long* rec_out, void* temp, size_t temp_bytes, cudaStream_t s, LaunchCounter& lc);
+size_t sort_records_temp_bytes(long long m);
+void launch_sort_records_and_rebuild(
+    int m, int key_bits, const unsigned long long* rec_in, unsigned long long* rec_out, void* temp,
+    size_t temp_bytes, const MeshView& mesh, int list, int axis, SortedList out, cudaStream_t s,
+    LaunchCounter& lc, cudaEvent_t gather_begin = nullptr, cudaEvent_t gather_end = nullptr);
 
 size_t sort_temp_bytes(int n);
 // sorts m (key, box index) records on key bits [kKeyFlagBits, kKeyFlagBits + key_bits) and

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(kThreads)
 
 // one CTA; fixed reduction tree => deterministic sums
 __global__ void __launch_bounds__(kThreads)
-    box_stats_final_kernel(const double* __restrict__ partials, int blocks, int stride, double* out)
+    box_stats_final_kernel(const double* __restrict__ partials, int blocks, double scale, double* out)
 {
     double r[kNumStats];
     stats_identity(r);
@@ -53,8 +53,8 @@ __global__ void __launch_bounds__(kThreads)
     __shared__ double red[32 * kNumStats];
     stats_block_reduce(r, red);
     if (threadIdx.x == 0) {
-        r[4] *= (double)stride; // sums over a 1-in-stride sample -> estimates for the list
-        r[5] *= (double)stride;
+        r[4] *= scale; // sums over a 1-in-stride sample -> estimates for the list
+        r[5] *= scale;
         for (int k = 0; k < kNumStats; k++)
             out[k] = r[k];
     }
@@ -228,12 +228,92 @@ __global__ void __launch_bounds__(kThreads) expand_fill_kernel(
     }
 }
 
+// Multi-GPU sender side: one 64-bit record (key << 32 | global box index) per touched cell of
+// every box of this rank's SLICE of the list, plus the rank that owns the cell (cells are dealt
+// to the ranks in contiguous ranges, splits[0..world]).  idx_base: list index of the slice's
+// first box.
+__global__ void __launch_bounds__(kThreads) expand_fill_records_kernel(
+    BoxArrays boxes, int n, GridParams g, const unsigned long long* __restrict__ offsets,
+    uint32_t idx_base, const unsigned long long* __restrict__ splits, int world,
+    unsigned long long* __restrict__ rec, uint8_t* __restrict__ dest)
+{
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n)
+        return;
+    int y0, y1, z0, z1;
+    cell_range(ldg_d4(&boxes.yz[i]), g, y0, y1, z0, z1);
+    const uint32_t xq = quantize_x(__ldg(&boxes.x[i]).x, g) << kKeyFlagBits;
+    const uint32_t type = __ldg(&boxes.id[i]).w < 0 ? kKeyFlagType : 0u;
+    const int cell_shift = g.x_bits + kKeyFlagBits;
+    unsigned long long o = offsets[i];
+    for (int cy = y0; cy <= y1; cy++)
+        for (int cz = z0; cz <= z1; cz++) {
+            const uint32_t cell = (uint32_t)(cy * g.sz + cz);
+            const uint32_t hi = cell_shift >= 32 ? 0u : (cell << cell_shift);
+            const uint32_t key =
+                hi | xq | type | (cy == y0 ? kKeyFlagY : 0u) | (cz == z0 ? kKeyFlagZ : 0u);
+            int d = 0;
+            while (d + 1 < world && (unsigned long long)cell >= splits[d + 1])
+                d++;
+            rec[o] = ((unsigned long long)key << 32) | (unsigned long long)(idx_base + (uint32_t)i);
+            dest[o] = (uint8_t)d;
+            o++;
+        }
+}
+
+// send_count[d] = records of destination d in the dest-sorted array (first index with
+// dest > d, minus the first with dest >= d)
+__global__ void dest_counts_kernel(
+    const uint8_t* __restrict__ dest_sorted, unsigned long long m, int world,
+    unsigned long long* __restrict__ counts)
+{
+    const int d = threadIdx.x;
+    if (d >= world)
+        return;
+    auto lower = [&](int v) { // first index with dest >= v
+        unsigned long long a = 0, b = m;
+        while (a < b) {
+            const unsigned long long mid = (a + b) >> 1;
+            if ((int)dest_sorted[mid] < v)
+                a = mid + 1;
+            else
+                b = mid;
+        }
+        return a;
+    };
+    counts[d] = lower(d + 1) - lower(d);
+}
+
 } // namespace
+
+void launch_expand_fill_records(
+    const BoxArrays& unsorted, int n, GridParams g, const unsigned long long* offsets,
+    uint32_t idx_base, const unsigned long long* splits, int world, unsigned long long* rec,
+    uint8_t* dest, cudaStream_t s, LaunchCounter& lc)
+{
+    if (n <= 0)
+        return;
+    expand_fill_records_kernel<<<(n + kThreads - 1) / kThreads, kThreads, 0, s>>>(
+        unsorted, n, g, offsets, idx_base, splits, world, rec, dest);
+    SCCD_CUDA(cudaGetLastError());
+    lc.n++;
+}
+
+void launch_dest_counts(
+    const uint8_t* dest_sorted, unsigned long long m, int world, unsigned long long* counts,
+    cudaStream_t s, LaunchCounter& lc)
+{
+    dest_counts_kernel<<<1, 32, 0, s>>>(dest_sorted, m, world, counts);
+    SCCD_CUDA(cudaGetLastError());
+    lc.n++;
+}
 
 void launch_box_stats(
     const BoxArrays& unsorted, int n, int stride, double* partials, double* stats,
-    cudaStream_t s, LaunchCounter& lc)
+    cudaStream_t s, LaunchCounter& lc, double sum_scale)
 {
+    if (sum_scale <= 0.0)
+        sum_scale = (double)stride;
     int blocks = ((n + stride - 1) / stride + kThreads - 1) / kThreads;
     if (blocks > kStatsBlocks)
         blocks = kStatsBlocks;
@@ -241,7 +321,7 @@ void launch_box_stats(
         blocks = 1;
     box_stats_kernel<<<blocks, kThreads, 0, s>>>(unsorted, n, stride, partials);
     SCCD_CUDA(cudaGetLastError());
-    box_stats_final_kernel<<<1, kThreads, 0, s>>>(partials, blocks, stride, stats);
+    box_stats_final_kernel<<<1, kThreads, 0, s>>>(partials, blocks, sum_scale, stats);
     SCCD_CUDA(cudaGetLastError());
     lc.n += 2;
 }

@@ -11,7 +11,7 @@
 // The radix sort is stable, so ties keep element order and the result is deterministic.
 // The vertex-face list is sorted as one tagged list (vertex element ids are already
 // flipped at build time), so no merge is needed.
-#include "common.cuh"
+#include "boxmake.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -39,6 +39,36 @@ __global__ void __launch_bounds__(kThreads) gather_sorted_kernel(
     out.id[j] = id;
     pf.key[j] = key;
     // same cell, q(xmax), every flag bit set (common.cuh)
+    const int cell_shift = g.x_bits + kKeyFlagBits;
+    const uint32_t cell_part = cell_shift >= 32 ? 0u : (key >> cell_shift) << cell_shift;
+    pf.reach[j] = cell_part | (quantize_x(x.y, g) << kKeyFlagBits) | ((1u << kKeyFlagBits) - 1u);
+    pf.yz[j] = make_float4(
+        __double2float_rd(yz.x), __double2float_ru(yz.z), __double2float_rd(yz.y),
+        __double2float_ru(yz.w));
+}
+
+// Multi-GPU receiver side: the exact record of a received (key, box index) record is REBUILT
+// from the replicated per-vertex boxes and topology instead of being shipped (64 B) or gathered
+// from a replica of every box of the mesh.  Same outputs as gather_sorted_kernel.
+__global__ void __launch_bounds__(kThreads) gather_rebuild_kernel(
+    int m, const unsigned long long* __restrict__ sorted_rec, MeshView mesh, int list, int axis,
+    BoxArrays out, PrefilterArrays pf, GridParams g)
+{
+    const int j = blockIdx.x * kThreads + threadIdx.x;
+    if (j >= m)
+        return;
+    const unsigned long long r = sorted_rec[j];
+    const uint32_t key = (uint32_t)(r >> 32);
+    double lo[3], hi[3];
+    int4 id;
+    make_list_box(mesh, list, (int)(uint32_t)r, lo, hi, id); // (indices were checked by the sender)
+    double2 x;
+    double4 yz;
+    rotate_box(lo, hi, axis, x, yz);
+    out.x[j] = x;
+    out.yz[j] = yz;
+    out.id[j] = id;
+    pf.key[j] = key;
     const int cell_shift = g.x_bits + kKeyFlagBits;
     const uint32_t cell_part = cell_shift >= 32 ? 0u : (key >> cell_shift) << cell_shift;
     pf.reach[j] = cell_part | (quantize_x(x.y, g) << kKeyFlagBits) | ((1u << kKeyFlagBits) - 1u);
@@ -84,6 +114,62 @@ void launch_sort_and_gather(
         m, keys_out, idx_out, unsorted, out.box, out.pf, out.grid);
     SCCD_CUDA(cudaGetLastError());
     lc.n++;
+    if (gather_end)
+        SCCD_CUDA(cudaEventRecord(gather_end, s));
+}
+
+// ---- multi-GPU (shard.cu) ---------------------------------------------------------------
+size_t partition_temp_bytes(long long m)
+{
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(
+        nullptr, bytes, (const uint8_t*)nullptr, (uint8_t*)nullptr,
+        (const unsigned long long*)nullptr, (unsigned long long*)nullptr, m > 0 ? m : 1, 0, 5);
+    return bytes;
+}
+
+// stable partition of the records by destination rank (one digit pass)
+void launch_partition_by_dest(
+    long long m, const uint8_t* dest_in, uint8_t* dest_out, const unsigned long long* rec_in,
+    unsigned long long* rec_out, void* temp, size_t temp_bytes, cudaStream_t s, LaunchCounter& lc)
+{
+    if (m <= 0)
+        return;
+    SCCD_CUDA(cub::DeviceRadixSort::SortPairs(
+        temp, temp_bytes, dest_in, dest_out, rec_in, rec_out, m, 0, 5, s));
+    lc.n += 3;
+}
+
+size_t sort_records_temp_bytes(long long m)
+{
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortKeys(
+        nullptr, bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
+        m > 0 ? m : 1, 32, 64);
+    return bytes;
+}
+
+// sorts m received records on key bits [kKeyFlagBits, kKeyFlagBits + key_bits) of their high
+// word (stable: equal keys keep arrival order = global box order) and rebuilds the sorted views
+void launch_sort_records_and_rebuild(
+    int m, int key_bits, const unsigned long long* rec_in, unsigned long long* rec_out, void* temp,
+    size_t temp_bytes, const MeshView& mesh, int list, int axis, SortedList out, cudaStream_t s,
+    LaunchCounter& lc, cudaEvent_t gather_begin, cudaEvent_t gather_end)
+{
+    if (m > 0) {
+        SCCD_CUDA(cub::DeviceRadixSort::SortKeys(
+            temp, temp_bytes, rec_in, rec_out, m, 32 + kKeyFlagBits, 32 + kKeyFlagBits + key_bits,
+            s));
+        lc.n += 2 + (key_bits + 7) / 8;
+    }
+    if (gather_begin)
+        SCCD_CUDA(cudaEventRecord(gather_begin, s));
+    if (m > 0) {
+        gather_rebuild_kernel<<<(m + kThreads - 1) / kThreads, kThreads, 0, s>>>(
+            m, rec_out, mesh, list, axis, out.box, out.pf, out.grid);
+        SCCD_CUDA(cudaGetLastError());
+        lc.n++;
+    }
     if (gather_end)
         SCCD_CUDA(cudaEventRecord(gather_end, s));
 }
