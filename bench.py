@@ -6,11 +6,17 @@
 
 A "step" = one full CCD pass (AABB build -> sort -> sweep -> Tight-Inclusion narrow phase
 -> earliest TOI, vertex-face then edge-edge) over one synthetic two-frame scene.
-  value : ms/step with the mesh already resident in HBM (sccd_ccd)
-  e2e   : ms/step through the host-pointer entry point (sccd_ccd_host): pinned host
-          buffers -> H2D -> pipeline -> TOI back on the host, all inside the timed region
-N > 1 : one process per GPU (torchrun); every rank sweeps its owner slice of the sorted
-        lists and solves the pairs it found; NCCL all-reduce(min) of the TOI ("strong").
+  value : ms/step with the mesh already resident in HBM (sccd_ccd / sccd_ccd_sharded)
+  e2e   : ms/step through the host-pointer entry point (sccd_ccd_host / sccd_ccd_sharded_host):
+          pinned host buffers -> H2D -> pipeline -> TOI back on the host, all inside the timed
+          region
+Workload: config 2 (the 1M-primitive scene the metric is quoted on) for a plain `python
+bench.py`; config 4 (~50M AABBs) for EVERY launch under torch.distributed.run, world size 1
+included, so that one scaling series is one scene ("strong" scaling).
+N > 1 : one process per GPU; torch.distributed (gloo) is the rendezvous only.  The ranks split
+        the step inside the library (csrc/shard.cu): element slices -> 8-byte records exchanged by
+        owning cell range (NCCL send/recv) -> local sort / sweep / narrow phase -> NCCL
+        all-reduce(min) of the TOI.
 """
 import argparse
 import json
@@ -164,22 +170,37 @@ def cpu_step(orc, scene):
             "kind": kind, "toi": toi, "n_pairs": [len(vf), len(ee)]}
 
 
+def host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU reference arm is entitled to
+    all host cores, so the count is set explicitly before any OpenMP runtime starts."""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    return n
+
+
 def run_reference(args, rank, world):
     """Reference arm: the reference's own CPU implementation of the path on the host cores
     (oracle/_ref when it was built, else the oracle port), all host threads.  Config 4 is too
-    big for a CPU step of a few minutes, so its step is a BOUNDED SAMPLE: the same pile
-    generator with 1/16 of the instances (same density), time scaled by 16 -- stated in
-    `sample`."""
+    big for a CPU step of a few minutes (the reference's one-axis CPU sweep is O(N^5/3) on a
+    dense pile), so there the arm times a NAMED SAMPLE SCENE -- the same generator with 1/16 of
+    the instances -- and reports that scene's own time: nothing is extrapolated, and
+    `config.workload` says what was run."""
     if rank != 0:
         return
+    threads = host_threads()
     from _pkg import load_package
     from oracle import orc
     sccd = load_package()
-    scale = 1
     if args.workload == "c4":
-        scale = 16
-        scene = sccd.scenes.scene_c4(n_inst=83_000 // scale)
-        desc = make_desc("c4")
+        n_inst = 83_000 // 16
+        scene = sccd.scenes.scene_c4(n_inst=n_inst)
+        nb = scene['V0'].shape[0] + scene['E'].shape[0] + scene['F'].shape[0]
+        desc = (f"config 4 SAMPLE SCENE: {n_inst} blobs in an x-slab ({nb} boxes; 1/16 of the "
+                "instances of config 4, same generator and density) -- its own time, not scaled")
     else:
         scene, desc = make_scene(sccd.scenes, args.workload)
     budget_s = 150.0
@@ -192,17 +213,13 @@ def run_reference(args, rank, world):
             steps.append(r)
         if time.perf_counter() - t_start > budget_s and steps:
             break
-    ms = statistics.mean(s["ms"] for s in steps) * scale
+    ms = statistics.mean(s["ms"] for s in steps)
     cores = orc.lib().orc_num_threads()
-    what = (f"{len(steps)} full step(s) of the workload" if scale == 1 else
-            f"{len(steps)} step(s) of a 1/{scale} sample of the workload (same generator and "
-            f"density, {scene['V0'].shape[0] + scene['E'].shape[0] + scene['F'].shape[0]} boxes), "
-            f"time x{scale}")
-    sample = (f"{what} (time-bounded to ~{int(budget_s)} s); "
+    sample = (f"{len(steps)} full step(s) of `config.workload` (time-bounded to ~{int(budget_s)} s); "
               f"broad phase = {steps[0]['kind']} CPU sort_and_sweep "
               f"({statistics.mean(s['broad_ms'] for s in steps):.0f} ms, oneTBB replaced by an OpenMP stub), "
               f"narrow phase = oracle port with OpenMP ({statistics.mean(s['narrow_ms'] for s in steps):.0f} ms; "
-              "the reference has no CPU narrow phase)")
+              f"the reference has no CPU narrow phase); OMP_NUM_THREADS={threads}")
     line = {
         "impl": "reference", "metric": METRIC, "value": ms, "unit": UNIT, "n_gpus": args.gpus,
         "steps": len(steps), "warmup": warm, "ms_per_step": ms, "higher_is_better": False,
@@ -216,11 +233,12 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def ref_cuda_subprocess(workload, timeout_s=240):
-    """Reference CUDA ccd() on the same box, in a subprocess so a crash/hang cannot take the
-    bench down.  Returns dict or {'unavailable': why}."""
+def ref_cuda_subprocess(workload, calls=10, timeout_s=300):
+    """The UNMODIFIED reference CUDA ccd() on the same box (oracle/_ref/libref_sccd_cuda.so), in
+    a subprocess so a crash / hang cannot take the bench down: 3 untimed calls, then `calls`
+    timed ones; the median is the number to compare with.  {'unavailable': why} otherwise."""
     code = f"""
-import sys, json
+import sys, json, statistics
 sys.path.insert(0, {ROOT!r})
 from _pkg import load_package
 from oracle import orc
@@ -229,12 +247,18 @@ sccd = load_package()
 if orc.ref_cuda(False) is None:
     print(json.dumps({{"unavailable": "oracle/_ref/libref_sccd_cuda.so not built"}})); sys.exit(0)
 scene, _ = bench.make_scene(sccd.scenes, {workload!r})
-out = []
 for i in range(3):
+    r = orc.ref_cuda_ccd(scene, **bench.PARAMS)
+out = []
+for i in range({calls}):
     r = orc.ref_cuda_ccd(scene, **bench.PARAMS)
     out.append(r["ms"])
 b = orc.ref_cuda_broad_phase(scene, want_pairs=False)
-print(json.dumps({{"ccd_ms": out, "toi": r["toi"], "broad_ms": b["ms"], "n_vf": b["n_vf"], "n_ee": b["n_ee"]}}))
+print(json.dumps({{"median_ms": statistics.median(out), "min_ms": min(out), "max_ms": max(out),
+                  "calls": len(out), "warmup_calls": 3, "all_ms": out, "toi": r["toi"],
+                  "broad_phase_ms": b["ms"], "n_vf": b["n_vf"], "n_ee": b["n_ee"],
+                  "what": "unmodified reference CUDA ccd() (host mesh in, TOI out), wall clock "
+                          "inside the shim around the call"}}))
 """
     try:
         p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
@@ -254,16 +278,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None,
-                    help="c1|c2|c3|c4|small; default: c2 on one GPU (config 2, the scene the "
-                         "metric is quoted on), c4 (config 4, ~50M AABBs) on several")
+                    help="c1|c2|c3|c4|small.  Default: config 2 (the 1M-primitive scene the metric "
+                         "is quoted on) for a plain `python bench.py`; config 4 (~50M AABBs) for "
+                         "EVERY launch under torch.distributed.run, world size 1 included, so "
+                         "that one scaling series is one scene")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
     args = ap.parse_args()
+    under_launcher = "RANK" in os.environ
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.workload is None:
-        args.workload = "c2" if max(world, args.gpus) == 1 else "c4"
+        args.workload = "c4" if (under_launcher or max(world, args.gpus) > 1) else "c2"
     if args.impl == "reference":
         return run_reference(args, rank, world)
     args.warmup = max(args.warmup, 3)
@@ -273,46 +300,38 @@ def main():
     import torch.distributed as dist
     from _pkg import load_package
     sccd = load_package()
+    K = sccd.capi
     torch.cuda.set_device(local)
     if world > 1:
+        # torch.distributed is the launcher's rendezvous only (gloo): it carries rank 0's NCCL id
+        # and the max-over-ranks of the timings.  The data path -- record exchange, all-gather of
+        # the host mesh, min-TOI all-reduce -- is NCCL inside the library (sccd_comm_create).
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("gloo")
     scene, desc = make_scene(sccd.scenes, args.workload)
     nV, nE, nF = scene["V0"].shape[0], scene["E"].shape[0], scene["F"].shape[0]
 
     stream = torch.cuda.current_stream().cuda_stream
     ctx = sccd.Context(local, stream)
     ctx.upload_mesh(scene["V0"], scene["V1"], scene["E"], scene["F"])
-    sharded = sccd.multigpu.ShardedCCD(ctx) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-    toi_t = torch.zeros(1, dtype=torch.float64, device="cuda")
 
     def barrier():
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
 
-    def step_resident():
-        if world > 1:   # sharded sweep, pair rebalancing, NCCL min-TOI (multigpu.py)
-            ctx.reset_stats()
-            return sharded.ccd(**PARAMS)
-        return ctx.ccd(**PARAMS)
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    # pinned host copies for the end-to-end arm
+    # pinned host copies for the end-to-end arm (column-major, as the C ABI takes them)
     pinned = {k: torch.from_numpy(np.ascontiguousarray(v.T)).pin_memory() for k, v in scene.items()}
-
-    packed = sccd.multigpu.pack_mesh(scene["V0"], scene["V1"], scene["E"], scene["F"], world) \
-        if world > 1 else None
-
-    def step_e2e():
-        if world > 1:
-            # every rank copies 1/world of the host mesh over its own PCIe link; the slices
-            # are all-gathered over NVLink (multigpu.gather_mesh)
-            ctx.reset_stats()
-            sharded.upload_mesh_host(packed[0], packed[1], (nV, nE, nF))
-            return sharded.ccd(**PARAMS)
-        return ctx.ccd_host(pinned["V0"].data_ptr(), pinned["V1"].data_ptr(), pinned["E"].data_ptr(),
-                            pinned["F"].data_ptr(), sizes=(nV, nE, nF), **PARAMS)
+    host_args = (pinned["V0"].data_ptr(), pinned["V1"].data_ptr(), pinned["E"].data_ptr(),
+                 pinned["F"].data_ptr())
 
     def timed(fn, steps, warmup, sampler=False):
         # the sampler starts before the warm-up (NVML initialisation stalls the first CUDA calls
@@ -335,39 +354,49 @@ def main():
         t1 = time.time()
         clocks = smp.stop(t0, t1) if smp else None
         per_step = [a.elapsed_time(b) for a, b in ev]
-        ms = sum(per_step) / steps
         timed.last_steps = per_step
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, toi, stats, clocks
+        return max_over_ranks(sum(per_step) / steps), toi, stats, clocks
 
-    single_ms = None
+    single_ms = single_toi = single_pairs = None
     if world > 1:
-        # the same scene on ONE GPU (every rank, unsharded, untimed except on rank 0) so the
-        # line carries its own strong-scaling reference
-        single = ctx.ccd(**PARAMS)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(2):
-            ctx.ccd(**PARAMS)
-        torch.cuda.synchronize()
-        single_ms = (time.perf_counter() - t0) / 2 * 1e3
-        sharded = sccd.multigpu.ShardedCCD(ctx)   # re-arm the shard after the unsharded runs
-        barrier()
+        # the same scene on ONE GPU (every rank, plain pipeline) so that the line carries its own
+        # strong-scaling reference, timed like the steps below
+        ms1, single_toi, st1, _ = timed(lambda: ctx.ccd(**PARAMS), 3, 2)
+        single_ms = ms1
+        single_pairs = st1[-1]["n_pairs"]
+        uid = [sccd.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_create(uid[0], rank, world)
+        step_resident = lambda: ctx.ccd_sharded(**PARAMS)
+        step_e2e = lambda: ctx.ccd_sharded_host(*host_args, sizes=(nV, nE, nF), **PARAMS)
+    else:
+        step_resident = lambda: ctx.ccd(**PARAMS)
+        step_e2e = lambda: ctx.ccd_host(*host_args, sizes=(nV, nE, nF), **PARAMS)
+
     ms, toi, stats, clocks = timed(step_resident, args.steps, args.warmup, sampler=True)
     ms_steps = list(timed.last_steps)
-    rank_stage_ms = None
+
+    def avg(key, *idx, src=None):
+        vals = []
+        for s in (src or stats):
+            v = s[key]
+            for i in idx:
+                v = v[i]
+            vals.append(v)
+        return float(sum(vals)) / len(vals)
+
+    def allsum(x):   # whole-job counts (sum over ranks)
+        if world == 1:
+            return x
+        t = torch.tensor(x, dtype=torch.float64)
+        dist.all_reduce(t)
+        return [float(v) for v in t.tolist()]
+
+    n_pairs = allsum([avg("n_pairs", 0), avg("n_pairs", 1)])
     if world > 1:
-        assert toi == single, ("sharded TOI differs from the single-GPU TOI", toi, single)
-        sharded.profile = True            # one extra untimed step with per-stage events
-        step_resident()
-        sharded.profile = False
-        rank_stage_ms = sharded.last.pop("ms", None)
-        gathered = [None] * world
-        dist.all_gather_object(gathered, rank_stage_ms)
-        rank_stage_ms = gathered
+        assert toi == single_toi, ("sharded TOI differs from the single-GPU TOI", toi, single_toi)
+        assert [int(v) for v in n_pairs] == list(single_pairs), \
+            ("the ranks' pair lists do not add up to the single-GPU lists", n_pairs, single_pairs)
     e2e_ms, toi2, _, _ = timed(step_e2e, args.steps, 1)
     assert toi == toi2, (toi, toi2)
     # what a simulator with a fixed topology pays per step (sccd_update_vertices: only the two
@@ -387,101 +416,165 @@ def main():
         except Exception as exc:  # never let the extra arm cost the bench line
             e2e_v = {"error": repr(exc)[:200]}
 
-    def avg(key, idx=None):
-        vals = [s[key] if idx is None else s[key][idx] for s in stats]
-        return float(sum(vals)) / len(vals)
+    # ---- kernel-level pass (untimed for `value`): every solver round gets its own event pair
+    ctx.set_option(K.OPT_PROFILE, 1)
+    prof = []
+    for _ in range(3):
+        flush.zero_()
+        step_resident()
+        prof.append(ctx.stats())
+    ctx.set_option(K.OPT_PROFILE, 0)
+    pavg = lambda key, *idx: avg(key, *idx, src=prof)
 
-    # whole-job counts (sum over ranks)
-    def allsum(x):
-        if world == 1:
-            return x
-        t = torch.tensor(x, dtype=torch.float64, device="cuda")
-        dist.all_reduce(t)
-        return [float(v) for v in t.tolist()]
-
-    n_pairs = allsum([avg("n_pairs", 0), avg("n_pairs", 1)])
     n_checks = allsum([avg("n_box_checks", 0), avg("n_box_checks", 1)])
     n_cand = allsum([avg("n_candidates", 0), avg("n_candidates", 1)])
-    n_boxes = [nV + nF, nE]
-    k_ms = {
-        "boxes": avg("ms_k_boxes"), "gather": avg("ms_k_gather"),
-        "sweep_count_vf": avg("ms_k_sweep_count", 0), "sweep_count_ee": avg("ms_k_sweep_count", 1),
-        "sweep_fill_vf": avg("ms_k_sweep_fill", 0), "sweep_fill_ee": avg("ms_k_sweep_fill", 1),
-        "narrow_vf": avg("ms_k_narrow", 0), "narrow_ee": avg("ms_k_narrow", 1),
-    }
-    stage_ms = {"build": avg("ms_build"), "sort": avg("ms_sort"), "sweep_vf": avg("ms_sweep", 0),
-                "sweep_ee": avg("ms_sweep", 1), "narrow_vf": avg("ms_narrow", 0),
-                "narrow_ee": avg("ms_narrow", 1), "total_device": avg("ms_total")}
-    # algorithmic bytes per launch.  The sweep reads each box once
-    # (64 B) in the pass that finds the pairs and writes each pair once (8 B) in the pass that
-    # places them; on N > 1 GPUs a rank's sweep / gather only covers its own share of the boxes.
     loc_pairs = [avg("n_pairs", 0), avg("n_pairs", 1)]
-    share = 1.0 / world
-    alg_bytes = {
-        "boxes": 48 * nV + 8 * nE + 12 * nF + 64 * (nV + nE + nF),
-        "gather": 2 * 64 * (nV + nE + nF) * share,
-        "sweep_count_vf": 64 * n_boxes[0] * share, "sweep_count_ee": 64 * n_boxes[1] * share,
-        "sweep_fill_vf": 8 * loc_pairs[0], "sweep_fill_ee": 8 * loc_pairs[1],
-        "narrow_vf": (8 + 192 + 8) * loc_pairs[0], "narrow_ee": (8 + 192 + 8) * loc_pairs[1],
-    }
-    dom = max(k_ms, key=lambda k: k_ms[k])
+    loc_recs = [avg("n_records", 0), avg("n_records", 1)]
+    loc_culled = [avg("n_culled", 0), avg("n_culled", 1)]
+    n_boxes = [nV + nF, nE]
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = alg_bytes[dom] / (k_ms[dom] * 1e-3) / 1e9 if k_ms[dom] > 0 else 0.0
-    traffic = None
-    try:  # per-launch DRAM bytes of the same kernel from the committed ncu capture, if any
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json"))).get(
-            f"{args.workload}:{dom}")
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_source = "MEASURED_PEAKS.json (measured copy bandwidth)" if peaks else \
+        "fallback 6650 GB/s (B200_PROFILING.md)"
+    dfma_peak = ctx.measure_fp64_peak()        # thread-level DFMA/s of this device, measured now
+    fp64_peak_tflops = 2.0 * dfma_peak / 1e12
+    traffic_db = {}
+    try:
+        traffic_db = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic,
-                "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s",
-                "algorithmic_bytes_per_launch": alg_bytes[dom], "kernel_ms": k_ms[dom],
-                "all_kernels": {k: {"ms": k_ms[k], "GBps": (alg_bytes[k] / (k_ms[k] * 1e-3) / 1e9
-                                                             if k_ms[k] > 0 else 0.0)} for k in k_ms}}
-    narrow_ms = k_ms["narrow_vf"] + k_ms["narrow_ee"]
-    # FP64 work of the narrow phase (96 / 84 arithmetic instr per box check) against
-    # the FP64 pipe rate measured on this device by a register-only DFMA micro-benchmark
+
+    # One entry per KERNEL: measured device time per launch of this rank, the
+    # roofline that bounds it, and its algorithmic work per launch.
+    #   HBM kernels : bytes every box / record / query has to cross the memory system once
+    #   solver      : FP64 flops = box checks x (VF 60 DFMA + 36 DADD = 156, EE 48 + 36 = 132)
+    kernels = {}
+
+    def hbm(name, ms_, nbytes, what):
+        if ms_ > 0:
+            gbs = nbytes / (ms_ * 1e-3) / 1e9
+            kernels[name] = {"ms": ms_, "bound": "hbm", "achieved": gbs, "peak": hbm_peak,
+                             "unit": "GB/s", "frac": gbs / hbm_peak,
+                             "algorithmic_bytes_per_launch": nbytes, "work": what}
+
+    def fp64(name, ms_, checks, flop_per_check):
+        if ms_ > 0:
+            tf = checks * flop_per_check / (ms_ * 1e-3) / 1e12
+            kernels[name] = {"ms": ms_, "bound": "fp64", "achieved": tf, "peak": fp64_peak_tflops,
+                             "unit": "TFLOP/s", "frac": tf / fp64_peak_tflops,
+                             "algorithmic_flop_per_launch": checks * flop_per_check,
+                             "work": f"{checks:.0f} box checks x {flop_per_check} FP64 flop"}
+
+    share = 1.0 / world
+    if world == 1:
+        hbm("vertex_boxes+element_boxes (2 launches)", pavg("ms_k_boxes"),
+            48 * nV + 8 * nE + 12 * nF + 64 * (nV + nE + nF), "48 B/vertex + indices in, 64 B/box out")
+    else:
+        hbm("vertex_boxes + 2 x list_boxes(sample) (3 launches)", pavg("ms_k_boxes"),
+            (48 + 96) * nV + (64 + 60) * (nV + nE + nF) / 16,
+            "replicated: vertex table + vertex boxes of all vertices, 1-in-16 box sample")
+    hbm("gather (2 launches)", pavg("ms_k_gather"), 2 * 64 * (loc_recs[0] + loc_recs[1]),
+        "64 B exact record in + out per sweep record")
+    for k, nm in ((0, "vf"), (1, "ee")):
+        passes = (int(pavg("key_bits", k)) + 7) // 8
+        hbm(f"radix_sort_{nm} ({passes} digit passes + histogram)", pavg("ms_k_sort", k),
+            16 * loc_recs[k] * passes + 8 * loc_recs[k],
+            "8 B (key, index) record read + written per digit pass, read once for the histogram")
+        hbm(f"sweep_count_{nm}", pavg("ms_k_sweep_count", k), 64 * loc_recs[k],
+            "64 B per sweep record read once")
+        hbm(f"sweep_place_{nm}", pavg("ms_k_sweep_fill", k), 8 * loc_pairs[k], "8 B per pair written")
+        hbm(f"narrow_cull_{nm}", pavg("ms_k_cull", k), (8 + 192 + 4) * loc_pairs[k],
+            "pair + 8 vertices (192 B) in, survivor index out, per query")
+        for r in range(5):
+            fp64(f"narrow_round{r}_{nm}", pavg("ms_k_round", k, r), pavg("n_round_checks", k, r),
+                 156 if k == 0 else 132)
+    dom = max(kernels, key=lambda k_: kernels[k_]["ms"]) if kernels else None
+    roofline = None
+    if dom:
+        d = kernels[dom]
+        roofline = {"kernel": dom, "bound": d["bound"], "achieved": d["achieved"], "peak": d["peak"],
+                    "unit": d["unit"], "frac": d["frac"],
+                    "traffic": traffic_db.get(f"{args.workload}:{dom}"),
+                    "traffic_source": "profiles/dram_traffic.json (ncu --set full capture of this "
+                                      "commit's kernels; not measured in this run)",
+                    "kernel_ms": d["ms"], "work_per_launch": d["work"],
+                    "peak_source": (peak_source if d["bound"] == "hbm" else
+                                    "FP64 peak = 2 x DFMA/s measured on this device in this run by "
+                                    "a register-only micro-benchmark (sccd_measure_fp64_peak)"),
+                    "note": ("dominant kernel by measured device time among ALL kernels of the "
+                             "step (per-kernel event pairs, SCCD_OPT_PROFILE pass); the solver "
+                             "rounds are bound by the FP64 pipe / dependent-chain latency, "
+                             "everything else by HBM"),
+                    "all_kernels": kernels}
+    # the HBM-bound kernel with the most time, for the memory-system view of the same step
+    hbm_only = {k_: v for k_, v in kernels.items() if v["bound"] == "hbm"}
+    dom_h = max(hbm_only, key=lambda k_: hbm_only[k_]["ms"]) if hbm_only else None
+    narrow_ms = avg("ms_k_narrow", 0) + avg("ms_k_narrow", 1)
+    stage_ms = {"build": avg("ms_build"), "sort": avg("ms_sort"), "sweep_vf": avg("ms_sweep", 0),
+                "sweep_ee": avg("ms_sweep", 1), "narrow_vf": avg("ms_narrow", 0),
+                "narrow_ee": avg("ms_narrow", 1), "exchange": avg("ms_exchange"),
+                "total_device": avg("ms_total")}
+    rank_stage_ms = None
+    if world > 1:
+        rank_stage_ms = [None] * world
+        mine = dict(stage_ms)
+        mine.update(records=loc_recs, pairs=loc_pairs, records_sent=[avg("n_records_sent", 0),
+                                                                    avg("n_records_sent", 1)],
+                    k_boxes=avg("ms_k_boxes"), k_expand=[avg("ms_k_expand", 0), avg("ms_k_expand", 1)],
+                    k_sort=[avg("ms_k_sort", 0), avg("ms_k_sort", 1)], k_gather=avg("ms_k_gather"),
+                    host_syncs=avg("n_host_syncs"))
+        dist.all_gather_object(rank_stage_ms, mine)
     fp64_instr = 96 * n_checks[0] + 84 * n_checks[1]
-    dfma_peak = ctx.measure_fp64_peak() * world
-    fp64 = {"bound": "fp64 pipe", "kernel": "narrow_vf + narrow_ee",
-            "achieved": (fp64_instr / (narrow_ms * 1e-3)) if narrow_ms > 0 else None,
-            "peak": dfma_peak, "unit": "thread-level FP64 instr/s (peak: measured DFMA/s)",
-            "frac": (fp64_instr / (narrow_ms * 1e-3) / dfma_peak) if narrow_ms > 0 else None,
-            "note": "96 (VF) / 84 (EE) FP64 arithmetic instructions per box check, min/max and "
-                    "compares not counted"}
     line = {
         "metric": METRIC, "value": ms, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": desc, "n_vertices": nV, "n_edges": nE, "n_faces": nF,
+                   "workload_rule": ("config 2 for a plain `python bench.py`; config 4 for every "
+                                     "launch under torch.distributed.run (world size 1 included)"),
                    "l2": "256 MiB device write between timed steps (flush)", **PARAMS,
-                   "parallelism": f"cell-range shards x{world}" if world > 1 else "single GPU"},
+                   "parallelism": (f"{world} ranks: element slices -> 8 B records exchanged by cell "
+                                   "range (NCCL send/recv) -> local sort/sweep/narrow -> NCCL min"
+                                   if world > 1 else "single GPU")},
         "clocks": clocks,
         "e2e": {"value": e2e_ms, "unit": UNIT,
                 "h2d_bytes_per_step": 2 * 24 * nV + 8 * nE + 12 * nF, "d2h_bytes_per_step": 8,
-                "note": ("whole job: each rank copies 1/N of the mesh H2D, NCCL all-gather of the "
-                         "slices" if world > 1 else "pinned host mesh -> sccd_ccd_host")},
+                "note": ("sccd_ccd_sharded_host: each rank copies 1/N of the pinned host mesh "
+                         "H2D, NCCL all-gather of the slices (whole job bytes)" if world > 1
+                         else "pinned host mesh -> sccd_ccd_host")},
         "e2e_vertices_only": e2e_v,
         "gpu_launches": int(avg("n_launches")) * args.steps,
-        "roofline": roofline, "roofline_fp64": fp64,
-        "toi": toi, "n_pairs": n_pairs,
-        "pairs_per_rank": (sharded.last if sharded else None),
-        "stage_ms_per_rank": rank_stage_ms, "ms_steps_rank0": ms_steps,
+        "host_syncs_per_step": avg("n_host_syncs"),
+        "roofline": roofline,
+        "roofline_hbm": ({"kernel": dom_h, **{k_: hbm_only[dom_h][k_] for k_ in
+                                              ("achieved", "peak", "unit", "frac", "ms")},
+                          "traffic": traffic_db.get(f"{args.workload}:{dom_h}")} if dom_h else None),
+        "toi": toi, "n_pairs": n_pairs, "ms_steps_rank0": ms_steps,
+        "stage_ms_per_rank": rank_stage_ms,
         "single_gpu_ms_same_workload": single_ms,
-        "speedup_vs_single_gpu": (single_ms / ms if single_ms else None), "n_prefilter_survivors": n_cand, "n_box_checks": n_checks,
+        "speedup_vs_single_gpu": (single_ms / ms if single_ms else None),
+        "n_prefilter_survivors": n_cand, "n_box_checks": n_checks,
         "narrow_queries_per_s": (sum(n_pairs) / (narrow_ms * 1e-3)) if narrow_ms > 0 else None,
         "narrow_box_checks_per_s": (sum(n_checks) / (narrow_ms * 1e-3)) if narrow_ms > 0 else None,
         "narrow_fp64_instr_per_s": (fp64_instr / (narrow_ms * 1e-3)) if narrow_ms > 0 else None,
-        "stage_ms": stage_ms, "kernel_ms": k_ms,
+        "sweep_candidate_tests_per_s": ((n_cand[0] + n_cand[1]) / ((avg("ms_k_sweep_count", 0)
+                                        + avg("ms_k_sweep_count", 1)) * 1e-3)
+                                        if avg("ms_k_sweep_count", 0) + avg("ms_k_sweep_count", 1) > 0 else None),
+        # queue load balance: items every solver round read, box checks per round,
+        # sub-boxes handed on, and whether a bounded item list was ever full -- this rank
+        "narrow_load_balance": {"round_items": [[avg("n_round_items", k, r) for r in range(6)] for k in (0, 1)],
+                                "round_checks": [[avg("n_round_checks", k, r) for r in range(5)] for k in (0, 1)],
+                                "culled": loc_culled, "donated": [avg("n_donated", 0), avg("n_donated", 1)],
+                                "queue_overflow": avg("queue_overflow")},
+        "stage_ms": stage_ms,
     }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload in ("small", "c1", "c2"):
         from oracle import orc
+        host_threads()
         r = cpu_step(orc, scene)
         assert r["toi"] == toi and r["n_pairs"] == [int(n_pairs[0]), int(n_pairs[1])], \
             ("GPU result differs from the CPU baseline", r["toi"], toi, r["n_pairs"], n_pairs)
@@ -491,7 +584,13 @@ def main():
                        f"sort_and_sweep ({r['broad_ms']:.0f} ms; oneTBB replaced by an OpenMP stub), "
                        f"narrow phase = oracle port with OpenMP ({r['narrow_ms']:.0f} ms; the "
                        "reference has no CPU narrow phase); result checked equal to the GPU's")}
-    if rank == 0 and world == 1 and not args.no_ref_cuda:
+    elif rank == 0 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = {
+            "value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
+            "sample": ("not run inside this line: one CPU step of this workload takes minutes "
+                       "(O(N^5/3) one-axis sweep on a dense pile); see `bench.py --impl reference`, "
+                       "which times a named 1/16 sample scene")}
+    if rank == 0 and world == 1 and not args.no_ref_cuda and args.workload in ("small", "c1", "c2"):
         line["reference_cuda"] = ref_cuda_subprocess(args.workload)
     if rank == 0:
         print(json.dumps(line), flush=True)

@@ -108,6 +108,7 @@ typedef struct {
     float ms_k_cull[2];      /* separating-axis cull kernel                                     */
     float ms_k_round[2][5];  /* solver rounds (SCCD_OPT_PROFILE only)                           */
     float pad2_;
+    int32_t key_bits[2];     /* sort-key bits in use (cell + quantised major axis) per list       */
 } sccd_stats;
 /* sizeof(sccd_stats) of the library (binding sanity check) */
 size_t sccd_stats_size(void);

@@ -68,7 +68,8 @@ float elapsed(sccd_ctx* c, int a, int b)
     return ms;
 }
 
-size_t kt_begin(sccd_ctx* c, float* dst)
+// pooled event pair that will be resolved into *dst (+=) at the end of the call
+size_t kt_alloc(sccd_ctx* c, float* dst)
 {
     if (c->kt_used == c->ktimers.size()) {
         sccd_ctx::KTimer k;
@@ -76,14 +77,19 @@ size_t kt_begin(sccd_ctx* c, float* dst)
         SCCD_CUDA(cudaEventCreate(&k.b));
         c->ktimers.push_back(k);
     }
-    sccd_ctx::KTimer& k = c->ktimers[c->kt_used];
-    k.dst = dst;
-    SCCD_CUDA(cudaEventRecord(k.a, c->cur->stream));
+    c->ktimers[c->kt_used].dst = dst;
     return c->kt_used++;
+}
+size_t kt_begin(sccd_ctx* c, float* dst, cudaStream_t st)
+{
+    const size_t id = kt_alloc(c, dst);
+    c->ktimers[id].st = st ? st : c->cur->stream;
+    SCCD_CUDA(cudaEventRecord(c->ktimers[id].a, c->ktimers[id].st));
+    return id;
 }
 void kt_end(sccd_ctx* c, size_t id)
 {
-    SCCD_CUDA(cudaEventRecord(c->ktimers[id].b, c->cur->stream));
+    SCCD_CUDA(cudaEventRecord(c->ktimers[id].b, c->ktimers[id].st));
 }
 void kt_resolve(sccd_ctx* c)
 {
@@ -427,9 +433,16 @@ void sort_list_finish(
         SCCD_CUDA(cudaEventRecord(c->ev_counts, c->stream));
         SCCD_CUDA(cudaStreamWaitEvent(st, c->ev_counts, 0));
     }
+    const int slot = which == 1 ? 1 : 0;
+    c->stats.key_bits[slot] = cell_bits + g.x_bits;
+    const size_t kt_e = kt_begin(c, &c->stats.ms_k_expand[slot], st);
     launch_expand_fill(
         L.unsorted, n, g, L.offs.as<unsigned long long>(), L.keys.as<uint32_t>(),
         L.idx.as<uint32_t>(), st, c->lc);
+    kt_end(c, kt_e);
+    // (radix passes = from here to the gather's begin event; resolved in finish_stats)
+    if (ga)
+        SCCD_CUDA(cudaEventRecord(c->ev[slot == 0 ? EV_SB0 : EV_SB1], st));
     launch_sort_and_gather(
         (int)m, cell_bits + g.x_bits, L.keys.as<uint32_t>(), L.keys_tmp.as<uint32_t>(),
         L.idx.as<uint32_t>(), L.idx_out.as<uint32_t>(), L.sort_temp.ptr, L.sort_temp.cap,
@@ -845,11 +858,22 @@ void narrow_enqueue(
     uint32_t* survivors = nullptr;
     if (c->opt.np_cull)
         survivors = (uint32_t*)R.b_surv.reserve((size_t)in.n * 4);
+    // kernel-level timers: the cull always, every solver round with SCCD_OPT_PROFILE
+    cudaEvent_t tev[2 * (1 + kNarrowRounds)] = {};
+    if (survivors) {
+        const size_t id = kt_alloc(c, &c->stats.ms_k_cull[kind]);
+        tev[0] = c->ktimers[id].a, tev[1] = c->ktimers[id].b;
+    }
+    if (c->opt.profile)
+        for (int r = 0; r < kNarrowRounds; r++) {
+            const size_t id = kt_alloc(c, &c->stats.ms_k_round[kind][r]);
+            tev[2 + 2 * r] = c->ktimers[id].a, tev[3 + 2 * r] = c->ktimers[id].b;
+        }
     const size_t kt = kt_begin(c, &c->stats.ms_k_narrow[kind]);
     launch_narrow_phase(
         kind == SCCD_VF, c->f32, in, P, R.b_counters.as<NarrowCounters>(), d_gtoi,
         R.b_items[0].as<WorkItem>(), R.b_items[1].as<WorkItem>(), R.item_cap, d_toi_per_query,
-        checks, survivors, c->num_sms, st, c->lc);
+        checks, survivors, c->num_sms, st, c->lc, tev);
     kt_end(c, kt);
     SCCD_CUDA(cudaMemcpyAsync(
         R.h_counters, R.b_counters.ptr, sizeof(NarrowCounters), cudaMemcpyDeviceToHost, st));
@@ -974,6 +998,8 @@ void finish_stats(sccd_ctx* c, bool pipeline)
     if (c->gather_timed && !c->sort1_pending) {
         SCCD_CUDA(cudaEventSynchronize(c->ev[EV_GB1]));
         c->stats.ms_k_gather = elapsed(c, EV_GA0, EV_GB0) + elapsed(c, EV_GA1, EV_GB1);
+        c->stats.ms_k_sort[0] = elapsed(c, EV_SB0, EV_GA0);
+        c->stats.ms_k_sort[1] = elapsed(c, EV_SB1, EV_GA1);
         c->gather_timed = false;
     }
     if (!pipeline)
@@ -1309,6 +1335,7 @@ int sccd_set_option(sccd_ctx* ctx, int option, int64_t value)
             return SCCD_ERR_ARG;
         ctx->grid_repl = (double)value / 1000.0;
         break;
+    case SCCD_OPT_PROFILE: o.profile = value != 0; break;
     case SCCD_OPT_SWEEP_AXIS:
         if (value < -1 || value > 2)
             return SCCD_ERR_ARG;
@@ -1340,6 +1367,7 @@ int sccd_get_option(const sccd_ctx* ctx, int option, int64_t* value)
     case SCCD_OPT_GRID_SCALE_MILLI: *value = (int64_t)std::llround(ctx->grid_scale * 1000.0); break;
     case SCCD_OPT_GRID_REPL_MILLI: *value = (int64_t)std::llround(ctx->grid_repl * 1000.0); break;
     case SCCD_OPT_SWEEP_AXIS: *value = o.sweep_axis; break;
+    case SCCD_OPT_PROFILE: *value = o.profile; break;
     default: return SCCD_ERR_ARG;
     }
     return SCCD_OK;

@@ -418,7 +418,8 @@ void launch_narrow_phase(
     bool is_vf, bool f32, const NarrowInput& in, const NarrowParams& p, NarrowCounters* counters,
     double* g_toi, WorkItem* items0, WorkItem* items1, unsigned long long item_cap, double* toi_per_query,
     unsigned int* checks_per_query, uint32_t* survivors /* in.n words, or null: no cull */,
-    int num_sms, cudaStream_t s, LaunchCounter& lc);
+    int num_sms, cudaStream_t s, LaunchCounter& lc,
+    const cudaEvent_t* tev = nullptr /* 2 * (1 + kNarrowRounds) optional timing events */);
 // moves n_items[kNarrowRounds] to n_items[kNarrowRounds - 1] and reruns the last round
 void launch_narrow_extra_round(
     bool is_vf, bool f32, const NarrowInput& in, const NarrowParams& p, NarrowCounters* counters,

@@ -86,6 +86,7 @@ struct sccd_ctx {
         int cap_drops = 0;      // max_iter reached: 0 accept at t_lo, 1 drop (reference)
         int key_steps = 3;      // log2 of the x quantisation steps per record of a cell
         int sweep_axis = 0;     // 0/1/2, or -1: variance argmax of the previous build
+        int profile = 0;        // time every solver round (sccd_stats.ms_k_round)
     } opt;
     int next_axis = 0;          // argmax of the box-centre variance of the last build
 
@@ -144,11 +145,12 @@ struct sccd_ctx {
 
     sccd_stats stats {};
     LaunchCounter lc;
-    cudaEvent_t ev[20] {};
+    cudaEvent_t ev[24] {};
     bool gather_timed = false;
     // pooled event pairs timing single kernels; resolved into stats at the end of a call
     struct KTimer {
         cudaEvent_t a = nullptr, b = nullptr;
+        cudaStream_t st = nullptr;
         float* dst = nullptr;
     };
     std::vector<KTimer> ktimers;
@@ -196,7 +198,8 @@ namespace sccd {
 namespace host {
 
 enum { EV_T0, EV_BUILD, EV_SORT, EV_SW0A, EV_SW0B, EV_NP0A, EV_NP0B, EV_SW1A, EV_SW1B,
-       EV_NP1A, EV_NP1B, EV_T1, EV_TMPA, EV_TMPB, EV_GA0, EV_GB0, EV_GA1, EV_GB1, EV_COUNT };
+       EV_NP1A, EV_NP1B, EV_T1, EV_TMPA, EV_TMPB, EV_GA0, EV_GB0, EV_GA1, EV_GB1, EV_SB0, EV_SB1,
+       EV_COUNT };
 
 inline void use_device(sccd_ctx* c) { SCCD_CUDA(cudaSetDevice(c->device)); }
 
@@ -238,7 +241,9 @@ inline void host_sync(sccd_ctx* c, cudaStream_t s)
 void record(sccd_ctx* c, int which);
 void rrecord(sccd_ctx* c, int which);
 float elapsed(sccd_ctx* c, int a, int b);
-size_t kt_begin(sccd_ctx* c, float* dst);
+size_t kt_alloc(sccd_ctx* c, float* dst);
+size_t kt_begin(sccd_ctx* c, float* dst, cudaStream_t st = nullptr); // null: the current run's
+
 void kt_end(sccd_ctx* c, size_t id);
 sccd_ctx::ListHost& list_host(sccd_ctx* c, int which);
 GridParams choose_grid(const double* st, int n, int max_cells, double scale);

@@ -435,7 +435,7 @@ void build_boxes_sliced(sccd_ctx* c, double inflation_radius)
         L.sorted.pf.yz = (float4*)L.pyz.reserve(mm * sizeof(float4));
         unsigned long long* sorted_rec = (unsigned long long*)S.recv_sorted.reserve(mm * 8);
         S.sort_temp.reserve(sort_records_temp_bytes((long long)plan[k].recv_total));
-        // (timed on the main stream only: kt_* record on the current run's stream)
+        SCCD_CUDA(cudaEventRecord(c->ev[k == 0 ? EV_SB0 : EV_SB1], sk));
         launch_sort_records_and_rebuild(
             (int)plan[k].recv_total, cell_bits[k] + gk.x_bits, recv[k], sorted_rec, S.sort_temp.ptr,
             S.sort_temp.cap, mv, k, L.axis, L.sorted, sk, c->lc, c->ev[k == 0 ? EV_GA0 : EV_GA1],
@@ -455,6 +455,7 @@ void build_boxes_sliced(sccd_ctx* c, double inflation_radius)
         c->stats.grid_cells[k][1] = g[k].sz;
         c->stats.sweep_axis[k] = c->lists[k].axis;
         c->stats.next_axis[k] = c->lists[k].next_axis;
+        c->stats.key_bits[k] = cell_bits[k] + g[k].x_bits;
     }
 }
 
