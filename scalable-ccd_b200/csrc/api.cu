@@ -338,7 +338,7 @@ void list_stats(sccd_ctx* c, int which)
     const size_t per = (size_t)(kStatsBlocks + 1) * kNumStats;
     double* base = (double*)c->b_stats.reserve(3 * per * sizeof(double)) + which * per;
     double* d_stats = base + kStatsBlocks * kNumStats;
-    const int stride = std::min(16, std::max(1, L.n_boxes >> 18));
+    const int stride = stats_stride(L.n_boxes);
     launch_box_stats(L.unsorted, L.n_boxes, stride, base, d_stats, c->stream, c->lc);
     SCCD_CUDA(cudaMemcpyAsync(
         H.stats, d_stats, kNumStats * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -515,7 +515,7 @@ void build_boxes(sccd_ctx* c, double inflation_radius)
         // it back (sort_and_sweep.cpp:176-195); here over the sampled boxes of the statistics
         auto& L = c->lists[which];
         const double* st = list_host(c, which).stats;
-        const int stride = std::min(16, std::max(1, L.n_boxes >> 18));
+        const int stride = stats_stride(L.n_boxes);
         const double ns = (double)((L.n_boxes + stride - 1) / stride);
         double var[3] = { 0, 0, 0 }; // in the caller's axes
         for (int k = 0; k < 3; k++)
@@ -839,6 +839,9 @@ void narrow_enqueue(
     P.max_iter = max_iter;
     P.allow_zero_toi = allow_zero_toi ? 1 : 0;
     P.use_ms = ms > 0 ? 1 : 0;
+    P.n_peers = (c->share_toi && !d_toi_per_query) ? c->n_peers : 0;
+    for (int p = 0; p < 15; p++)
+        P.peer_toi[p] = p < P.n_peers ? c->peer_toi[p] : nullptr;
     // (the edge-edge pass inherits the earliest toi of the vertex-face pass and may want other
     // budgets: SCCD_OPT_NARROW_FLAGS_EE)
     P.flags = (kind == SCCD_EE && c->opt.np_flags_ee >= 0) ? c->opt.np_flags_ee : c->opt.np_flags;
@@ -1032,6 +1035,12 @@ void run_pipeline(
     record(c, EV_T0);
     if (sharded && (ipc || want_collisions))
         throw std::logic_error("sharded pipeline: only the plain ccd() is supported");
+    // (sharded: the solver kernels publish the bound to the other ranks' toi words)
+    struct ShareGuard {
+        sccd_ctx* c;
+        ~ShareGuard() { c->share_toi = false; }
+    } share_guard { c };
+    c->share_toi = sharded;
     if (sharded) // collective over the context's communicator (shard.cu)
         build_boxes_sliced(c, min_distance);
     else

@@ -247,6 +247,13 @@ struct NarrowParams {
     int flags;      // debug knobs (SCCD_NP_FLAGS env), see narrow.cu
     int max_depth;  // levels a walk may track before handing on (<= 128)
     int cap_drops;  // max_iter reached: 0 = accept the box at t_lo (conservative), 1 = drop it
+    // Multi-GPU (sccd_ccd_sharded): the earliest-toi words of the OTHER ranks, mapped into this
+    // rank's address space over NVLink (CUDA IPC, shard.cu).  A lane that lowers the bound also
+    // lowers it on every peer with a system-scope atomicMin, so all ranks prune with the global
+    // earliest toi while they work -- the collective is fused into the solver kernels; the
+    // all-reduce at the end of the step only closes the race of the last updates.
+    int n_peers;
+    double* peer_toi[15];
 };
 
 // A pending sub-box of a query, handed from one round of the narrow phase to the next

@@ -5,6 +5,7 @@
 
 #include "common.cuh"
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -132,6 +133,12 @@ struct sccd_ctx {
         long long lo = 0, hi = 0;             // slice [lo, hi) of the list's boxes
         int stride = 1, ns = 0;               // sample stride and size
     } slice[2];
+    // earliest-toi words of the other ranks (CUDA IPC mappings over NVLink): the solver kernels
+    // publish every improvement of the bound to all ranks (NarrowParams::peer_toi)
+    int n_peers = 0;
+    double* peer_toi[15] = {};
+    bool peer_is_ipc[15] = {};
+    bool share_toi = false;             // set for the duration of a sharded pipeline call
     bool sliced = false;                // the mesh lists hold slices / received records
     DevBuf b_xcnt, b_xsplits;           // all ranks' send counts; both lists' cell splits
     unsigned long long* h_xcnt = nullptr; // pinned
@@ -229,6 +236,11 @@ template <typename F> int guarded(sccd_ctx* c, F&& f)
         return SCCD_ERR_MEMORY;
     }
 }
+
+// The box statistics (grid choice, key quantisation, next sweep axis) and the multi-GPU cell
+// histogram look at every stride-th box of a list: ~260 K .. 1 M samples steer them as well as
+// the whole list does (both clamp), and the pass stays off the critical path of a 50 M-box step.
+inline int stats_stride(long long n) { return (int)std::min<long long>(64, std::max<long long>(1, n >> 18)); }
 
 // every host <-> device synchronisation of a pipeline call goes through here (sccd_stats)
 inline void host_sync(sccd_ctx* c, cudaStream_t s)

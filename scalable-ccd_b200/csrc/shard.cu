@@ -25,6 +25,7 @@
 #include "boxmake.cuh"
 
 #include <dlfcn.h>
+#include <unistd.h>
 #include <nccl.h> // types and prototypes only: the library is loaded at run time
 
 #include <algorithm>
@@ -115,8 +116,65 @@ inline ncclComm_t comm_of(sccd_ctx* c) { return (ncclComm_t)c->nccl_comm; }
 
 } // namespace
 
+// Maps the earliest-toi word of every other rank into this rank's address space (CUDA IPC over
+// NVLink; plain peer access for ranks that are threads of this process).  Collective.
+static void map_peer_toi(sccd_ctx* c, int rank, int world)
+{
+    struct Card {
+        cudaIpcMemHandle_t handle;
+        unsigned long long pid, ptr, device, pad;
+    };
+    static_assert(sizeof(Card) % 8 == 0, "Card");
+    double* mine = (double*)c->b_gtoi.reserve(64);
+    Card card {};
+    SCCD_CUDA(cudaIpcGetMemHandle(&card.handle, mine));
+    card.pid = (unsigned long long)getpid();
+    card.ptr = (unsigned long long)(uintptr_t)mine;
+    card.device = (unsigned long long)c->device;
+    DevBuf stage;
+    Card* d_cards = (Card*)stage.reserve(sizeof(Card) * world);
+    std::vector<Card> cards(world);
+    SCCD_CUDA(cudaMemcpyAsync(d_cards + rank, &card, sizeof(Card), cudaMemcpyHostToDevice, c->stream));
+    SCCD_NCCL(nccl().AllGather(
+        d_cards + rank, d_cards, sizeof(Card), ncclChar, (ncclComm_t)c->nccl_comm, c->stream));
+    SCCD_CUDA(cudaMemcpyAsync(
+        cards.data(), d_cards, sizeof(Card) * world, cudaMemcpyDeviceToHost, c->stream));
+    SCCD_CUDA(cudaStreamSynchronize(c->stream));
+    c->n_peers = 0;
+    for (int p = 0; p < world; p++) {
+        if (p == rank)
+            continue;
+        void* ptr = nullptr;
+        bool ipc = false;
+        if (cards[p].pid == card.pid) { // a thread of this process: peer access, same pointer
+            if ((int)cards[p].device != c->device) {
+                const cudaError_t e = cudaDeviceEnablePeerAccess((int)cards[p].device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                    (void)cudaGetLastError();
+                    continue; // no peer access: this peer only gets the final all-reduce
+                }
+                (void)cudaGetLastError();
+            }
+            ptr = (void*)(uintptr_t)cards[p].ptr;
+        } else {
+            if (cudaIpcOpenMemHandle(&ptr, cards[p].handle, cudaIpcMemLazyEnablePeerAccess)
+                != cudaSuccess) {
+                (void)cudaGetLastError();
+                continue;
+            }
+            ipc = true;
+        }
+        c->peer_is_ipc[c->n_peers] = ipc;
+        c->peer_toi[c->n_peers++] = (double*)ptr;
+    }
+}
+
 void comm_destroy(sccd_ctx* c)
 {
+    for (int p = 0; p < c->n_peers; p++)
+        if (c->peer_is_ipc[p])
+            cudaIpcCloseMemHandle(c->peer_toi[p]);
+    c->n_peers = 0;
     if (c->nccl_comm) {
         nccl().CommDestroy(comm_of(c));
         c->nccl_comm = nullptr;
@@ -206,7 +264,7 @@ void build_boxes_sliced(sccd_ctx* c, double inflation_radius)
     for (int k = 0; k < 2; k++) {
         auto& S = c->slice[k];
         auto& H = list_host(c, k);
-        S.stride = (int)std::min<long long>(16, std::max<long long>(1, n_list[k] >> 18));
+        S.stride = stats_stride(n_list[k]);
         S.ns = (int)((n_list[k] + S.stride - 1) / S.stride);
         S.lo = n_list[k] * rank / W;
         S.hi = n_list[k] * (rank + 1) / W;
@@ -386,34 +444,39 @@ void build_boxes_sliced(sccd_ctx* c, double inflation_radius)
         c->stats.n_records_sent[k] = (int64_t)(plan[k].send_total - plan[k].send_cnt[rank]);
         c->stats.n_records_received[k] = (int64_t)(plan[k].recv_total - plan[k].recv_cnt[rank]);
     }
+    // One group per list: the vertex-face records on the main stream, the edge records on the
+    // sort stream, so that the vertex-face sort starts while the edge records are still moving
+    // (NCCL orders the two groups on the communicator; every rank issues them in this order).
+    SCCD_CUDA(cudaEventRecord(c->ev_counts, st)); // everything the senders made is on `st`
+    SCCD_CUDA(cudaStreamWaitEvent(c->sort_stream, c->ev_counts, 0));
     SCCD_CUDA(cudaEventRecord(c->ev_xa, st));
-    if (W > 1)
-        SCCD_NCCL(nccl().GroupStart());
-    for (int k = 0; k < 2; k++)
+    for (int k = 0; k < 2; k++) {
+        cudaStream_t sk = k == 0 ? st : c->sort_stream;
+        const ExchangePlan& P = plan[k];
+        if (W > 1)
+            SCCD_NCCL(nccl().GroupStart());
         for (int p = 0; p < W; p++) {
-            const ExchangePlan& P = plan[k];
             if (p == rank) {
                 if (P.send_cnt[p])
                     SCCD_CUDA(cudaMemcpyAsync(
                         recv[k] + P.recv_off[p], send_rec[k] + P.send_off[p], P.send_cnt[p] * 8,
-                        cudaMemcpyDeviceToDevice, st));
+                        cudaMemcpyDeviceToDevice, sk));
                 continue;
             }
             if (P.send_cnt[p])
                 SCCD_NCCL(nccl().Send(
-                    send_rec[k] + P.send_off[p], P.send_cnt[p], ncclUint64, p, comm_of(c), st));
+                    send_rec[k] + P.send_off[p], P.send_cnt[p], ncclUint64, p, comm_of(c), sk));
             if (P.recv_cnt[p])
                 SCCD_NCCL(nccl().Recv(
-                    recv[k] + P.recv_off[p], P.recv_cnt[p], ncclUint64, p, comm_of(c), st));
+                    recv[k] + P.recv_off[p], P.recv_cnt[p], ncclUint64, p, comm_of(c), sk));
         }
-    if (W > 1)
-        SCCD_NCCL(nccl().GroupEnd());
-    SCCD_CUDA(cudaEventRecord(c->ev_xb, st));
+        if (W > 1)
+            SCCD_NCCL(nccl().GroupEnd());
+    }
+    SCCD_CUDA(cudaEventRecord(c->ev_xb, c->sort_stream));
 
     // ---- 6. per list: sort the received records, rebuild their exact boxes.  The edge list on
     // the sort stream, under the vertex-face sweep and narrow phase (as build_boxes).
-    SCCD_CUDA(cudaEventRecord(c->ev_counts, st));
-    SCCD_CUDA(cudaStreamWaitEvent(c->sort_stream, c->ev_counts, 0));
     for (int k = 0; k < 2; k++) {
         auto& S = c->slice[k];
         auto& L = c->lists[k];
@@ -533,6 +596,8 @@ int sccd_comm_create(sccd_ctx* ctx, const void* id, int rank, int world)
             ncclComm_t comm = nullptr;
             SCCD_NCCL(n.CommInitRank(&comm, world, uid, rank));
             ctx->nccl_comm = comm;
+            if (!getenv("SCCD_NO_PEER_TOI"))
+                map_peer_toi(ctx, rank, world);
         }
         ctx->comm_world = world;
         ctx->rank = rank;
