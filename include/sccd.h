@@ -226,6 +226,15 @@ int sccd_ccd_sharded_host(
     const int32_t* F, int64_t nF, double min_distance, int max_iter, double tol,
     int allow_zero_toi, double* toi);
 
+/* Host arithmetic of the record exchange, exposed for tests that have no GPU: from the matrix
+ * counts[src * world + dst] (records rank src holds for rank dst, one list) it gives rank
+ * `rank` the offsets of its per-destination parts in its send buffer, and the count / offset of
+ * what it receives from every source (sources land in rank order).  Arrays of `world` words;
+ * any output may be NULL. */
+int sccd_exchange_plan(
+    const uint64_t* counts, int list, int rank, int world, uint64_t* send_off, uint64_t* recv_cnt,
+    uint64_t* recv_off, uint64_t* recv_total);
+
 /* ---- mesh + boxes --------------------------------------------------------------- */
 
 /* DeviceMatrix uploads of ccd() (cuda/ccd.cu:103-106).  on_device != 0: the four

@@ -36,7 +36,7 @@ SYMBOLS = [
     "sccd_narrow_phase", "sccd_narrow_phase_queries", "sccd_ccd", "sccd_ccd_collisions",
     "sccd_get_collisions", "sccd_set_option", "sccd_get_option", "sccd_narrow_phase_checks",
     "sccd_stats_size", "sccd_comm_get_unique_id", "sccd_comm_create", "sccd_comm_destroy",
-    "sccd_ccd_sharded", "sccd_ccd_sharded_host",
+    "sccd_ccd_sharded", "sccd_ccd_sharded_host", "sccd_exchange_plan",
     "sccd_ccd_host", "sccd_ipc_ccd_strategy", "sccd_get_stats", "sccd_reset_stats",
     "sccd_synchronize", "sccd_measure_fp64_peak",
     "sccd_version",
@@ -107,6 +107,19 @@ def _ptr(a):
     if isinstance(a, (int, np.integer)):
         return C.c_void_p(int(a))
     return a.ctypes.data_as(C.c_void_p)
+
+
+def exchange_plan(counts, rank: int, list_: int = 0):
+    """sccd_exchange_plan: counts[src, dst] -> (send_off, recv_cnt, recv_off, recv_total) of `rank`."""
+    counts = np.ascontiguousarray(counts, dtype=np.uint64)
+    world = counts.shape[0]
+    so, rc, ro = (np.zeros(world, np.uint64) for _ in range(3))
+    tot = C.c_uint64(0)
+    rcode = load().sccd_exchange_plan(_ptr(counts), C.c_int(list_), C.c_int(rank), C.c_int(world),
+                                      _ptr(so), _ptr(rc), _ptr(ro), C.byref(tot))
+    if rcode != OK:
+        raise SccdError(rcode, "sccd_exchange_plan: bad argument")
+    return so, rc, ro, int(tot.value)
 
 
 class Context:

@@ -416,10 +416,8 @@ void sort_list_finish(
     int cell_bits = 0;
     key_layout(g, m_total, H.stats, c->opt.key_steps, cell_bits);
     const size_t mm = (size_t)m;
-    L.keys.reserve(mm * 4);
-    L.keys_tmp.reserve(mm * 4);
-    L.idx.reserve(mm * 4);
-    L.idx_out.reserve(mm * 4);
+    L.keys.reserve(mm * 8);     // 64-bit records (key << 32 | box index) ...
+    L.keys_tmp.reserve(mm * 8); // ... and their ping-pong buffer
     L.sorted.n = (int)m;
     L.sorted.grid = g;
     L.sorted.box.x = (double2*)L.sx.reserve(mm * sizeof(double2));
@@ -437,16 +435,15 @@ void sort_list_finish(
     c->stats.key_bits[slot] = cell_bits + g.x_bits;
     const size_t kt_e = kt_begin(c, &c->stats.ms_k_expand[slot], st);
     launch_expand_fill(
-        L.unsorted, n, g, L.offs.as<unsigned long long>(), L.keys.as<uint32_t>(),
-        L.idx.as<uint32_t>(), st, c->lc);
+        L.unsorted, n, g, L.offs.as<unsigned long long>(), L.keys.as<unsigned long long>(), st, c->lc);
     kt_end(c, kt_e);
     // (radix passes = from here to the gather's begin event; resolved in finish_stats)
     if (ga)
         SCCD_CUDA(cudaEventRecord(c->ev[slot == 0 ? EV_SB0 : EV_SB1], st));
     launch_sort_and_gather(
-        (int)m, cell_bits + g.x_bits, L.keys.as<uint32_t>(), L.keys_tmp.as<uint32_t>(),
-        L.idx.as<uint32_t>(), L.idx_out.as<uint32_t>(), L.sort_temp.ptr, L.sort_temp.cap,
-        L.unsorted, L.sorted, st, c->lc, ga, gb);
+        (int)m, cell_bits + g.x_bits, L.keys.as<unsigned long long>(),
+        L.keys_tmp.as<unsigned long long>(), L.sort_temp.ptr, L.sort_temp.cap, L.unsorted, L.sorted,
+        st, c->lc, ga, gb);
 }
 
 // one list on its own (caller-made boxes; re-sharding an already built list)

@@ -336,10 +336,10 @@ void launch_expand_count(
 void launch_cell_splits(
     const BoxArrays& unsorted, int n, int stride, GridParams g, int world, uint32_t* hist,
     unsigned long long* out, cudaStream_t s, LaunchCounter& lc);
-// one (key, box index) record per touched cell, at offsets[i] ...
+// one 64-bit record (key << 32 | idx_base + box index) per touched cell, at offsets[i] ...
 void launch_expand_fill(
     const BoxArrays& unsorted, int n, GridParams g, const unsigned long long* offsets,
-    uint32_t* keys, uint32_t* idx, cudaStream_t s, LaunchCounter& lc);
+    unsigned long long* rec, cudaStream_t s, LaunchCounter& lc);
 
 // ---- multi-GPU build (shard.cu): slice / sample boxes, records, partition, rebuild
 struct MeshView;
@@ -348,29 +348,26 @@ void launch_list_boxes(
     int* bad, cudaStream_t s, LaunchCounter& lc);
 void launch_expand_fill_records(
     const BoxArrays& unsorted, int n, GridParams g, const unsigned long long* offsets,
-    uint32_t idx_base, const unsigned long long* splits, int world, unsigned long long* rec,
-    uint8_t* dest, cudaStream_t s, LaunchCounter& lc);
-void launch_dest_counts(
-    const uint8_t* dest_sorted, unsigned long long m, int world, unsigned long long* counts,
-    cudaStream_t s, LaunchCounter& lc);
+    uint32_t idx_base, unsigned long long* rec, cudaStream_t s, LaunchCounter& lc);
 size_t partition_temp_bytes(long long m);
+// stable partition of the records by the rank that owns their cell; counts: `world` device words
 void launch_partition_by_dest(
-    long long m, const uint8_t* dest_in, uint8_t* dest_out, const unsigned long long* rec_in,
-    unsigned long long* rec_out, void* temp, size_t temp_bytes, cudaStream_t s, LaunchCounter& lc);
+    long long m, const unsigned long long* rec_in, unsigned long long* rec_out, int cell_shift,
+    const unsigned long long* h_first_cell /* world + 1, host */, int world,
+    unsigned long long* counts, void* temp, size_t temp_bytes, cudaStream_t s, LaunchCounter& lc);
 size_t sort_records_temp_bytes(long long m);
 void launch_sort_records_and_rebuild(
-    int m, int key_bits, const unsigned long long* rec_in, unsigned long long* rec_out, void* temp,
+    int m, int key_bits, unsigned long long* rec, unsigned long long* rec_tmp, void* temp,
     size_t temp_bytes, const MeshView& mesh, int list, int axis, SortedList out, cudaStream_t s,
     LaunchCounter& lc, cudaEvent_t gather_begin = nullptr, cudaEvent_t gather_end = nullptr);
 
-size_t sort_temp_bytes(int n);
-// sorts m (key, box index) records on key bits [kKeyFlagBits, kKeyFlagBits + key_bits) and
-// gathers the sorted views
+size_t sort_temp_bytes(long long m);
+// sorts m 64-bit records (key << 32 | box index) on key bits [kKeyFlagBits, kKeyFlagBits +
+// key_bits) and gathers the sorted views; rec / rec_tmp are ping-pong buffers
 void launch_sort_and_gather(
-    int m, int key_bits, uint32_t* keys_in, uint32_t* keys_out, uint32_t* idx_in,
-    uint32_t* idx_out, void* temp, size_t temp_bytes, BoxArrays unsorted, SortedList out,
-    cudaStream_t s, LaunchCounter& lc, cudaEvent_t gather_begin = nullptr,
-    cudaEvent_t gather_end = nullptr);
+    int m, int key_bits, unsigned long long* rec, unsigned long long* rec_tmp, void* temp,
+    size_t temp_bytes, BoxArrays unsorted, SortedList out, cudaStream_t s, LaunchCounter& lc,
+    cudaEvent_t gather_begin = nullptr, cudaEvent_t gather_end = nullptr);
 
 // window[i] = number of candidates after owner i whose f32 xmin <= owner's f32 xmax
 void launch_sweep_windows(

@@ -41,7 +41,7 @@ struct sccd_ctx {
     struct ListBufs {
         DevBuf ux, uyz, uid;     // unsorted exact records (one per box)
         DevBuf copies, offs;     // cells touched per box, and their exclusive scan
-        DevBuf keys, keys_tmp, idx, idx_out; // (key, box index) records, one per (box, cell)
+        DevBuf keys, keys_tmp;   // 64-bit (key, box index) records, one per (box, cell)
         DevBuf sx, syz, sid;     // sorted exact records
         DevBuf pkey, preach, pyz; // sorted prefilter view
         DevBuf sort_temp;         // radix sort scratch
@@ -127,7 +127,7 @@ struct sccd_ctx {
     int comm_world = 0;                 // 0: no communicator attached (sccd_comm_create)
     struct SliceList {
         DevBuf samp_x, samp_yz, samp_id;      // every stride-th box of the WHOLE list (statistics)
-        DevBuf rec, rec_tmp, dest, dest_tmp;  // records of this rank's slice, then grouped by owner
+        DevBuf rec, rec_tmp;                  // records of this rank's slice, then grouped by owner
         DevBuf recv, recv_sorted;             // records of this rank's cell range, from every rank
         DevBuf part_temp, sort_temp;
         long long lo = 0, hi = 0;             // slice [lo, hi) of the list's boxes

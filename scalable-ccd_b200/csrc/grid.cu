@@ -198,22 +198,23 @@ __global__ void __launch_bounds__(1024) cell_splits_kernel(
 
 __global__ void __launch_bounds__(kThreads) expand_fill_kernel(
     BoxArrays boxes, int n, GridParams g, const unsigned long long* __restrict__ offsets,
-    uint32_t* __restrict__ keys, uint32_t* __restrict__ idx)
+    uint32_t idx_base, unsigned long long* __restrict__ rec)
 {
     const int i = blockIdx.x * kThreads + threadIdx.x;
     if (i >= n)
         return;
-    // multi-GPU: most boxes have no record in this rank's cell range -- 16 bytes instead of 64.
-    // (Measured and dropped: fusing count + scan + fill into one chained-scan pass; with
-    // 256-box tiles the look-back latency made it 40 % slower than the three passes.)
+    // multi-GPU (replicated build): most boxes have no record in this rank's cell range -- 16
+    // bytes instead of 64.  (Measured and dropped: fusing count + scan + fill into one
+    // chained-scan pass; with 256-box tiles the look-back latency made it 40 % slower.)
     if (offsets[i + 1] == offsets[i])
         return;
     int y0, y1, z0, z1;
     cell_range(ldg_d4(&boxes.yz[i]), g, y0, y1, z0, z1);
-    // key layout: common.cuh ("32-bit sweep key of a record")
+    // key layout: common.cuh ("32-bit sweep key of a record"); record = key << 32 | box index
     const uint32_t xq = quantize_x(__ldg(&boxes.x[i]).x, g) << kKeyFlagBits;
     const uint32_t type = __ldg(&boxes.id[i]).w < 0 ? kKeyFlagType : 0u;
     const int cell_shift = g.x_bits + kKeyFlagBits;
+    const unsigned long long idx = (unsigned long long)(idx_base + (uint32_t)i);
     unsigned long long o = offsets[i];
     for (int cy = y0; cy <= y1; cy++) {
         int a = z0, b = z1;
@@ -221,89 +222,23 @@ __global__ void __launch_bounds__(kThreads) expand_fill_kernel(
         for (int cz = a; cz <= b; cz++) {
             const uint32_t cell = (uint32_t)(cy * g.sz + cz);
             const uint32_t hi = cell_shift >= 32 ? 0u : (cell << cell_shift);
-            keys[o] = hi | xq | type | (cy == y0 ? kKeyFlagY : 0u) | (cz == z0 ? kKeyFlagZ : 0u);
-            idx[o] = (uint32_t)i;
-            o++;
-        }
-    }
-}
-
-// Multi-GPU sender side: one 64-bit record (key << 32 | global box index) per touched cell of
-// every box of this rank's SLICE of the list, plus the rank that owns the cell (cells are dealt
-// to the ranks in contiguous ranges, splits[0..world]).  idx_base: list index of the slice's
-// first box.
-__global__ void __launch_bounds__(kThreads) expand_fill_records_kernel(
-    BoxArrays boxes, int n, GridParams g, const unsigned long long* __restrict__ offsets,
-    uint32_t idx_base, const unsigned long long* __restrict__ splits, int world,
-    unsigned long long* __restrict__ rec, uint8_t* __restrict__ dest)
-{
-    const int i = blockIdx.x * kThreads + threadIdx.x;
-    if (i >= n)
-        return;
-    int y0, y1, z0, z1;
-    cell_range(ldg_d4(&boxes.yz[i]), g, y0, y1, z0, z1);
-    const uint32_t xq = quantize_x(__ldg(&boxes.x[i]).x, g) << kKeyFlagBits;
-    const uint32_t type = __ldg(&boxes.id[i]).w < 0 ? kKeyFlagType : 0u;
-    const int cell_shift = g.x_bits + kKeyFlagBits;
-    unsigned long long o = offsets[i];
-    for (int cy = y0; cy <= y1; cy++)
-        for (int cz = z0; cz <= z1; cz++) {
-            const uint32_t cell = (uint32_t)(cy * g.sz + cz);
-            const uint32_t hi = cell_shift >= 32 ? 0u : (cell << cell_shift);
             const uint32_t key =
                 hi | xq | type | (cy == y0 ? kKeyFlagY : 0u) | (cz == z0 ? kKeyFlagZ : 0u);
-            int d = 0;
-            while (d + 1 < world && (unsigned long long)cell >= splits[d + 1])
-                d++;
-            rec[o] = ((unsigned long long)key << 32) | (unsigned long long)(idx_base + (uint32_t)i);
-            dest[o] = (uint8_t)d;
-            o++;
+            rec[o++] = ((unsigned long long)key << 32) | idx;
         }
-}
-
-// send_count[d] = records of destination d in the dest-sorted array (first index with
-// dest > d, minus the first with dest >= d)
-__global__ void dest_counts_kernel(
-    const uint8_t* __restrict__ dest_sorted, unsigned long long m, int world,
-    unsigned long long* __restrict__ counts)
-{
-    const int d = threadIdx.x;
-    if (d >= world)
-        return;
-    auto lower = [&](int v) { // first index with dest >= v
-        unsigned long long a = 0, b = m;
-        while (a < b) {
-            const unsigned long long mid = (a + b) >> 1;
-            if ((int)dest_sorted[mid] < v)
-                a = mid + 1;
-            else
-                b = mid;
-        }
-        return a;
-    };
-    counts[d] = lower(d + 1) - lower(d);
+    }
 }
 
 } // namespace
 
 void launch_expand_fill_records(
     const BoxArrays& unsorted, int n, GridParams g, const unsigned long long* offsets,
-    uint32_t idx_base, const unsigned long long* splits, int world, unsigned long long* rec,
-    uint8_t* dest, cudaStream_t s, LaunchCounter& lc)
+    uint32_t idx_base, unsigned long long* rec, cudaStream_t s, LaunchCounter& lc)
 {
     if (n <= 0)
         return;
-    expand_fill_records_kernel<<<(n + kThreads - 1) / kThreads, kThreads, 0, s>>>(
-        unsorted, n, g, offsets, idx_base, splits, world, rec, dest);
-    SCCD_CUDA(cudaGetLastError());
-    lc.n++;
-}
-
-void launch_dest_counts(
-    const uint8_t* dest_sorted, unsigned long long m, int world, unsigned long long* counts,
-    cudaStream_t s, LaunchCounter& lc)
-{
-    dest_counts_kernel<<<1, 32, 0, s>>>(dest_sorted, m, world, counts);
+    expand_fill_kernel<<<(n + kThreads - 1) / kThreads, kThreads, 0, s>>>(
+        unsorted, n, g, offsets, idx_base, rec);
     SCCD_CUDA(cudaGetLastError());
     lc.n++;
 }
@@ -358,14 +293,9 @@ void launch_cell_splits(
 
 void launch_expand_fill(
     const BoxArrays& unsorted, int n, GridParams g, const unsigned long long* offsets,
-    uint32_t* keys, uint32_t* idx, cudaStream_t s, LaunchCounter& lc)
+    unsigned long long* rec, cudaStream_t s, LaunchCounter& lc)
 {
-    if (n <= 0)
-        return;
-    expand_fill_kernel<<<(n + kThreads - 1) / kThreads, kThreads, 0, s>>>(
-        unsorted, n, g, offsets, keys, idx);
-    SCCD_CUDA(cudaGetLastError());
-    lc.n++;
+    launch_expand_fill_records(unsorted, n, g, offsets, 0u, rec, s, lc);
 }
 
 } // namespace sccd

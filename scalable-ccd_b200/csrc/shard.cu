@@ -397,20 +397,17 @@ void build_boxes_sliced(sccd_ctx* c, double inflation_radius)
         const int cnt = (int)(S.hi - S.lo);
         const size_t m = (size_t)H.m;
         unsigned long long* rec = (unsigned long long*)S.rec.reserve(std::max<size_t>(m, 1) * 8);
-        uint8_t* dest = (uint8_t*)S.dest.reserve(std::max<size_t>(m, 1));
-        const unsigned long long* sp = d_splits + (size_t)k * (2 * kMaxWorld + 2);
         const size_t kt = kt_begin(c, &c->stats.ms_k_expand[k]);
         launch_expand_fill_records(
-            L.unsorted, cnt, g[k], L.offs.as<unsigned long long>(), (uint32_t)S.lo, sp, W, rec, dest,
-            st, c->lc);
+            L.unsorted, cnt, g[k], L.offs.as<unsigned long long>(), (uint32_t)S.lo, rec, st, c->lc);
         unsigned long long* cnt_out = d_xcnt + (size_t)rank * kXWords + (size_t)k * kMaxWorld;
-        if (W > 1 && m > 0) {
-            unsigned long long* rec2 = (unsigned long long*)S.rec_tmp.reserve(m * 8);
-            uint8_t* dest2 = (uint8_t*)S.dest_tmp.reserve(m);
+        if (W > 1) {
+            // stable partition by the rank that owns the record's cell: one digit pass
+            unsigned long long* rec2 = (unsigned long long*)S.rec_tmp.reserve(std::max<size_t>(m, 1) * 8);
             S.part_temp.reserve(partition_temp_bytes((long long)m));
             launch_partition_by_dest(
-                (long long)m, dest, dest2, rec, rec2, S.part_temp.ptr, S.part_temp.cap, st, c->lc);
-            launch_dest_counts(dest2, m, W, cnt_out, st, c->lc);
+                (long long)m, rec, rec2, 32 + kKeyFlagBits + g[k].x_bits, H.splits, W, cnt_out,
+                S.part_temp.ptr, S.part_temp.cap, st, c->lc);
             send_rec[k] = rec2;
         } else {
             SCCD_CUDA(cudaMemcpyAsync(cnt_out, &H.m, 8, cudaMemcpyHostToDevice, st));
@@ -566,6 +563,31 @@ void upload_mesh_sharded(
 using namespace sccd::host;
 
 extern "C" {
+
+int sccd_exchange_plan(
+    const uint64_t* counts, int list, int rank, int world, uint64_t* send_off, uint64_t* recv_cnt,
+    uint64_t* recv_off, uint64_t* recv_total)
+{
+    if (!counts || world < 1 || world > kMaxWorld || rank < 0 || rank >= world || list < 0 || list > 1)
+        return SCCD_ERR_ARG;
+    // same (rank x kXWords) layout the ranks all-gather: send counts of list 0, of list 1, flag
+    std::vector<unsigned long long> all((size_t)world * kXWords, 0ull);
+    for (int r = 0; r < world; r++)
+        for (int d = 0; d < world; d++)
+            all[(size_t)r * kXWords + list * kMaxWorld + d] = counts[(size_t)r * world + d];
+    const ExchangePlan p = exchange_plan(all.data(), list, rank, world);
+    for (int i = 0; i < world; i++) {
+        if (send_off)
+            send_off[i] = p.send_off[i];
+        if (recv_cnt)
+            recv_cnt[i] = p.recv_cnt[i];
+        if (recv_off)
+            recv_off[i] = p.recv_off[i];
+    }
+    if (recv_total)
+        *recv_total = p.recv_total;
+    return SCCD_OK;
+}
 
 int sccd_comm_get_unique_id(void* id_out)
 {

@@ -476,22 +476,6 @@ def test_cell_grid_does_not_change_the_overlap_set(sccd, orc, scene_c1, max_cell
         assert max(cells) <= max_cells
 
 
-def test_sharded_driver_on_one_gpu(sccd, orc, scene_small, torch_cuda):
-    """ShardedCCD (the N > 1 orchestration) degenerates to the plain pipeline at world size 1,
-    including the packed host-mesh entry; multi-rank runs are covered by tests/mgpu_check.py
-    (NCCL, on the GPU box) and tests/test_multigpu_host.py (gloo, host logic)."""
-    s = scene_small
-    c = sccd.Context(0, torch_cuda.cuda.current_stream().cuda_stream)
-    sh = sccd.multigpu.ShardedCCD(c)
-    flat, offs = sccd.multigpu.pack_mesh(s["V0"], s["V1"], s["E"], s["F"], 1)
-    sh.upload_mesh_host(flat, offs, (s["V0"].shape[0], s["E"].shape[0], s["F"].shape[0]))
-    want = orc.ccd(s)["toi"]
-    assert sh.ccd() == want
-    sh.profile = True
-    assert sh.ccd() == want and "ms" in sh.last
-    c.close()
-
-
 def test_update_vertices_equals_a_fresh_upload(ctx, sccd, orc, scene_small):
     """Frame-to-frame reuse: new positions for the uploaded topology give exactly what a
     fresh upload of the whole mesh gives (host arrays and device pointers)."""
