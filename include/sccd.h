@@ -109,6 +109,8 @@ typedef struct {
     float ms_k_round[2][5];  /* solver rounds (SCCD_OPT_PROFILE only)                           */
     float pad2_;
     int32_t key_bits[2];     /* sort-key bits in use (cell + quantised major axis) per list       */
+    int64_t n_skipped[2];    /* cull survivors never started: their toi lower bound was not below
+                                the running earliest toi (shared-bound mode, max_iter < 0)        */
 } sccd_stats;
 /* sizeof(sccd_stats) of the library (binding sanity check) */
 size_t sccd_stats_size(void);
@@ -168,6 +170,19 @@ int sccd_set_scalar_type(sccd_ctx* ctx, int type);
 #define SCCD_OPT_KEY_STEPS 6        /* log2 of the major-axis quantisation steps per record     */
 #define SCCD_OPT_GRID_SCALE_MILLI 7 /* cell edge in mean box extents, x 1000 (default 3000)     */
 #define SCCD_OPT_GRID_REPL_MILLI 8  /* records per box above which the grid is coarsened, x1000 */
+#define SCCD_OPT_NARROW_SOLVER 11   /* how the solver schedules the bisection trees:
+                                       0 = by the length of the work list -- one lane per tree,
+                                           cut into rounds (long lists); one warp per tree in a
+                                           persistent work queue (short lists);
+                                       1 = rounds for short lists as well;
+                                       4 / 8 = that many lanes per tree, one kernel per round.
+                                       Results never depend on it.                               */
+#define SCCD_OPT_CONCURRENT_PASSES 12 /* plain ccd(): 1 = the edge-edge solver starts as soon as its
+                                       own list is ready instead of after the vertex-face solver
+                                       (whose earliest toi it would inherit as its pruning bound).
+                                       Both publish to the same toi word, so each still profits
+                                       from the other's finds; the result is the same, the work
+                                       can be more.  0 = in sequence (default).                  */
 #define SCCD_OPT_PROFILE 10         /* 1: time every solver round with its own event pair
                                        (sccd_stats.ms_k_round); 0 (default): stage timers only */
 #define SCCD_OPT_SWEEP_AXIS 9       /* axis the mesh pipeline sorts and sweeps along: 0 (default,

@@ -18,7 +18,8 @@ VF, EE, BOXES = 0, 1, 2
 F64, F32 = 0, 1  # sccd_set_scalar_type: the reference's SCALABLE_CCD_USE_DOUBLE switch
 OK, ERR_CUDA, ERR_ARG, ERR_STATE, ERR_MEMORY = 0, -1, -2, -3, -4
 (OPT_NARROW_CULL, OPT_NARROW_FLAGS, OPT_NARROW_FLAGS_EE, OPT_NARROW_MAX_DEPTH, OPT_MAX_ITER_MODE,
- OPT_KEY_STEPS, OPT_GRID_SCALE_MILLI, OPT_GRID_REPL_MILLI, OPT_SWEEP_AXIS, OPT_PROFILE) = range(1, 11)
+ OPT_KEY_STEPS, OPT_GRID_SCALE_MILLI, OPT_GRID_REPL_MILLI, OPT_SWEEP_AXIS, OPT_PROFILE,
+ OPT_NARROW_SOLVER, OPT_CONCURRENT_PASSES) = range(1, 13)
 UNIQUE_ID_BYTES = 128
 
 AABB_DTYPE = np.dtype(
@@ -59,7 +60,7 @@ class Stats(C.Structure):
         ("n_records_sent", C.c_int64 * 2), ("n_records_received", C.c_int64 * 2),
         ("ms_exchange", C.c_float), ("ms_k_sort", C.c_float * 2), ("ms_k_expand", C.c_float * 2),
         ("ms_k_cull", C.c_float * 2), ("ms_k_round", (C.c_float * 5) * 2), ("pad2_", C.c_float),
-        ("key_bits", C.c_int32 * 2),
+        ("key_bits", C.c_int32 * 2), ("n_skipped", C.c_int64 * 2),
     ]
 
     def as_dict(self):

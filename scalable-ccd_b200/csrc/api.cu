@@ -57,7 +57,17 @@ namespace host {
 
 
 
-void record(sccd_ctx* c, int which) { SCCD_CUDA(cudaEventRecord(c->ev[which], c->stream)); }
+// Stage / kernel timers are opt-in (SCCD_OPT_PROFILE): a 1 ms step is made of ~50 launches, and
+// ~40 more event records were a sixth of the host's work per step.  Only the total is always timed.
+inline bool timed_event(const sccd_ctx* c, int which)
+{
+    return c->opt.profile || which == EV_T0 || which == EV_T1 || which == EV_TMPA || which == EV_TMPB;
+}
+void record(sccd_ctx* c, int which)
+{
+    if (timed_event(c, which))
+        SCCD_CUDA(cudaEventRecord(c->ev[which], c->stream));
+}
 float elapsed(sccd_ctx* c, int a, int b)
 {
     float ms = 0.f;
@@ -82,6 +92,8 @@ size_t kt_alloc(sccd_ctx* c, float* dst)
 }
 size_t kt_begin(sccd_ctx* c, float* dst, cudaStream_t st)
 {
+    if (!c->opt.profile)
+        return (size_t)-1;
     const size_t id = kt_alloc(c, dst);
     c->ktimers[id].st = st ? st : c->cur->stream;
     SCCD_CUDA(cudaEventRecord(c->ktimers[id].a, c->ktimers[id].st));
@@ -89,6 +101,8 @@ size_t kt_begin(sccd_ctx* c, float* dst, cudaStream_t st)
 }
 void kt_end(sccd_ctx* c, size_t id)
 {
+    if (id == (size_t)-1)
+        return;
     SCCD_CUDA(cudaEventRecord(c->ktimers[id].b, c->ktimers[id].st));
 }
 void kt_resolve(sccd_ctx* c)
@@ -434,8 +448,10 @@ void sort_list_finish(
     const int slot = which == 1 ? 1 : 0;
     c->stats.key_bits[slot] = cell_bits + g.x_bits;
     const size_t kt_e = kt_begin(c, &c->stats.ms_k_expand[slot], st);
+    uint32_t* sort_hist = launch_sort_prepare(L.sort_temp.ptr, L.sort_temp.cap, (long long)m, st);
     launch_expand_fill(
-        L.unsorted, n, g, L.offs.as<unsigned long long>(), L.keys.as<unsigned long long>(), st, c->lc);
+        L.unsorted, n, g, L.offs.as<unsigned long long>(), L.keys.as<unsigned long long>(), sort_hist,
+        cell_bits + g.x_bits, st, c->lc);
     kt_end(c, kt_e);
     // (radix passes = from here to the gather's begin event; resolved in finish_stats)
     if (ga)
@@ -443,7 +459,7 @@ void sort_list_finish(
     launch_sort_and_gather(
         (int)m, cell_bits + g.x_bits, L.keys.as<unsigned long long>(),
         L.keys_tmp.as<unsigned long long>(), L.sort_temp.ptr, L.sort_temp.cap, L.unsorted, L.sorted,
-        st, c->lc, ga, gb);
+        st, c->lc, ga, gb, /*hist_ready=*/true);
 }
 
 // one list on its own (caller-made boxes; re-sharding an already built list)
@@ -528,13 +544,15 @@ void build_boxes(sccd_ctx* c, double inflation_radius)
     sort_list_begin(c, 0);
     sort_list_begin(c, 1);
     host_sync(c, c->stream);
-    sort_list_finish(c, 0, c->ev[EV_GA0], c->ev[EV_GB0]);
+    const bool prof = c->opt.profile != 0;
+    sort_list_finish(c, 0, prof ? c->ev[EV_GA0] : nullptr, prof ? c->ev[EV_GB0] : nullptr);
     // (if the grid of list 1 has to be coarsened, its retry runs -- and syncs -- on the main
     // stream before anything is enqueued on the sort stream)
-    sort_list_finish(c, 1, c->ev[EV_GA1], c->ev[EV_GB1], c->sort_stream);
+    sort_list_finish(
+        c, 1, prof ? c->ev[EV_GA1] : nullptr, prof ? c->ev[EV_GB1] : nullptr, c->sort_stream);
     SCCD_CUDA(cudaEventRecord(c->ev_sorted1, c->sort_stream));
     c->sort1_pending = true;
-    c->gather_timed = true;
+    c->gather_timed = prof;
     record(c, EV_SORT);
     c->have_boxes = true;
     c->runs[0].bp_kind = c->runs[1].bp_kind = -1;
@@ -623,7 +641,11 @@ void small_scratch(sccd_ctx* c)
         SCCD_CUDA(cudaMallocHost((void**)&R.h_small, 256));
 }
 
-void rrecord(sccd_ctx* c, int which) { SCCD_CUDA(cudaEventRecord(c->ev[which], c->cur->stream)); }
+void rrecord(sccd_ctx* c, int which)
+{
+    if (timed_event(c, which))
+        SCCD_CUDA(cudaEventRecord(c->ev[which], c->cur->stream));
+}
 
 // BroadPhase::build: choose the list, the owner slice of this rank, enqueue the count pass,
 // the scan and the D2H of the totals.  broad_phase_begin_finish() waits for them.
@@ -804,8 +826,14 @@ void narrow_setup(sccd_ctx* c, long long n_queries)
         : std::min<long long>(std::max<long long>(n_queries, 1 << 20), 1 << 24);
     cap = std::max<long long>(cap, 64);
     if ((unsigned long long)cap != R.item_cap || !R.b_items[0].ptr) {
-        R.b_items[0].reserve((size_t)cap * sizeof(WorkItem));
-        R.b_items[1].reserve((size_t)cap * sizeof(WorkItem));
+        for (int i = 0; i < 2; i++) {
+            const void* before = R.b_items[i].ptr;
+            R.b_items[i].reserve((size_t)cap * sizeof(WorkItem));
+            // fresh memory: no slot may carry the ready mark of a work-queue launch by accident
+            // (the marks are launch numbers, never zero: narrow.cu Round0::epoch)
+            if (R.b_items[i].ptr != before)
+                SCCD_CUDA(cudaMemsetAsync(R.b_items[i].ptr, 0, R.b_items[i].cap, R.stream));
+        }
         R.item_cap = (unsigned long long)cap;
     }
 }
@@ -816,11 +844,13 @@ void narrow_setup(sccd_ctx* c, long long n_queries)
 // d_gtoi: device word holding the running earliest toi (shared by concurrent batches).
 void narrow_enqueue(
     sccd_ctx* c, int kind, const NarrowInput& in, double ms, int max_iter, double tol,
-    bool allow_zero_toi, double* d_gtoi, double* d_toi_per_query)
+    bool allow_zero_toi, double* d_gtoi, double* d_toi_per_query, cudaEvent_t solver_waits_for)
 {
     auto& R = *c->cur;
     cudaStream_t st = R.stream;
     R.pending.active = false;
+    if (in.n <= 0 && solver_waits_for) // nothing to launch, but keep the streams ordered
+        SCCD_CUDA(cudaStreamWaitEvent(st, solver_waits_for, 0));
     c->stats.n_queries[kind] += in.n;
     if (in.n <= 0)
         return;
@@ -844,6 +874,7 @@ void narrow_enqueue(
     P.flags = (kind == SCCD_EE && c->opt.np_flags_ee >= 0) ? c->opt.np_flags_ee : c->opt.np_flags;
     P.max_depth = c->opt.np_depth;
     P.cap_drops = c->opt.cap_drops;
+    P.solver = c->opt.np_solver;
     SCCD_CUDA(cudaMemsetAsync(R.b_counters.ptr, 0, sizeof(NarrowCounters), st));
     if (d_toi_per_query)
         launch_fill_f64(d_toi_per_query, in.n, INFINITY, st, c->lc);
@@ -855,12 +886,18 @@ void narrow_enqueue(
         R.checks_n = in.n;
     }
     // separating-axis cull in front of the solver (SCCD_NP_CULL=0 switches it off: A/B, tests)
-    uint32_t* survivors = nullptr;
-    if (c->opt.np_cull)
-        survivors = (uint32_t*)R.b_surv.reserve((size_t)in.n * 4);
+    // survivor records of the cull (two buffers: as written, and sorted by lower-bound bucket),
+    // every survivor's toi lower bound, and the scratch of that one-pass sort
+    unsigned long long* survivors = nullptr;
+    float* tlb = nullptr;
+    if (c->opt.np_cull) {
+        survivors = (unsigned long long*)R.b_surv.reserve((size_t)in.n * 16);
+        tlb = (float*)R.b_tlb.reserve((size_t)in.n * 4);
+        R.b_surv_sort.reserve(sort_survivors_temp_bytes(in.n));
+    }
     // kernel-level timers: the cull always, every solver round with SCCD_OPT_PROFILE
     cudaEvent_t tev[2 * (1 + kNarrowRounds)] = {};
-    if (survivors) {
+    if (survivors && c->opt.profile) {
         const size_t id = kt_alloc(c, &c->stats.ms_k_cull[kind]);
         tev[0] = c->ktimers[id].a, tev[1] = c->ktimers[id].b;
     }
@@ -873,7 +910,8 @@ void narrow_enqueue(
     launch_narrow_phase(
         kind == SCCD_VF, c->f32, in, P, R.b_counters.as<NarrowCounters>(), d_gtoi,
         R.b_items[0].as<WorkItem>(), R.b_items[1].as<WorkItem>(), R.item_cap, d_toi_per_query,
-        checks, survivors, c->num_sms, st, c->lc, tev);
+        checks, survivors, tlb, R.b_surv_sort.ptr, R.b_surv_sort.cap, c->num_sms, st, c->lc, tev,
+        solver_waits_for);
     kt_end(c, kt);
     SCCD_CUDA(cudaMemcpyAsync(
         R.h_counters, R.b_counters.ptr, sizeof(NarrowCounters), cudaMemcpyDeviceToHost, st));
@@ -912,8 +950,10 @@ void narrow_finish(sccd_ctx* c, double* d_gtoi)
     }
     const NarrowCounters& r = *R.h_counters;
     c->stats.n_box_checks[kind] += (int64_t)r.box_checks;
-    if (R.pending.culling)
+    if (R.pending.culling) {
         c->stats.n_culled[kind] += R.pending.in.n - (int64_t)r.n_items[0];
+        c->stats.n_skipped[kind] += (int64_t)r.n_items[0] - (int64_t)r.started;
+    }
     c->stats.n_donated[kind] += (int64_t)r.donated;
     for (int i = 0; i <= kNarrowRounds; i++) {
         unsigned long long n = r.n_items[i];
@@ -958,7 +998,7 @@ void narrow_run(
     if (c->f32) // Scalar& toi of the float build
         *toi_inout = (double)(float)*toi_inout;
     double* d_gtoi = gtoi_set(c, *toi_inout, c->cur->stream);
-    narrow_enqueue(c, kind, in, ms, max_iter, tol, allow_zero_toi, d_gtoi, d_toi_per_query);
+    narrow_enqueue(c, kind, in, ms, max_iter, tol, allow_zero_toi, d_gtoi, d_toi_per_query, nullptr);
     if (!c->cur->pending.active)
         return;
     narrow_finish(c, d_gtoi);
@@ -1005,6 +1045,9 @@ void finish_stats(sccd_ctx* c, bool pipeline)
     if (!pipeline)
         return;
     SCCD_CUDA(cudaEventSynchronize(c->ev[EV_T1]));
+    c->stats.ms_total = elapsed(c, EV_T0, EV_T1);
+    if (!c->opt.profile)
+        return;
     c->stats.ms_build = elapsed(c, EV_T0, EV_BUILD);
     c->stats.ms_sort = elapsed(c, EV_BUILD, EV_SORT);
     c->stats.ms_sweep[0] = elapsed(c, EV_SW0A, EV_SW0B);
@@ -1075,15 +1118,16 @@ void run_pipeline(
                 const sccd_pair* d_pairs = nullptr;
                 int64_t n = 0;
                 broad_phase_partial(c, &d_pairs, &n);
-                if (first) {
-                    if (kind == SCCD_EE) // after the vertex-face narrow phase and the toi word
-                        SCCD_CUDA(cudaStreamWaitEvent(c->cur->stream, c->ev_vf_done, 0));
+                if (first)
                     rrecord(c, kind == SCCD_VF ? EV_NP0A : EV_NP1A);
-                }
-                first = false;
+                // The edge-edge SOLVER starts after the vertex-face narrow phase, so that it
+                // prunes with its earliest toi; the edge-edge cull and the sort of its survivors
+                // need no bound and run before that wait, under the vertex-face work.
                 narrow_enqueue(
                     c, kind, mesh_input(c, d_pairs, n), min_distance, max_iter, tol,
-                    allow_zero_toi, d_gtoi, nullptr);
+                    allow_zero_toi, d_gtoi, nullptr,
+                    (first && kind == SCCD_EE && !c->opt.concurrent_passes) ? c->ev_vf_done : nullptr);
+                first = false;
                 any_batch = any_batch || c->cur->pending.active;
             }
             rrecord(c, kind == SCCD_VF ? EV_NP0B : EV_NP1B);
@@ -1228,6 +1272,10 @@ int sccd_create(int device, void* stream, sccd_ctx** out)
             c->opt.np_cull = atoi(e) != 0;
         if (const char* e = getenv("SCCD_KEY_STEPS"))
             c->opt.key_steps = std::min(16, std::max(0, atoi(e)));
+        if (const char* e = getenv("SCCD_CONCURRENT_PASSES"))
+            c->opt.concurrent_passes = atoi(e) != 0;
+        if (const char* e = getenv("SCCD_NP_SOLVER"))
+            c->opt.np_solver = (atoi(e) == 1 || atoi(e) == 4 || atoi(e) == 8) ? atoi(e) : 0;
         if (const char* e = getenv("SCCD_SWEEP_AXIS"))
             c->opt.sweep_axis = std::min(2, std::max(-1, atoi(e)));
         narrow_init_device();
@@ -1342,6 +1390,12 @@ int sccd_set_option(sccd_ctx* ctx, int option, int64_t value)
         ctx->grid_repl = (double)value / 1000.0;
         break;
     case SCCD_OPT_PROFILE: o.profile = value != 0; break;
+    case SCCD_OPT_CONCURRENT_PASSES: o.concurrent_passes = value != 0; break;
+    case SCCD_OPT_NARROW_SOLVER:
+        if (value != 0 && value != 1 && value != 4 && value != 8)
+            return SCCD_ERR_ARG;
+        o.np_solver = (int)value;
+        break;
     case SCCD_OPT_SWEEP_AXIS:
         if (value < -1 || value > 2)
             return SCCD_ERR_ARG;
@@ -1374,6 +1428,8 @@ int sccd_get_option(const sccd_ctx* ctx, int option, int64_t* value)
     case SCCD_OPT_GRID_REPL_MILLI: *value = (int64_t)std::llround(ctx->grid_repl * 1000.0); break;
     case SCCD_OPT_SWEEP_AXIS: *value = o.sweep_axis; break;
     case SCCD_OPT_PROFILE: *value = o.profile; break;
+    case SCCD_OPT_NARROW_SOLVER: *value = o.np_solver; break;
+    case SCCD_OPT_CONCURRENT_PASSES: *value = o.concurrent_passes; break;
     default: return SCCD_ERR_ARG;
     }
     return SCCD_OK;

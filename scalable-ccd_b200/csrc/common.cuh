@@ -247,6 +247,8 @@ struct NarrowParams {
     int flags;      // debug knobs (SCCD_NP_FLAGS env), see narrow.cu
     int max_depth;  // levels a walk may track before handing on (<= 128)
     int cap_drops;  // max_iter reached: 0 = accept the box at t_lo (conservative), 1 = drop it
+    int solver;     // 0: by list length -- lane per tree in rounds (long), persistent work queue
+                    // (short); 1: rounds for short lists too; 4, 8: lanes per tree (group solver)
     // Multi-GPU (sccd_ccd_sharded): the earliest-toi words of the OTHER ranks, mapped into this
     // rank's address space over NVLink (CUDA IPC, shard.cu).  A lane that lowers the bound also
     // lowers it on every peer with a system-scope atomicMin, so all ranks prune with the global
@@ -277,17 +279,23 @@ struct alignas(128) NarrowCounters {
     alignas(128) unsigned long long n_items[kNarrowRounds + 1]; // [r] = items round r reads
     // [r] != 0: the list round r reads was closed at item ~closed[r] (narrow.cu reserve_items)
     alignas(128) unsigned long long closed[kNarrowRounds + 1];
+    alignas(128) unsigned long long next_scout;       // claim counter of round 0's scout launch
+    // persistent work queues of a short list (narrow_coop_kernel<QUEUE>; [0] scout launch, [1]
+    // bulk launch): tickets taken / slots pushed of the item list, "closed at" marker, and the
+    // items being worked on or queued
+    struct alignas(128) Queue {
+        alignas(128) unsigned long long head;
+        alignas(128) unsigned long long tail;
+        unsigned long long closed;
+        alignas(128) unsigned long long outstanding;
+    } queue[2];
     alignas(128) int overflow;                        // an item list was full (work kept local)
     int bad_input;                                    // a pair id is no element of the mesh
     unsigned long long box_checks;
     unsigned long long round_checks[kNarrowRounds]; // box checks per round (load-balance report)
     unsigned long long donated;
     unsigned long long capped;
-    // Longest-first claim order (flag bit 23): the cull writes survivors whose swept hulls overlap
-    // (likely real contacts = deep trees) from the front of the survivor list and the others
-    // from its back, so that round 0 claims the long trees first.  n_items[0] stays the total.
-    alignas(128) unsigned long long n_front; // survivors written at [0, n_front)
-    alignas(128) unsigned long long n_back;  // survivors written at [n - n_back, n)
+    unsigned long long started;  // trees round 0 started (survivors - started were skipped)
 };
 
 // ---- kernel launchers (defined in the .cu files) -----------------------------------
@@ -337,9 +345,11 @@ void launch_cell_splits(
     const BoxArrays& unsorted, int n, int stride, GridParams g, int world, uint32_t* hist,
     unsigned long long* out, cudaStream_t s, LaunchCounter& lc);
 // one 64-bit record (key << 32 | idx_base + box index) per touched cell, at offsets[i] ...
+// sort_hist (launch_sort_prepare): the digit histograms of the sort on key_bits that follows
 void launch_expand_fill(
     const BoxArrays& unsorted, int n, GridParams g, const unsigned long long* offsets,
-    unsigned long long* rec, cudaStream_t s, LaunchCounter& lc);
+    unsigned long long* rec, uint32_t* sort_hist, int key_bits, cudaStream_t s, LaunchCounter& lc);
+uint32_t* launch_sort_prepare(void* temp, size_t temp_bytes, long long m, cudaStream_t s);
 
 // ---- multi-GPU build (shard.cu): slice / sample boxes, records, partition, rebuild
 struct MeshView;
@@ -367,7 +377,8 @@ size_t sort_temp_bytes(long long m);
 void launch_sort_and_gather(
     int m, int key_bits, unsigned long long* rec, unsigned long long* rec_tmp, void* temp,
     size_t temp_bytes, BoxArrays unsorted, SortedList out, cudaStream_t s, LaunchCounter& lc,
-    cudaEvent_t gather_begin = nullptr, cudaEvent_t gather_end = nullptr);
+    cudaEvent_t gather_begin = nullptr, cudaEvent_t gather_end = nullptr,
+    bool hist_ready = false /* launch_sort_prepare + launch_expand_fill made the histograms */);
 
 // window[i] = number of candidates after owner i whose f32 xmin <= owner's f32 xmax
 void launch_sweep_windows(
@@ -421,9 +432,16 @@ struct NarrowInput {
 void launch_narrow_phase(
     bool is_vf, bool f32, const NarrowInput& in, const NarrowParams& p, NarrowCounters* counters,
     double* g_toi, WorkItem* items0, WorkItem* items1, unsigned long long item_cap, double* toi_per_query,
-    unsigned int* checks_per_query, uint32_t* survivors /* in.n words, or null: no cull */,
-    int num_sms, cudaStream_t s, LaunchCounter& lc,
-    const cudaEvent_t* tev = nullptr /* 2 * (1 + kNarrowRounds) optional timing events */);
+    unsigned int* checks_per_query,
+    unsigned long long* survivors /* 2 * in.n records, or null: no cull */,
+    float* tlb /* in.n: lower bound of every surviving query's toi */, void* sort_temp,
+    size_t sort_temp_bytes, int num_sms, cudaStream_t s, LaunchCounter& lc,
+    const cudaEvent_t* tev = nullptr /* 2 * (1 + kNarrowRounds) optional timing events */,
+    cudaEvent_t solver_waits_for = nullptr /* the rounds (not the cull) start after this event */);
+size_t sort_survivors_temp_bytes(long long n_max);
+void launch_sort_survivors(
+    const unsigned long long* rec, unsigned long long* rec_out, const unsigned long long* d_n,
+    long long n_max, void* temp, size_t temp_bytes, cudaStream_t s, LaunchCounter& lc);
 // moves n_items[kNarrowRounds] to n_items[kNarrowRounds - 1] and reruns the last round
 void launch_narrow_extra_round(
     bool is_vf, bool f32, const NarrowInput& in, const NarrowParams& p, NarrowCounters* counters,

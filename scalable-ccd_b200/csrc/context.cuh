@@ -88,6 +88,8 @@ struct sccd_ctx {
         int key_steps = 3;      // log2 of the x quantisation steps per record of a cell
         int sweep_axis = 0;     // 0/1/2, or -1: variance argmax of the previous build
         int profile = 0;        // time every solver round (sccd_stats.ms_k_round)
+        int np_solver = 0;      // 0: lane / warp per tree by list length; 4, 8: lanes per tree
+        int concurrent_passes = 0; // edge-edge solver does not wait for the vertex-face one
     } opt;
     int next_axis = 0;          // argmax of the box-centre variance of the last build
 
@@ -103,7 +105,7 @@ struct sccd_ctx {
         DevBuf b_counts, b_offsets, b_scan, b_pairs, b_small;
         DevBuf b_stage_pairs, b_stage_tags, b_stage_count; // count pass -> place pass
         int* h_small = nullptr; // pinned scratch for tiny D2H results
-        DevBuf b_counters, b_items[2], b_toi_q, b_checks_q, b_queries, b_surv;
+        DevBuf b_counters, b_items[2], b_toi_q, b_checks_q, b_queries, b_surv, b_tlb, b_surv_sort;
         NarrowCounters* h_counters = nullptr; // pinned
         unsigned long long item_cap = 0; // capacity of each of the two hand-on lists
         long long checks_n = 0;          // queries of the last batch that counted its checks

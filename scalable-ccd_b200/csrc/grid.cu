@@ -196,13 +196,12 @@ __global__ void __launch_bounds__(1024) cell_splits_kernel(
     }
 }
 
-__global__ void __launch_bounds__(kThreads) expand_fill_kernel(
-    BoxArrays boxes, int n, GridParams g, const unsigned long long* __restrict__ offsets,
-    uint32_t idx_base, unsigned long long* __restrict__ rec)
+template <bool HIST>
+__device__ __forceinline__ void expand_fill_one(
+    const BoxArrays& boxes, int i, const GridParams& g, const unsigned long long* __restrict__ offsets,
+    uint32_t idx_base, unsigned long long* __restrict__ rec, uint32_t* h, int hist_shift,
+    int hist_passes, int hist_top)
 {
-    const int i = blockIdx.x * kThreads + threadIdx.x;
-    if (i >= n)
-        return;
     // multi-GPU (replicated build): most boxes have no record in this rank's cell range -- 16
     // bytes instead of 64.  (Measured and dropped: fusing count + scan + fill into one
     // chained-scan pass; with 256-box tiles the look-back latency made it 40 % slower.)
@@ -224,8 +223,40 @@ __global__ void __launch_bounds__(kThreads) expand_fill_kernel(
             const uint32_t hi = cell_shift >= 32 ? 0u : (cell << cell_shift);
             const uint32_t key =
                 hi | xq | type | (cy == y0 ? kKeyFlagY : 0u) | (cz == z0 ? kKeyFlagZ : 0u);
-            rec[o++] = ((unsigned long long)key << 32) | idx;
+            const unsigned long long r = ((unsigned long long)key << 32) | idx;
+            rec[o++] = r;
+            if (HIST)
+                for (int p = 0; p < hist_passes; p++) {
+                    const uint32_t mask = p == hist_passes - 1 ? ((1u << hist_top) - 1u) : 255u;
+                    atomicAdd(&h[p * 256 + ((uint32_t)(r >> (hist_shift + 8 * p)) & mask)], 1u);
+                }
         }
+    }
+}
+
+// hist (optional): the digit histograms of the radix sort that follows (sort.cu), built here while
+// the keys are in registers -- one launch and one read of the records less on the critical path.
+// hist_passes digits of 8 bits from bit hist_shift of the 64-bit record, the top one hist_top wide.
+template <bool HIST>
+__global__ void __launch_bounds__(kThreads) expand_fill_kernel(
+    BoxArrays boxes, int n, GridParams g, const unsigned long long* __restrict__ offsets,
+    uint32_t idx_base, unsigned long long* __restrict__ rec, uint32_t* __restrict__ hist,
+    int hist_shift, int hist_passes, int hist_top)
+{
+    __shared__ uint32_t h[HIST ? 4 * 256 : 1];
+    if (HIST) {
+        for (int j = threadIdx.x; j < 4 * 256; j += kThreads)
+            h[j] = 0;
+        __syncthreads();
+    }
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i < n)
+        expand_fill_one<HIST>(boxes, i, g, offsets, idx_base, rec, h, hist_shift, hist_passes, hist_top);
+    if (HIST) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < hist_passes * 256; j += kThreads)
+            if (h[j])
+                atomicAdd(&hist[j], h[j]);
     }
 }
 
@@ -237,8 +268,8 @@ void launch_expand_fill_records(
 {
     if (n <= 0)
         return;
-    expand_fill_kernel<<<(n + kThreads - 1) / kThreads, kThreads, 0, s>>>(
-        unsorted, n, g, offsets, idx_base, rec);
+    expand_fill_kernel<false><<<(n + kThreads - 1) / kThreads, kThreads, 0, s>>>(
+        unsorted, n, g, offsets, idx_base, rec, nullptr, 0, 0, 0);
     SCCD_CUDA(cudaGetLastError());
     lc.n++;
 }
@@ -293,9 +324,18 @@ void launch_cell_splits(
 
 void launch_expand_fill(
     const BoxArrays& unsorted, int n, GridParams g, const unsigned long long* offsets,
-    unsigned long long* rec, cudaStream_t s, LaunchCounter& lc)
+    unsigned long long* rec, uint32_t* sort_hist, int key_bits, cudaStream_t s, LaunchCounter& lc)
 {
-    launch_expand_fill_records(unsorted, n, g, offsets, 0u, rec, s, lc);
+    if (n <= 0)
+        return;
+    // digits of the sort that follows: key bits [kKeyFlagBits, kKeyFlagBits + key_bits) of the
+    // record's high word (sort.cu: launch_sort_and_gather)
+    const int passes = (key_bits + 7) / 8;
+    expand_fill_kernel<true><<<(n + kThreads - 1) / kThreads, kThreads, 0, s>>>(
+        unsorted, n, g, offsets, 0u, rec, sort_hist, 32 + kKeyFlagBits, passes,
+        key_bits - 8 * (passes - 1));
+    SCCD_CUDA(cudaGetLastError());
+    lc.n++;
 }
 
 } // namespace sccd

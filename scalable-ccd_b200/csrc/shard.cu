@@ -446,7 +446,8 @@ void build_boxes_sliced(sccd_ctx* c, double inflation_radius)
     // (NCCL orders the two groups on the communicator; every rank issues them in this order).
     SCCD_CUDA(cudaEventRecord(c->ev_counts, st)); // everything the senders made is on `st`
     SCCD_CUDA(cudaStreamWaitEvent(c->sort_stream, c->ev_counts, 0));
-    SCCD_CUDA(cudaEventRecord(c->ev_xa, st));
+    if (c->opt.profile)
+        SCCD_CUDA(cudaEventRecord(c->ev_xa, st));
     for (int k = 0; k < 2; k++) {
         cudaStream_t sk = k == 0 ? st : c->sort_stream;
         const ExchangePlan& P = plan[k];
@@ -470,7 +471,8 @@ void build_boxes_sliced(sccd_ctx* c, double inflation_radius)
         if (W > 1)
             SCCD_NCCL(nccl().GroupEnd());
     }
-    SCCD_CUDA(cudaEventRecord(c->ev_xb, c->sort_stream));
+    if (c->opt.profile)
+        SCCD_CUDA(cudaEventRecord(c->ev_xb, c->sort_stream));
 
     // ---- 6. per list: sort the received records, rebuild their exact boxes.  The edge list on
     // the sort stream, under the vertex-face sweep and narrow phase (as build_boxes).
@@ -495,15 +497,18 @@ void build_boxes_sliced(sccd_ctx* c, double inflation_radius)
         L.sorted.pf.yz = (float4*)L.pyz.reserve(mm * sizeof(float4));
         unsigned long long* sorted_rec = (unsigned long long*)S.recv_sorted.reserve(mm * 8);
         S.sort_temp.reserve(sort_records_temp_bytes((long long)plan[k].recv_total));
-        SCCD_CUDA(cudaEventRecord(c->ev[k == 0 ? EV_SB0 : EV_SB1], sk));
+        const bool prof = c->opt.profile != 0;
+        if (prof)
+            SCCD_CUDA(cudaEventRecord(c->ev[k == 0 ? EV_SB0 : EV_SB1], sk));
         launch_sort_records_and_rebuild(
             (int)plan[k].recv_total, cell_bits[k] + gk.x_bits, recv[k], sorted_rec, S.sort_temp.ptr,
-            S.sort_temp.cap, mv, k, L.axis, L.sorted, sk, c->lc, c->ev[k == 0 ? EV_GA0 : EV_GA1],
-            c->ev[k == 0 ? EV_GB0 : EV_GB1]);
+            S.sort_temp.cap, mv, k, L.axis, L.sorted, sk, c->lc,
+            prof ? c->ev[k == 0 ? EV_GA0 : EV_GA1] : nullptr,
+            prof ? c->ev[k == 0 ? EV_GB0 : EV_GB1] : nullptr);
     }
     SCCD_CUDA(cudaEventRecord(c->ev_sorted1, c->sort_stream));
     c->sort1_pending = true;
-    c->gather_timed = true;
+    c->gather_timed = c->opt.profile != 0;
     record(c, EV_SORT);
     c->have_boxes = true;
     c->sliced = true;

@@ -87,12 +87,16 @@ __global__ void __launch_bounds__(kThreads) radix_hist_kernel(
         if (h[i])
             atomicAdd(&hist[i], h[i]);
 }
+// (d_n, where given: the record count lives on the device -- n is then only its upper bound)
 template <typename Digit>
 __global__ void __launch_bounds__(kThreads) digit_hist_kernel(
-    const unsigned long long* __restrict__ rec, long long n, Digit digit, uint32_t* __restrict__ hist)
+    const unsigned long long* __restrict__ rec, long long n, Digit digit, uint32_t* __restrict__ hist,
+    const unsigned long long* __restrict__ d_n)
 {
     __shared__ uint32_t h[kRadix];
     h[threadIdx.x] = 0;
+    if (d_n)
+        n = min(n, (long long)*d_n);
     __syncthreads();
     const long long stride = (long long)gridDim.x * kThreads;
     for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride)
@@ -116,7 +120,8 @@ template <typename Digit>
 __global__ void __launch_bounds__(kThreads) radix_pass_kernel(
     const unsigned long long* __restrict__ in, unsigned long long* __restrict__ out, long long n,
     Digit digit, const uint32_t* __restrict__ hist /* 256: this pass */,
-    uint32_t* __restrict__ status, uint32_t* __restrict__ ctr)
+    uint32_t* __restrict__ status, uint32_t* __restrict__ ctr,
+    const unsigned long long* __restrict__ d_n)
 {
     __shared__ SortSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -124,9 +129,13 @@ __global__ void __launch_bounds__(kThreads) radix_pass_kernel(
         sm.tile = atomicAdd(ctr, 1u); // tiles start in ticket order: look-back cannot deadlock
     for (int i = tid; i < (kThreads / 32) * kRadix; i += kThreads)
         (&sm.warp_hist[0][0])[i] = 0;
+    if (d_n)
+        n = min(n, (long long)*d_n);
     __syncthreads();
     const uint32_t tile = sm.tile;
     const long long tile0 = (long long)tile * kSortTile;
+    if (tile0 >= n)
+        return; // (launched for the upper bound of a device-side count)
     const int tile_n = (int)min((long long)kSortTile, n - tile0);
 
     // ---- load (warp-striped: item i of lane l is record warp * 512 + i * 32 + l) and rank
@@ -168,20 +177,35 @@ __global__ void __launch_bounds__(kThreads) radix_pass_kernel(
         }
         const uint32_t count = run;
         volatile uint32_t* st = status + (size_t)tile * kRadix + d;
+        volatile const uint32_t* status_v = status;
         uint32_t excl = 0;
         if (tile == 0) {
             *st = kFlagPrefix | count;
         } else {
             *st = kFlagAgg | count;
-            for (long long t = (long long)tile - 1; t >= 0; t--) {
-                volatile const uint32_t* ps = status + (size_t)t * kRadix + d;
-                uint32_t v;
-                do {
-                    v = *ps;
-                } while ((v & ~kValMask) == 0u);
-                excl += v & kValMask;
-                if (v & kFlagPrefix)
-                    break;
+            // look back over the tiles before this one, kWin status words per round trip (the
+            // loads of a window are independent; a serial walk pays one L2 latency per tile,
+            // which IS the run time of a small sort whose tiles all start together)
+            constexpr int kWin = 8;
+            bool done = false;
+            for (long long t = (long long)tile - 1; t >= 0 && !done; t -= kWin) {
+                uint32_t v[kWin];
+#pragma unroll
+                for (int j = 0; j < kWin; j++) {
+                    v[j] = 2u << 30; // (before tile 0: a prefix of 0)
+                    if (t - j >= 0)
+                        v[j] = status_v[(size_t)(t - j) * kRadix + d];
+                }
+#pragma unroll
+                for (int j = 0; j < kWin; j++) {
+                    if (done)
+                        break;
+                    while ((v[j] & ~kValMask) == 0u) // not published yet
+                        v[j] = status_v[(size_t)(t - j) * kRadix + d];
+                    excl += v[j] & kValMask;
+                    if (v[j] & kFlagPrefix)
+                        done = true;
+                }
             }
             *st = kFlagPrefix | (excl + count);
         }
@@ -237,8 +261,8 @@ inline size_t sort_scratch_words(long long m, int passes)
 // ------------------------------------------------------------------------------------------
 // exclusive scan u32 -> u64, single pass (chained look-back on 64-bit status words)
 // ------------------------------------------------------------------------------------------
-constexpr int kScanItems = 8;
-constexpr int kScanTile = kThreads * kScanItems; // 2048
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kThreads * kScanItems; // 4096
 constexpr unsigned long long kSFlagAgg = 1ull << 62, kSFlagPrefix = 2ull << 62,
                              kSValMask = (1ull << 62) - 1ull;
 
@@ -279,26 +303,36 @@ __global__ void __launch_bounds__(kThreads) scan_u32_to_u64_kernel(
             before += wsum[w];
         total += wsum[w];
     }
-    if (tid == 0) {
-        volatile unsigned long long* st = status + tile;
+    if (warp == 0) {
+        // warp-wide look-back: 32 tiles before this one per round trip
+        volatile unsigned long long* st = status;
         unsigned long long excl = 0;
-        if (tile == 0) {
-            *st = kSFlagPrefix | total;
-        } else {
-            *st = kSFlagAgg | total;
-            for (long long t = (long long)tile - 1; t >= 0; t--) {
-                volatile const unsigned long long* ps = status + t;
-                unsigned long long s;
-                do {
-                    s = *ps;
-                } while ((s & ~kSValMask) == 0ull);
-                excl += s & kSValMask;
-                if (s & kSFlagPrefix)
+        if (tile > 0) {
+            if (lane == 0)
+                st[tile] = kSFlagAgg | total;
+            for (long long t0 = (long long)tile - 1;; t0 -= 32) {
+                const long long t = t0 - lane;
+                unsigned long long s = 2ull << 62; // (before tile 0: a prefix of 0)
+                if (t >= 0)
+                    s = st[t];
+                while (__any_sync(kFull, (s & ~kSValMask) == 0ull))
+                    if ((s & ~kSValMask) == 0ull)
+                        s = st[t];
+                const unsigned pm = __ballot_sync(kFull, (s & kSFlagPrefix) != 0ull);
+                const int first = pm ? __ffs(pm) - 1 : 32; // nearest tile with a full prefix
+                unsigned long long v = lane <= first ? (s & kSValMask) : 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+                    v += __shfl_xor_sync(kFull, v, o);
+                excl += v;
+                if (pm)
                     break;
             }
-            *st = kSFlagPrefix | (excl + total);
         }
-        tile_excl = excl;
+        if (lane == 0) {
+            st[tile] = kSFlagPrefix | (excl + total);
+            tile_excl = excl;
+        }
     }
     __syncthreads();
     unsigned long long run = tile_excl + before + incl - sum;
@@ -373,7 +407,7 @@ __global__ void widen_counts_kernel(const uint32_t* hist, int world, unsigned lo
 // run the digit passes of one sort; returns the buffer that holds the result
 unsigned long long* sort_records(
     long long m, int lo_bit, int n_bits, unsigned long long* a, unsigned long long* b, void* temp,
-    size_t temp_bytes, cudaStream_t s, LaunchCounter& lc)
+    size_t temp_bytes, cudaStream_t s, LaunchCounter& lc, bool hist_ready = false)
 {
     if (m <= 0 || n_bits <= 0)
         return a;
@@ -388,16 +422,19 @@ unsigned long long* sort_records(
     uint32_t* hist = (uint32_t*)temp;
     uint32_t* ctr = hist + kMaxPasses * kRadix;
     uint32_t* status = ctr + 64;
-    SCCD_CUDA(cudaMemsetAsync(temp, 0, words * 4, s));
-    radix_hist_kernel<<<std::min(tiles, 148 * 8), kThreads, 0, s>>>(a, m, lo_bit, passes, top_bits, hist);
-    SCCD_CUDA(cudaGetLastError());
-    lc.n++;
+    if (!hist_ready) { // (else: launch_sort_prepare + the kernel that made the records did it)
+        SCCD_CUDA(cudaMemsetAsync(temp, 0, words * 4, s));
+        radix_hist_kernel<<<std::min(tiles, 148 * 8), kThreads, 0, s>>>(
+            a, m, lo_bit, passes, top_bits, hist);
+        SCCD_CUDA(cudaGetLastError());
+        lc.n++;
+    }
     for (int p = 0; p < passes; p++) {
         BitsDigit dg;
         dg.shift = lo_bit + 8 * p;
         dg.mask = p == passes - 1 ? ((1u << top_bits) - 1u) : 255u;
         radix_pass_kernel<BitsDigit><<<tiles, kThreads, 0, s>>>(
-            a, b, m, dg, hist + p * kRadix, status + (size_t)p * tiles * kRadix, ctr + p);
+            a, b, m, dg, hist + p * kRadix, status + (size_t)p * tiles * kRadix, ctr + p, nullptr);
         SCCD_CUDA(cudaGetLastError());
         lc.n++;
         std::swap(a, b);
@@ -408,14 +445,26 @@ unsigned long long* sort_records(
 
 size_t sort_temp_bytes(long long m) { return sort_scratch_words(m > 0 ? m : 1, kMaxPasses) * 4; }
 
+// zeroes the sort scratch and returns where the digit histograms go, for a producer that
+// builds them while it writes the records (grid.cu: expand_fill_kernel)
+uint32_t* launch_sort_prepare(void* temp, size_t temp_bytes, long long m, cudaStream_t s)
+{
+    const size_t words = sort_scratch_words(m > 0 ? m : 1, kMaxPasses);
+    if (temp_bytes < words * 4)
+        throw std::logic_error("sort: scratch too small");
+    SCCD_CUDA(cudaMemsetAsync(temp, 0, words * 4, s));
+    return (uint32_t*)temp;
+}
+
 void launch_sort_and_gather(
     int m, int key_bits, unsigned long long* rec, unsigned long long* rec_tmp, void* temp,
     size_t temp_bytes, BoxArrays unsorted, SortedList out, cudaStream_t s, LaunchCounter& lc,
-    cudaEvent_t gather_begin, cudaEvent_t gather_end)
+    cudaEvent_t gather_begin, cudaEvent_t gather_end, bool hist_ready)
 {
     // the flag bits are not part of the order: equal (cell, q) records keep element order
     const unsigned long long* sorted = m > 0
-        ? sort_records(m, 32 + kKeyFlagBits, key_bits, rec, rec_tmp, temp, temp_bytes, s, lc)
+        ? sort_records(
+              m, 32 + kKeyFlagBits, key_bits, rec, rec_tmp, temp, temp_bytes, s, lc, hist_ready)
         : rec;
     if (gather_begin)
         SCCD_CUDA(cudaEventRecord(gather_begin, s));
@@ -455,16 +504,45 @@ void launch_partition_by_dest(
         for (int r = 0; r <= 16; r++)
             dg.first_cell[r] = r <= world ? (uint32_t)h_first_cell[r] : 0xffffffffu;
         const int tiles = sort_tiles(m);
-        digit_hist_kernel<DestDigit><<<std::min(tiles, 148 * 8), kThreads, 0, s>>>(rec_in, m, dg, hist);
+        digit_hist_kernel<DestDigit><<<std::min(tiles, 148 * 8), kThreads, 0, s>>>(
+            rec_in, m, dg, hist, nullptr);
         SCCD_CUDA(cudaGetLastError());
         radix_pass_kernel<DestDigit><<<tiles, kThreads, 0, s>>>(
-            rec_in, rec_out, m, dg, hist, status, ctr);
+            rec_in, rec_out, m, dg, hist, status, ctr, nullptr);
         SCCD_CUDA(cudaGetLastError());
         lc.n += 2;
     }
     widen_counts_kernel<<<1, 32, 0, s>>>(hist, world, counts);
     SCCD_CUDA(cudaGetLastError());
     lc.n++;
+}
+
+// Narrow phase: stable one-pass sort of the cull's survivor records on their lower-bound bucket
+// (bits 32..39).  The count is on the device (d_n); n_max bounds it.  rec -> rec_out.
+size_t sort_survivors_temp_bytes(long long n_max) { return partition_temp_bytes(n_max); }
+void launch_sort_survivors(
+    const unsigned long long* rec, unsigned long long* rec_out, const unsigned long long* d_n,
+    long long n_max, void* temp, size_t temp_bytes, cudaStream_t s, LaunchCounter& lc)
+{
+    if (n_max <= 0)
+        return;
+    const size_t words = sort_scratch_words(n_max, 1);
+    if (temp_bytes < words * 4)
+        throw std::logic_error("sort_survivors: scratch too small");
+    uint32_t* hist = (uint32_t*)temp;
+    uint32_t* ctr = hist + kMaxPasses * kRadix;
+    uint32_t* status = ctr + 64;
+    SCCD_CUDA(cudaMemsetAsync(temp, 0, words * 4, s));
+    BitsDigit dg;
+    dg.shift = 32;
+    dg.mask = 255u;
+    const int tiles = sort_tiles(n_max);
+    digit_hist_kernel<BitsDigit><<<std::min(tiles, 148 * 4), kThreads, 0, s>>>(rec, n_max, dg, hist, d_n);
+    SCCD_CUDA(cudaGetLastError());
+    radix_pass_kernel<BitsDigit><<<tiles, kThreads, 0, s>>>(
+        rec, rec_out, n_max, dg, hist, status, ctr, d_n);
+    SCCD_CUDA(cudaGetLastError());
+    lc.n += 2;
 }
 
 size_t sort_records_temp_bytes(long long m) { return sort_temp_bytes(m); }

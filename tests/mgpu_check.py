@@ -78,7 +78,10 @@ if not quick:
             fn()
         torch.cuda.synchronize(); dist.barrier()
         out[label] = (time.perf_counter() - t) / 5 * 1e3
+    ctx.set_option(sccd.capi.OPT_PROFILE, 1)     # stage timers are opt-in
+    ctx.ccd_sharded(**PARAMS)
     st = ctx.stats()
+    ctx.set_option(sccd.capi.OPT_PROFILE, 0)
     keys = ["ms_build", "ms_sort", "ms_sweep", "ms_narrow", "ms_total", "ms_exchange", "ms_k_boxes",
             "ms_k_expand", "ms_k_gather", "n_records", "n_records_sent", "n_pairs", "n_host_syncs"]
     per_rank = [None] * world

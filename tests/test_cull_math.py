@@ -61,6 +61,92 @@ def cull_mask(q, is_vf, tol, ms, f32=False):
     return sane & (0.5 * sep > bound)
 
 
+def toi_lower_bound(q, is_vf, tol, ms, f32=False):
+    """numpy mirror of the time-of-impact lower bound the cull kernel attaches to every
+    surviving query (csrc/narrow.cu): no box the root finder ACCEPTS for this query starts before
+    it.  Along a coordinate axis k the two primitives are `gap_k` apart at t = 0 and close in by
+    at most `D_k` per unit time (largest end-point displacement of either); an accepted box has
+    every corner within ms + err + W of the origin in every coordinate (the same W the cull
+    uses), so its t_lo is at least (gap_k - B) / D_k.  Used to ORDER the solver's work
+    (earliest possible contact first) and, in shared-bound mode without an iteration cap, to
+    skip queries that cannot lower the earliest toi."""
+    if f32:
+        q = q.astype(np.float32).astype(np.float64)
+        tol, ms = float(np.float32(tol)), float(np.float32(ms))
+    p = q.reshape(-1, 2, 4, 3)
+    s, e = p[:, 0], p[:, 1]
+    L = np.zeros((3, len(p)))
+    for k in range(3):
+        s0, s1, s2, s3 = (s[:, j, k] for j in range(4))
+        e0, e1, e2, e3 = (e[:, j, k] for j in range(4))
+        if is_vf:
+            p000, p001, p011, p010 = s0 - s1, s0 - s3, s0 - (s2 + s3 - s1), s0 - s2
+            p100, p101, p111, p110 = e0 - e1, e0 - e3, e0 - (e2 + e3 - e1), e0 - e2
+        else:
+            p000, p001, p010, p011 = s0 - s2, s0 - s3, s1 - s2, s1 - s3
+            p100, p101, p110, p111 = e0 - e2, e0 - e3, e1 - e2, e1 - e3
+        L[0] = np.maximum(L[0], absmax((p000, p100), (p001, p101), (p011, p111), (p010, p110)))
+        L[1] = np.maximum(L[1], absmax((p000, p010), (p100, p110), (p101, p111), (p001, p011)))
+        L[2] = np.maximum(L[2], absmax((p000, p001), (p100, p101), (p110, p111), (p010, p011)))
+    if is_vf:
+        A0, A1 = s[:, 0:1], e[:, 0:1]
+        B0 = np.concatenate([s[:, 1:4], (s[:, 2] + s[:, 3] - s[:, 1])[:, None]], axis=1)
+        B1 = np.concatenate([e[:, 1:4], (e[:, 2] + e[:, 3] - e[:, 1])[:, None]], axis=1)
+        width = np.full(len(p), tol)
+    else:
+        A0, A1 = s[:, 0:2], e[:, 0:2]
+        B0, B1 = s[:, 2:4], e[:, 2:4]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            width = np.where((L[0] > 0) & (L[1] > 0),
+                             tol * (1 + L[1] / L[0] + L[2] / L[1]) / 3 * 1.000001, np.inf)
+        width = np.maximum(width, tol)
+    maxabs = np.maximum(1.0, np.abs(p).reshape(len(p), -1).max(1))
+    extent = p.reshape(len(p), -1).max(1) - p.reshape(len(p), -1).min(1)
+    if f32:
+        bound = 2.0 * (width + ms + 2.0 * maxabs ** 3 * 8e-6 + 1e-6 * maxabs)
+        sane = (extent <= tol * 1e12) & (L.max(0) <= tol * 1e6)
+    else:
+        bound = 2.0 * (width + ms + 2.0 * maxabs ** 3 * 8e-15 + 1e-12 * maxabs)
+        sane = extent <= tol * 1e12
+    gap = np.maximum(B0.min(1) - A0.max(1), A0.min(1) - B0.max(1))          # per axis, t = 0
+    D = np.abs(A1 - A0).max(1) + np.abs(B1 - B0).max(1)                    # closing speed bound
+    with np.errstate(divide="ignore", invalid="ignore"):
+        tk = np.where(gap > bound[:, None], (gap - bound[:, None]) / D, 0.0)   # D = 0 -> inf
+    t = np.where(sane, tk.max(1), 0.0)
+    return np.minimum(t * (1.0 - 1e-9), 2.0)
+
+
+@pytest.mark.parametrize("f32", [False, True])
+@pytest.mark.parametrize("tol,ms", [(1e-6, 0.0), (1e-3, 0.0), (1e-6, 1e-3), (1e-9, 1e-8), (1e-2, 1e-2)])
+def test_toi_lower_bound_never_exceeds_the_solver(orc, sccd, scene_c1, tol, ms, f32):
+    """Every per-query TOI of the oracle (and every "no collision") respects the bound, on a
+    cloth scene, a rigid-body pile and the adversarial queries -- so ordering by it and skipping
+    queries whose bound is not below the running earliest toi changes no result."""
+    sets = []
+    vb, eb, fb = orc.build_boxes(scene_c1, ms, f32)
+    pile = sccd.scenes.blob_pile(60, seed=11)
+    pvb, peb, pfb = orc.build_boxes(pile, ms, f32)
+    for scene, (v, ed, f) in ((scene_c1, (vb, eb, fb)), (pile, (pvb, peb, pfb))):
+        vf = orc.canonical(orc.sort_and_sweep_two_lists(v, f, 0, f32)[0])
+        ee = orc.canonical(orc.sort_and_sweep(ed, 0, f32)[0])
+        sets.append((orc.gather_queries(scene, vf, True), True))
+        sets.append((orc.gather_queries(scene, ee, False), False))
+    ee5, vf5 = sccd.scenes.queries_c5(1500, seed=4, parallel=False)
+    sets += [(vf5, True), (ee5, False)]
+    n_pos = 0
+    for q, is_vf in sets:
+        m = orc.tractable(q, is_vf, ms, tol, limit=20000, f32=f32)
+        q = q[m]
+        lb = toi_lower_bound(q, is_vf, tol, ms, f32)
+        _, tpq, _ = orc.narrow_phase(q, is_vf, ms, -1, tol, True, f32=f32)
+        assert np.all(lb <= tpq)                 # (misses are +inf)
+        _, tpq0, _ = orc.narrow_phase(q, is_vf, ms, -1, tol, False, f32=f32)   # allow_zero_toi off
+        assert np.all(lb <= tpq0)
+        n_pos += int(((lb > 0) & (tpq < 1)).sum())
+    if ms == 0.0 and tol == 1e-6:
+        assert n_pos > 100                       # it is not vacuous: hits with a positive bound
+
+
 @pytest.mark.parametrize("f32", [False, True])
 @pytest.mark.parametrize("tol,ms", [(1e-6, 0.0), (1e-3, 0.0), (1e-6, 1e-3), (1e-9, 1e-8), (1e-2, 1e-2)])
 def test_culled_mesh_queries_are_misses(orc, scene_c1, tol, ms, f32):

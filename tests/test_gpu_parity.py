@@ -177,9 +177,10 @@ def np_env(ctx, sccd):
     set_()
 
 
-# refill | first-round budget << 8 | later budget << 16 | never-cooperate << 24 |
+# refill (6 bits) | no scout << 6 | no skip << 7 | first-round budget << 8 | later budget (7 bits)
+# << 16 | survivors not sorted by toi lower bound << 23 | never-cooperate << 24 |
 # log2(coop budget) - 3 << 25 | log2(coop limit) - 13 << 28
-VARIANTS = {"deep_first": 1 << 23, "lane_only": 1 << 24, "tiny_budgets": 4 | (3 << 8) | (2 << 16) | (1 << 25),
+VARIANTS = {"unsorted": 1 << 23, "no_scout": 1 << 6, "no_skip": 1 << 7, "lane_only": 1 << 24, "tiny_budgets": 4 | (3 << 8) | (2 << 16) | (1 << 25),
             "refill_every_lane": 1, "refill_all_idle": 32, "coop_big_budget": 5 << 25,
             "coop_small_limit": 1 << 28}
 
@@ -590,5 +591,115 @@ def test_max_iter_mode_drop_is_the_reference_rule(sccd, orc, torch_cuda):
             # (depth-first, earliest-t-first order usually reaches the earliest root before the
             # cap, so dropping the rest rarely loses it -- but it can; accepting never does)
             assert np.all(out[0][0] <= full) and np.all(out[1][0] >= full)
+    finally:
+        c.close()
+
+
+@pytest.fixture(params=[1, 4, 8])
+def group_ctx(request, sccd):
+    """A context whose solver is not the default (work queue for short lists): rounds for short
+    lists too (1), or the group solver with 4 / 8 lanes per tree."""
+    c = sccd.Context(0)
+    c.set_option(sccd.capi.OPT_NARROW_SOLVER, request.param)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_group_solver_matches_oracle_on_adversarial_queries(group_ctx, orc, sccd, torch_cuda, case):
+    """SCCD_OPT_NARROW_SOLVER = 4 / 8 lanes per tree: per-query hit / miss and TOI bit-equal to the
+    oracle, shared-bound mode returns the same minimum -- cull on and off, tiny budgets, paths
+    deeper than the tracked depth, a 64-entry item list."""
+    K = sccd.capi
+    c = group_ctx
+    ee, vf = sccd.scenes.queries_c5(3000, seed=4)
+    kw = CASES[case]
+    for kind, q in ((0, vf), (1, ee)):
+        q = q[orc.tractable(q, kind == 0, kw["ms"], kw["tol"], kw["allow_zero_toi"])]
+        otoi, otpq, _ = orc.narrow_phase(q, kind == 0, kw["ms"], kw["max_iter"], kw["tol"],
+                                         kw["allow_zero_toi"])
+        variants = [(1, 0, 128, 0), (0, 0, 128, 0), (1, 4 | (3 << 8) | (2 << 16), 128, 0)]
+        if case in ("default", "nozero"):
+            # (tol 1e-9 / ms > 0 make trees of 10^4 boxes: cut every 6 levels they outgrow the
+            # item list, and a 64-entry list cannot take the hand-on of a path deeper than 128
+            # levels -- both documented errors, not wrong answers)
+            variants += [(1, 0, 6, 0), (1, 8 | (5 << 8), 128, 64)]
+        for cull, flags, depth, qcap in variants:
+            c.set_option(K.OPT_NARROW_CULL, cull)
+            c.set_option(K.OPT_NARROW_FLAGS, flags)
+            c.set_option(K.OPT_NARROW_MAX_DEPTH, depth)
+            c.set_queue_capacity(qcap)
+            toi, tpq = _narrow_gpu(c, torch_cuda, kind, q, **kw)
+            assert np.array_equal(tpq, otpq), (kind, cull, flags, depth, qcap)
+            assert toi == otoi
+            assert c.narrow_phase_queries(kind, q, **kw) == otoi
+    c.set_option(K.OPT_NARROW_CULL, 1)
+    c.set_option(K.OPT_NARROW_FLAGS, 0)
+    c.set_option(K.OPT_NARROW_MAX_DEPTH, 128)
+    c.set_queue_capacity(0)
+
+
+def test_group_solver_pipeline_and_cap(group_ctx, orc, sccd, torch_cuda, scene_c1):
+    c = group_ctx
+    s = scene_c1
+    want = orc.ccd(s)
+    c.upload_mesh(s["V0"], s["V1"], s["E"], s["F"])
+    assert c.ccd() == want["toi"]
+    toi, (vf_ids, vf_t), (ee_ids, ee_t) = c.ccd_collisions()
+    assert toi == want["toi"]
+    for ids, t, pairs, tq in ((vf_ids, vf_t, want["vf"], want["toi_vf"]),
+                              (ee_ids, ee_t, want["ee"], want["toi_ee"])):
+        order = np.lexsort((ids[:, 1], ids[:, 0]))
+        hit = tq < 1
+        assert np.array_equal(ids[order], pairs[hit]) and np.array_equal(t[order], tq[hit])
+    # float build of the reference
+    c.set_scalar_type(sccd.capi.F32)
+    want32 = orc.ccd(s, f32=True)
+    assert c.ccd() == want32["toi"]
+    c.set_scalar_type(sccd.capi.F64)
+    # iteration cap: conservative, exact under the cap
+    ee, vf = sccd.scenes.queries_c5(2000, seed=12)
+    for kind, q in ((0, vf), (1, ee)):
+        _, full, _ = orc.narrow_phase(q, kind == 0, max_iter=-1)
+        _, capped = _narrow_gpu(c, torch_cuda, kind, q, max_iter=60)
+        ptr, n = c.narrow_phase_checks()
+        checks = torch_cuda.as_tensor(sccd.multigpu._DevArray(ptr, (n,), "<u4"), device="cuda").cpu().numpy()
+        under = checks <= 61
+        assert np.all(capped <= full) and np.array_equal(capped[under], full[under])
+        assert c.stats()["n_capped"][kind] > 0
+
+
+def test_time_ordered_solve_skips_work_but_changes_no_result(sccd, orc, scene_c1):
+    """The cull attaches a lower bound of the time of impact to every surviving query
+    (tests/test_cull_math.py: toi_lower_bound); round 0 solves the survivors earliest-possible-
+    contact first, a scout launch first of all, and skips queries whose bound is not below the
+    running earliest toi.  Same TOI with every part of it switched off; far fewer box checks
+    with it on."""
+    K = sccd.capi
+    s = scene_c1
+    want = orc.ccd(s)
+    c = sccd.Context(0)
+    try:
+        c.upload_mesh(s["V0"], s["V1"], s["E"], s["F"])
+        checks = {}
+        for name, flags in (("on", 0), ("no_scout", 1 << 6), ("no_skip", 1 << 7),
+                            ("unsorted", 1 << 23), ("all_off", (1 << 6) | (1 << 7) | (1 << 23))):
+            c.set_option(K.OPT_NARROW_FLAGS, flags)
+            assert c.ccd() == want["toi"], name
+            st = c.stats()
+            checks[name] = sum(st["n_box_checks"])
+            if name == "on":
+                assert sum(st["n_skipped"]) > 0
+            if name in ("no_skip", "all_off"):
+                assert st["n_skipped"] == [0, 0]
+        assert checks["on"] < checks["all_off"] and checks["on"] <= checks["no_skip"], checks
+        # the per-query list (TOI_PER_QUERY) never skips
+        c.set_option(K.OPT_NARROW_FLAGS, 0)
+        toi, (vi, vt), (ei, et) = c.ccd_collisions()
+        assert toi == want["toi"] and c.stats()["n_skipped"] == [0, 0]
+        assert len(vi) == int((want["toi_vf"] < 1).sum()) and len(ei) == int((want["toi_ee"] < 1).sum())
+        # ... nor does a run with an iteration cap
+        c.ccd(max_iter=1000)
+        assert c.stats()["n_skipped"] == [0, 0]
     finally:
         c.close()

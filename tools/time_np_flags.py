@@ -19,14 +19,23 @@ from _pkg import load_package  # noqa: E402
 
 sccd = load_package()
 name = sys.argv[1] if len(sys.argv) > 1 else "c2"
-flag_values = [int(v, 0) for v in sys.argv[2:]] or [0]
+# an argument is FLAGS or SOLVER:FLAGS (solver = 0, 4 or 8 lanes per tree, SCCD_OPT_NARROW_SOLVER)
+def _parse(v):
+    sv, _, fv = v.rpartition(":")
+    return (int(sv) if sv else 0, int(fv, 0))
+
+
+flag_values = [_parse(v) for v in sys.argv[2:]] or [(0, 0)]
 gen = {"small": lambda: sccd.scenes.cloth_on_sphere(31, seed=7, sphere="uv"),
        "c1": sccd.scenes.scene_c1, "c2": sccd.scenes.scene_c2, "c3": sccd.scenes.scene_c3}[name]
 s = gen()
 ctx = sccd.Context(0)
 ctx.upload_mesh(s["V0"], s["V1"], s["E"], s["F"])
-out = {"workload": name}
-for fv in flag_values:
+ctx.set_option(sccd.capi.OPT_PROFILE, int(os.environ.get("PROF", "1")))
+ctx.set_option(sccd.capi.OPT_CONCURRENT_PASSES, int(os.environ.get("CONC", "0")))
+out = {"workload": name, "concurrent_passes": int(os.environ.get("CONC", "0"))}
+for sv, fv in flag_values:
+    ctx.set_option(sccd.capi.OPT_NARROW_SOLVER, sv)
     ctx.set_option(sccd.capi.OPT_NARROW_FLAGS, fv)
     for _ in range(2):
         toi = ctx.ccd()
@@ -38,7 +47,8 @@ for fv in flag_values:
     b.record()
     torch.cuda.synchronize()
     st = ctx.stats()
-    out[hex(fv)] = {"ms_per_step": a.elapsed_time(b) / 5, "toi": toi,
+    out[f"{sv}:{hex(fv)}"] = {"ms_per_step": a.elapsed_time(b) / 5, "toi": toi,
+                    "round_items": st["n_round_items"], "round_checks": st["n_round_checks"],
                     "n_box_checks": st["n_box_checks"], "ms_narrow": st["ms_narrow"],
                     "ms_k_narrow": st["ms_k_narrow"], "ms_total_device": st["ms_total"]}
 ctx.close()
