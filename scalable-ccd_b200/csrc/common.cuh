@@ -296,6 +296,9 @@ struct alignas(128) NarrowCounters {
     unsigned long long donated;
     unsigned long long capped;
     unsigned long long started;  // trees round 0 started (survivors - started were skipped)
+    // survivors per bucket of their toi lower bound (1/256 of the step each), made by the cull:
+    // the digit histogram of the survivor sort, and what ordering_on() decides on (narrow.cu)
+    alignas(128) uint32_t tlb_hist[256];
 };
 
 // ---- kernel launchers (defined in the .cu files) -----------------------------------
@@ -439,9 +442,12 @@ void launch_narrow_phase(
     const cudaEvent_t* tev = nullptr /* 2 * (1 + kNarrowRounds) optional timing events */,
     cudaEvent_t solver_waits_for = nullptr /* the rounds (not the cull) start after this event */);
 size_t sort_survivors_temp_bytes(long long n_max);
+// hist: the 256-bucket histogram of bits 32..39 the producer made (device).  The sort does
+// nothing when the buckets do not discriminate (2 * hist[0] >= *d_n; narrow.cu: ordering_on).
 void launch_sort_survivors(
     const unsigned long long* rec, unsigned long long* rec_out, const unsigned long long* d_n,
-    long long n_max, void* temp, size_t temp_bytes, cudaStream_t s, LaunchCounter& lc);
+    const uint32_t* hist, long long n_max, void* temp, size_t temp_bytes, cudaStream_t s,
+    LaunchCounter& lc);
 // moves n_items[kNarrowRounds] to n_items[kNarrowRounds - 1] and reruns the last round
 void launch_narrow_extra_round(
     bool is_vf, bool f32, const NarrowInput& in, const NarrowParams& p, NarrowCounters* counters,

@@ -121,8 +121,11 @@ __global__ void __launch_bounds__(kThreads) radix_pass_kernel(
     const unsigned long long* __restrict__ in, unsigned long long* __restrict__ out, long long n,
     Digit digit, const uint32_t* __restrict__ hist /* 256: this pass */,
     uint32_t* __restrict__ status, uint32_t* __restrict__ ctr,
-    const unsigned long long* __restrict__ d_n)
+    const unsigned long long* __restrict__ d_n, bool gated)
 {
+    // gated: a sort that is only worth doing if its digit discriminates (see launch_sort_survivors)
+    if (gated && 2ull * (unsigned long long)hist[0] >= *d_n)
+        return;
     __shared__ SortSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0)
@@ -434,7 +437,8 @@ unsigned long long* sort_records(
         dg.shift = lo_bit + 8 * p;
         dg.mask = p == passes - 1 ? ((1u << top_bits) - 1u) : 255u;
         radix_pass_kernel<BitsDigit><<<tiles, kThreads, 0, s>>>(
-            a, b, m, dg, hist + p * kRadix, status + (size_t)p * tiles * kRadix, ctr + p, nullptr);
+            a, b, m, dg, hist + p * kRadix, status + (size_t)p * tiles * kRadix, ctr + p, nullptr,
+            false);
         SCCD_CUDA(cudaGetLastError());
         lc.n++;
         std::swap(a, b);
@@ -508,7 +512,7 @@ void launch_partition_by_dest(
             rec_in, m, dg, hist, nullptr);
         SCCD_CUDA(cudaGetLastError());
         radix_pass_kernel<DestDigit><<<tiles, kThreads, 0, s>>>(
-            rec_in, rec_out, m, dg, hist, status, ctr, nullptr);
+            rec_in, rec_out, m, dg, hist, status, ctr, nullptr, false);
         SCCD_CUDA(cudaGetLastError());
         lc.n += 2;
     }
@@ -522,27 +526,24 @@ void launch_partition_by_dest(
 size_t sort_survivors_temp_bytes(long long n_max) { return partition_temp_bytes(n_max); }
 void launch_sort_survivors(
     const unsigned long long* rec, unsigned long long* rec_out, const unsigned long long* d_n,
-    long long n_max, void* temp, size_t temp_bytes, cudaStream_t s, LaunchCounter& lc)
+    const uint32_t* hist, long long n_max, void* temp, size_t temp_bytes, cudaStream_t s,
+    LaunchCounter& lc)
 {
     if (n_max <= 0)
         return;
     const size_t words = sort_scratch_words(n_max, 1);
     if (temp_bytes < words * 4)
         throw std::logic_error("sort_survivors: scratch too small");
-    uint32_t* hist = (uint32_t*)temp;
-    uint32_t* ctr = hist + kMaxPasses * kRadix;
+    uint32_t* ctr = (uint32_t*)temp + kMaxPasses * kRadix;
     uint32_t* status = ctr + 64;
     SCCD_CUDA(cudaMemsetAsync(temp, 0, words * 4, s));
     BitsDigit dg;
     dg.shift = 32;
     dg.mask = 255u;
-    const int tiles = sort_tiles(n_max);
-    digit_hist_kernel<BitsDigit><<<std::min(tiles, 148 * 4), kThreads, 0, s>>>(rec, n_max, dg, hist, d_n);
+    radix_pass_kernel<BitsDigit><<<sort_tiles(n_max), kThreads, 0, s>>>(
+        rec, rec_out, n_max, dg, hist, status, ctr, d_n, true);
     SCCD_CUDA(cudaGetLastError());
-    radix_pass_kernel<BitsDigit><<<tiles, kThreads, 0, s>>>(
-        rec, rec_out, n_max, dg, hist, status, ctr, d_n);
-    SCCD_CUDA(cudaGetLastError());
-    lc.n += 2;
+    lc.n++;
 }
 
 size_t sort_records_temp_bytes(long long m) { return sort_temp_bytes(m); }
