@@ -875,6 +875,11 @@ void narrow_enqueue(
     P.max_depth = c->opt.np_depth;
     P.cap_drops = c->opt.cap_drops;
     P.solver = c->opt.np_solver;
+    // lower bounds only where they can pay: the shared minimum (not the per-query list), and not
+    // while the previous frames of this pass showed them useless (narrow_finish)
+    P.want_tlb = !d_toi_per_query && c->tlb_pause[kind] == 0;
+    if (!d_toi_per_query && c->tlb_pause[kind] > 0)
+        c->tlb_pause[kind]--;
     SCCD_CUDA(cudaMemsetAsync(R.b_counters.ptr, 0, sizeof(NarrowCounters), st));
     if (d_toi_per_query)
         launch_fill_f64(d_toi_per_query, in.n, INFINITY, st, c->lc);
@@ -953,6 +958,13 @@ void narrow_finish(sccd_ctx* c, double* d_gtoi)
     if (R.pending.culling) {
         c->stats.n_culled[kind] += R.pending.in.n - (int64_t)r.n_items[0];
         c->stats.n_skipped[kind] += (int64_t)r.n_items[0] - (int64_t)r.started;
+        // did the lower bounds earn their keep?  (only judged where skipping was allowed)
+        if (R.pending.P.want_tlb && R.pending.P.max_iter < 0 && !R.pending.d_tq
+            && !(R.pending.P.flags & (1 << 7)) && r.n_items[0] >= 4096
+            && (r.n_items[0] - r.started) * 2ull < r.n_items[0])
+            // (measured: config 4's edge pass skips 25 % of its survivors and saves 7 % of its
+            // box checks, for a cull that is 2 ms = 66 % longer; config 2 skips 66 % / 99 %)
+            c->tlb_pause[kind] = 15;
     }
     c->stats.n_donated[kind] += (int64_t)r.donated;
     for (int i = 0; i <= kNarrowRounds; i++) {

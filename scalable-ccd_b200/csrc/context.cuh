@@ -141,6 +141,11 @@ struct sccd_ctx {
     double* peer_toi[15] = {};
     bool peer_is_ipc[15] = {};
     bool share_toi = false;             // set for the duration of a sharded pipeline call
+    // Frame-to-frame: when the toi lower bounds of a pass let it skip less than half of its
+    // survivors -- a pile of rigid bodies whose boxes overlap at t = 0 -- the next batches of
+    // that pass do not compute them (a third of the cull's arithmetic); every 16th batch probes
+    // again.
+    int tlb_pause[2] = { 0, 0 };
     bool sliced = false;                // the mesh lists hold slices / received records
     DevBuf b_xcnt, b_xsplits;           // all ranks' send counts; both lists' cell splits
     unsigned long long* h_xcnt = nullptr; // pinned

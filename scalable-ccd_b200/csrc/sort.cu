@@ -58,9 +58,12 @@ struct DestDigit {
     __device__ __forceinline__ uint32_t operator()(unsigned long long r) const
     {
         const uint32_t cell = cell_shift >= 64 ? 0u : (uint32_t)(r >> cell_shift);
+        // (fully unrolled, compile-time indices: the table stays in the kernel's constant bank;
+        // entries past `world` are 0xffffffff and never count)
         uint32_t d = 0;
-        while ((int)d + 1 < world && cell >= first_cell[d + 1])
-            d++;
+#pragma unroll
+        for (int i = 1; i < 16; i++)
+            d += cell >= first_cell[i] ? 1u : 0u;
         return d;
     }
 };
@@ -505,8 +508,8 @@ void launch_partition_by_dest(
         DestDigit dg;
         dg.cell_shift = cell_shift;
         dg.world = world;
-        for (int r = 0; r <= 16; r++)
-            dg.first_cell[r] = r <= world ? (uint32_t)h_first_cell[r] : 0xffffffffu;
+        for (int r = 0; r <= 16; r++) // (first_cell[world] = number of cells: no cell reaches it)
+            dg.first_cell[r] = r < world ? (uint32_t)h_first_cell[r] : 0xffffffffu;
         const int tiles = sort_tiles(m);
         digit_hist_kernel<DestDigit><<<std::min(tiles, 148 * 8), kThreads, 0, s>>>(
             rec_in, m, dg, hist, nullptr);
