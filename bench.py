@@ -457,24 +457,26 @@ def main():
     def hbm(name, ms_, nbytes, what):
         if ms_ > 0:
             gbs = nbytes / (ms_ * 1e-3) / 1e9
-            kernels[name] = {"ms": ms_, "bound": "hbm", "achieved": gbs, "peak": hbm_peak,
+            kernels[name] = {"key": name.split(" ")[0],
+                             "ms": ms_, "bound": "hbm", "achieved": gbs, "peak": hbm_peak,
                              "unit": "GB/s", "frac": gbs / hbm_peak,
                              "algorithmic_bytes_per_launch": nbytes, "work": what}
 
     def fp64(name, ms_, checks, flop_per_check):
         if ms_ > 0:
             tf = checks * flop_per_check / (ms_ * 1e-3) / 1e12
-            kernels[name] = {"ms": ms_, "bound": "fp64", "achieved": tf, "peak": fp64_peak_tflops,
+            kernels[name] = {"key": name, "ms": ms_, "bound": "fp64", "achieved": tf,
+                             "peak": fp64_peak_tflops,
                              "unit": "TFLOP/s", "frac": tf / fp64_peak_tflops,
                              "algorithmic_flop_per_launch": checks * flop_per_check,
                              "work": f"{checks:.0f} box checks x {flop_per_check} FP64 flop"}
 
     share = 1.0 / world
     if world == 1:
-        hbm("vertex_boxes+element_boxes (2 launches)", pavg("ms_k_boxes"),
+        hbm("boxes (vertex_boxes + element_boxes, 2 launches)", pavg("ms_k_boxes"),
             48 * nV + 8 * nE + 12 * nF + 64 * (nV + nE + nF), "48 B/vertex + indices in, 64 B/box out")
     else:
-        hbm("vertex_boxes + 2 x list_boxes(sample) (3 launches)", pavg("ms_k_boxes"),
+        hbm("boxes (vertex_boxes + 2 x list_boxes of the sample, 3 launches)", pavg("ms_k_boxes"),
             (48 + 96) * nV + (64 + 60) * (nV + nE + nF) / 16,
             "replicated: vertex table + vertex boxes of all vertices, 1-in-16 box sample")
     hbm("gather (2 launches)", pavg("ms_k_gather"), 2 * 64 * (loc_recs[0] + loc_recs[1]),
@@ -492,15 +494,21 @@ def main():
         for r in range(5):
             fp64(f"narrow_round{r}_{nm}", pavg("ms_k_round", k, r), pavg("n_round_checks", k, r),
                  156 if k == 0 else 132)
+    for v in kernels.values():      # DRAM bytes per step of the same kernels from the ncu capture
+        if v["key"].startswith("narrow_round"):   # (the solver launches of a pass add up under one key)
+            v["key"] = "narrow_solve_" + v["key"][-2:]
+        v["traffic"] = traffic_db.get(f"{args.workload}:{v['key']}")
     dom = max(kernels, key=lambda k_: kernels[k_]["ms"]) if kernels else None
     roofline = None
     if dom:
         d = kernels[dom]
         roofline = {"kernel": dom, "bound": d["bound"], "achieved": d["achieved"], "peak": d["peak"],
                     "unit": d["unit"], "frac": d["frac"],
-                    "traffic": traffic_db.get(f"{args.workload}:{dom}"),
-                    "traffic_source": "profiles/dram_traffic.json (ncu --set full capture of this "
-                                      "commit's kernels; not measured in this run)",
+                    "traffic": traffic_db.get(f"{args.workload}:{d['key']}"),
+                    "traffic_source": "profiles/dram_traffic.json (ncu --set full capture of one "
+                                      "whole step of this workload, summed per kernel family; all "
+                                      "solver launches of a pass under one figure; not measured in "
+                                      "this run)",
                     "kernel_ms": d["ms"], "work_per_launch": d["work"],
                     "peak_source": (peak_source if d["bound"] == "hbm" else
                                     "FP64 peak = 2 x DFMA/s measured on this device in this run by "
@@ -554,7 +562,8 @@ def main():
         "roofline": roofline,
         "roofline_hbm": ({"kernel": dom_h, **{k_: hbm_only[dom_h][k_] for k_ in
                                               ("achieved", "peak", "unit", "frac", "ms")},
-                          "traffic": traffic_db.get(f"{args.workload}:{dom_h}")} if dom_h else None),
+                          "traffic": traffic_db.get(f"{args.workload}:{hbm_only[dom_h]['key']}")}
+                         if dom_h else None),
         "toi": toi, "n_pairs": n_pairs, "ms_steps_rank0": ms_steps,
         "stage_ms_per_rank": rank_stage_ms,
         "single_gpu_ms_same_workload": single_ms,

@@ -183,6 +183,18 @@ int sccd_set_scalar_type(sccd_ctx* ctx, int type);
                                        Both publish to the same toi word, so each still profits
                                        from the other's finds; the result is the same, the work
                                        can be more.  0 = in sequence (default).                  */
+#define SCCD_OPT_SWEEP_STAGED 13     /* sweep count pass: 1 = the prefilter stream of a tile (keys +
+                                       f32 yz of the next 1024 records) is staged in shared memory
+                                       by bulk async copies (cp.async.bulk + mbarrier) before the
+                                       window loop; 0 (default) = the loop reads it through L1.
+                                       Same pairs either way.                                    */
+#define SCCD_OPT_REUSE_GRID 14       /* frame-to-frame (default 1): when a build has the list sizes,
+                                       sweep axis and scalar type of the previous one, the cell
+                                       grid and key quantisation are chosen from the previous
+                                       build's box statistics -- one host sync less per step --
+                                       while this build's statistics are computed off the
+                                       critical path for the next one.  Any grid gives the same
+                                       overlap set; 0 = wait for this build's own statistics.    */
 #define SCCD_OPT_PROFILE 10         /* 1: time every solver round with its own event pair
                                        (sccd_stats.ms_k_round); 0 (default): stage timers only */
 #define SCCD_OPT_SWEEP_AXIS 9       /* axis the mesh pipeline sorts and sweeps along: 0 (default,

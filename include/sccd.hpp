@@ -84,6 +84,15 @@ namespace cuda {
         }
     } // namespace detail
 
+    // max_iter >= 0: 0 (default) = boxes of a query that reaches the cap are accepted at their
+    // t_lo (never later than the exact answer); 1 = dropped, the reference's rule
+    // (root_finder.cu:303-305), which can miss a collision.  No effect for max_iter < 0.
+    inline void set_max_iter_mode(int mode)
+    {
+        auto& c = detail::default_ctx();
+        c.check(sccd_set_option(c.h, SCCD_OPT_MAX_ITER_MODE, mode));
+    }
+
     // ---- cuda/ccd.cuh:26-38 -----------------------------------------------------------
     template <typename VMat, typename IMat>
     Scalar

@@ -19,7 +19,7 @@ F64, F32 = 0, 1  # sccd_set_scalar_type: the reference's SCALABLE_CCD_USE_DOUBLE
 OK, ERR_CUDA, ERR_ARG, ERR_STATE, ERR_MEMORY = 0, -1, -2, -3, -4
 (OPT_NARROW_CULL, OPT_NARROW_FLAGS, OPT_NARROW_FLAGS_EE, OPT_NARROW_MAX_DEPTH, OPT_MAX_ITER_MODE,
  OPT_KEY_STEPS, OPT_GRID_SCALE_MILLI, OPT_GRID_REPL_MILLI, OPT_SWEEP_AXIS, OPT_PROFILE,
- OPT_NARROW_SOLVER, OPT_CONCURRENT_PASSES) = range(1, 13)
+ OPT_NARROW_SOLVER, OPT_CONCURRENT_PASSES, OPT_SWEEP_STAGED, OPT_REUSE_GRID) = range(1, 15)
 UNIQUE_ID_BYTES = 128
 
 AABB_DTYPE = np.dtype(

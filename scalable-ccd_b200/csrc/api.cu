@@ -341,9 +341,11 @@ void sort_list_count(sccd_ctx* c, int which)
         &H.m, L.offs.as<unsigned long long>() + n, 8, cudaMemcpyDeviceToHost, c->stream));
 }
 
-// enqueue the statistics of a list towards list_host(c, which).stats (no sync)
-void list_stats(sccd_ctx* c, int which)
+// enqueue the statistics of a list towards list_host(c, which).stats_next (no sync)
+void list_stats(sccd_ctx* c, int which, cudaStream_t st = nullptr)
 {
+    if (!st)
+        st = c->stream;
     auto& L = c->lists[which];
     auto& H = list_host(c, which);
     if (L.n_boxes <= 0)
@@ -353,9 +355,36 @@ void list_stats(sccd_ctx* c, int which)
     double* base = (double*)c->b_stats.reserve(3 * per * sizeof(double)) + which * per;
     double* d_stats = base + kStatsBlocks * kNumStats;
     const int stride = stats_stride(L.n_boxes);
-    launch_box_stats(L.unsorted, L.n_boxes, stride, base, d_stats, c->stream, c->lc);
+    launch_box_stats(L.unsorted, L.n_boxes, stride, base, d_stats, st, c->lc);
     SCCD_CUDA(cudaMemcpyAsync(
-        H.stats, d_stats, kNumStats * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        H.stats_next, d_stats, kNumStats * sizeof(double), cudaMemcpyDeviceToHost, st));
+}
+// the statistics that arrived become the ones the next grid is chosen from
+void adopt_stats(sccd_ctx* c, int which, long long n_full)
+{
+    auto& L = c->lists[which];
+    auto& H = list_host(c, which);
+    std::memcpy(H.stats, H.stats_next, sizeof(H.stats));
+    L.stats_valid = n_full > 0;
+    L.stats_n = (int)n_full;
+    L.stats_axis = L.axis;
+    L.stats_f32 = c->f32;
+}
+bool stats_reusable(const sccd_ctx* c, int which, long long n_full)
+{
+    const auto& L = c->lists[which];
+    return c->opt.reuse_grid != 0
+        && (n_full == 0 || (L.stats_valid && L.stats_n == n_full && L.stats_axis == L.axis && L.stats_f32 == c->f32));
+}
+// statistics a previous build left in flight on the sort stream (long since there)
+void drain_stats(sccd_ctx* c)
+{
+    if (!c->stats_in_flight)
+        return;
+    SCCD_CUDA(cudaEventSynchronize(c->ev_stats));
+    adopt_stats(c, 0, c->lists[0].n_boxes);
+    adopt_stats(c, 1, c->lists[1].n_boxes);
+    c->stats_in_flight = false;
 }
 
 // requires the list's statistics in list_host(c, which).stats
@@ -467,6 +496,7 @@ void sort_list(sccd_ctx* c, int which, cudaEvent_t ga, cudaEvent_t gb)
 {
     list_stats(c, which);
     host_sync(c, c->stream);
+    adopt_stats(c, which, c->lists[which].n_boxes);
     sort_list_begin(c, which);
     host_sync(c, c->stream);
     sort_list_finish(c, which, ga, gb);
@@ -486,6 +516,7 @@ void build_boxes(sccd_ctx* c, double inflation_radius)
     if (!c->have_mesh)
         throw std::logic_error("build_boxes: no mesh uploaded");
     join_sort_stream(c, c->stream); // a previous build whose edge list nobody swept
+    drain_stats(c);
     c->sliced = false;
     const int nV = c->nV, nE = c->nE, nF = c->nF;
     const long long nVF = (long long)nV + nF;
@@ -516,13 +547,31 @@ void build_boxes(sccd_ctx* c, double inflation_radius)
         c->dE, nE, c->dF, nF, LE.unsorted, LV.unsorted, LE.axis, LV.axis, d_bad, c->stream, c->lc);
     kt_end(c, kt_boxes);
     record(c, EV_BUILD);
-    // sync 1: statistics of both lists; sync 2: record counts of both lists
-    list_stats(c, 0);
-    list_stats(c, 1);
+    // Frame-to-frame: the statistics only steer the cell grid and the key
+    // quantisation, and any grid gives the same overlap set.  When the lists have the size,
+    // axis and scalar type of the previous build, its statistics choose this build's grid at
+    // once -- no host sync, and the statistics of the new boxes are computed on the second
+    // stream, off the critical path, for the build after this one.
+    const bool reuse = stats_reusable(c, 0, c->lists[0].n_boxes) && stats_reusable(c, 1, c->lists[1].n_boxes);
     SCCD_CUDA(cudaMemcpyAsync(c->h_flags, d_bad, 4, cudaMemcpyDeviceToHost, c->stream));
-    host_sync(c, c->stream);
-    if (c->h_flags[0]) // the reference would read out of bounds (aabb.cu:199-226)
-        throw std::invalid_argument("build_boxes: an edge / face refers to a vertex that does not exist");
+    if (reuse) {
+        SCCD_CUDA(cudaEventRecord(c->ev_boxes, c->stream));
+        SCCD_CUDA(cudaStreamWaitEvent(c->sort_stream, c->ev_boxes, 0));
+        list_stats(c, 0, c->sort_stream);
+        list_stats(c, 1, c->sort_stream);
+        SCCD_CUDA(cudaEventRecord(c->ev_stats, c->sort_stream));
+        c->stats_in_flight = true;
+    } else {
+        // sync 1: statistics of both lists (sync 2: record counts of both lists)
+        list_stats(c, 0);
+        list_stats(c, 1);
+        host_sync(c, c->stream);
+        adopt_stats(c, 0, c->lists[0].n_boxes);
+        adopt_stats(c, 1, c->lists[1].n_boxes);
+        if (c->h_flags[0]) // the reference would read out of bounds (aabb.cu:199-226)
+            throw std::invalid_argument(
+                "build_boxes: an edge / face refers to a vertex that does not exist");
+    }
     for (int which = 0; which < 2; which++) {
         // next sweep axis = argmax of the variance of the box centres, as sort_and_sweep hands
         // it back (sort_and_sweep.cpp:176-195); here over the sampled boxes of the statistics
@@ -544,6 +593,8 @@ void build_boxes(sccd_ctx* c, double inflation_radius)
     sort_list_begin(c, 0);
     sort_list_begin(c, 1);
     host_sync(c, c->stream);
+    if (reuse && c->h_flags[0])
+        throw std::invalid_argument("build_boxes: an edge / face refers to a vertex that does not exist");
     const bool prof = c->opt.profile != 0;
     sort_list_finish(c, 0, prof ? c->ev[EV_GA0] : nullptr, prof ? c->ev[EV_GB0] : nullptr);
     // (if the grid of list 1 has to be coarsened, its retry runs -- and syncs -- on the main
@@ -714,7 +765,7 @@ void broad_phase_begin_enqueue(sccd_ctx* c, int kind)
     const size_t kt = kt_begin(c, &c->stats.ms_k_sweep_count[sk]);
     launch_sweep_count(
         L, R.shard_lo, R.shard_hi, R.b_counts.as<uint32_t>(), d_cand, R.b_stage_pairs.ptr,
-        R.b_stage_tags.ptr, R.b_stage_count.as<uint32_t>(), st, c->lc);
+        R.b_stage_tags.ptr, R.b_stage_count.as<uint32_t>(), st, c->lc, c->opt.sweep_staged != 0);
     kt_end(c, kt);
     launch_scan_u32_to_u64(
         R.b_counts.as<uint32_t>(), R.b_offsets.as<unsigned long long>(), m, R.b_scan.ptr,
@@ -1284,6 +1335,8 @@ int sccd_create(int device, void* stream, sccd_ctx** out)
             c->opt.np_cull = atoi(e) != 0;
         if (const char* e = getenv("SCCD_KEY_STEPS"))
             c->opt.key_steps = std::min(16, std::max(0, atoi(e)));
+        if (const char* e = getenv("SCCD_SWEEP_STAGED"))
+            c->opt.sweep_staged = atoi(e) != 0;
         if (const char* e = getenv("SCCD_CONCURRENT_PASSES"))
             c->opt.concurrent_passes = atoi(e) != 0;
         if (const char* e = getenv("SCCD_NP_SOLVER"))
@@ -1298,6 +1351,10 @@ int sccd_create(int device, void* stream, sccd_ctx** out)
         SCCD_CUDA(cudaEventCreateWithFlags(&c->ev_counts, cudaEventDisableTiming));
         SCCD_CUDA(cudaEventCreateWithFlags(&c->ev_sorted1, cudaEventDisableTiming));
         SCCD_CUDA(cudaEventCreateWithFlags(&c->ev_vf_done, cudaEventDisableTiming));
+        SCCD_CUDA(cudaEventCreateWithFlags(&c->ev_boxes, cudaEventDisableTiming));
+        SCCD_CUDA(cudaEventCreateWithFlags(&c->ev_stats, cudaEventDisableTiming));
+        if (const char* e = getenv("SCCD_REUSE_GRID"))
+            c->opt.reuse_grid = atoi(e) != 0;
         c->runs[1].stream = c->sort_stream;
         return SCCD_OK;
     });
@@ -1403,6 +1460,8 @@ int sccd_set_option(sccd_ctx* ctx, int option, int64_t value)
         break;
     case SCCD_OPT_PROFILE: o.profile = value != 0; break;
     case SCCD_OPT_CONCURRENT_PASSES: o.concurrent_passes = value != 0; break;
+    case SCCD_OPT_SWEEP_STAGED: o.sweep_staged = value != 0; break;
+    case SCCD_OPT_REUSE_GRID: o.reuse_grid = value != 0; break;
     case SCCD_OPT_NARROW_SOLVER:
         if (value != 0 && value != 1 && value != 4 && value != 8)
             return SCCD_ERR_ARG;
@@ -1442,6 +1501,8 @@ int sccd_get_option(const sccd_ctx* ctx, int option, int64_t* value)
     case SCCD_OPT_PROFILE: *value = o.profile; break;
     case SCCD_OPT_NARROW_SOLVER: *value = o.np_solver; break;
     case SCCD_OPT_CONCURRENT_PASSES: *value = o.concurrent_passes; break;
+    case SCCD_OPT_SWEEP_STAGED: *value = o.sweep_staged; break;
+    case SCCD_OPT_REUSE_GRID: *value = o.reuse_grid; break;
     default: return SCCD_ERR_ARG;
     }
     return SCCD_OK;

@@ -394,7 +394,8 @@ size_t sweep_stage_tag_bytes(int owners);
 void launch_sweep_count(
     const SortedList& L, int owner_lo, int owner_hi, uint32_t* counts,
     unsigned long long* n_candidates, void* stage_pairs, void* stage_tags, uint32_t* stage_count,
-    cudaStream_t s, LaunchCounter& lc);
+    cudaStream_t s, LaunchCounter& lc,
+    bool tma_staged = false /* prefilter stream through shared memory (cp.async.bulk) */);
 // counts / offsets are indexed relative to the first owner of the count pass (shard_lo);
 // the fill of owner range [owner_lo, owner_hi) writes pairs[offsets[i] - offsets[owner_lo]..).
 void launch_sweep_fill(

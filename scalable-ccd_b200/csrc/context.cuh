@@ -48,6 +48,11 @@ struct sccd_ctx {
         SortedList sorted;
         BoxArrays unsorted;
         int n_boxes = 0;
+        // frame-to-frame: the statistics the grid was chosen from (valid for a list of stats_n
+        // boxes swept along stats_axis in scalar mode stats_f32)
+        bool stats_valid = false;
+        int stats_n = -1, stats_axis = -1;
+        bool stats_f32 = false;
         int axis = 0;      // axis the records of this list are rotated to / swept along
         int next_axis = 0; // variance argmax of the last build (sort_and_sweep.cpp:176-195)
         int built_rank = 0, built_world = 1; // sharding the sorted records were made for
@@ -63,10 +68,13 @@ struct sccd_ctx {
     // idle.  ev_counts: both lists counted (main stream); ev_sorted1: edge list sorted.
     cudaStream_t sort_stream = nullptr;
     cudaEvent_t ev_counts = nullptr, ev_sorted1 = nullptr, ev_vf_done = nullptr;
+    cudaEvent_t ev_boxes = nullptr, ev_stats = nullptr; // frame-to-frame statistics (build_boxes)
+    bool stats_in_flight = false;
     bool sort1_pending = false;
     // pinned: per list, box statistics + record count + multi-GPU cell splits
     struct ListHost {
         double stats[kNumStats];
+        double stats_next[kNumStats]; // statistics of the CURRENT boxes, on their way for the next build
         unsigned long long m;
         unsigned long long splits[2 * 16 + 2];
     };
@@ -90,6 +98,8 @@ struct sccd_ctx {
         int profile = 0;        // time every solver round (sccd_stats.ms_k_round)
         int np_solver = 0;      // 0: lane / warp per tree by list length; 4, 8: lanes per tree
         int concurrent_passes = 0; // edge-edge solver does not wait for the vertex-face one
+        int sweep_staged = 0;   // sweep count pass reads its window from TMA-staged shared memory
+        int reuse_grid = 1;     // frame-to-frame: grid from the previous build's statistics
     } opt;
     int next_axis = 0;          // argmax of the box-centre variance of the last build
 
@@ -188,6 +198,10 @@ struct sccd_ctx {
             cudaEventDestroy(ev_sorted1);
         if (ev_vf_done)
             cudaEventDestroy(ev_vf_done);
+        if (ev_boxes)
+            cudaEventDestroy(ev_boxes);
+        if (ev_stats)
+            cudaEventDestroy(ev_stats);
         if (h_lists)
             cudaFreeHost(h_lists);
         if (h_flags)
@@ -269,6 +283,9 @@ GridParams choose_grid(const double* st, int n, int max_cells, double scale);
 void regrid(GridParams& g, const double st[kNumStats]);
 void key_layout(
     GridParams& g, unsigned long long m_total, const double* st, int key_steps, int& cell_bits);
+void adopt_stats(sccd_ctx* c, int which, long long n_full);
+bool stats_reusable(const sccd_ctx* c, int which, long long n_full);
+void drain_stats(sccd_ctx* c);
 void join_sort_stream(sccd_ctx* c, cudaStream_t st);
 void build_boxes(sccd_ctx* c, double inflation_radius);
 void small_scratch(sccd_ctx* c);

@@ -219,6 +219,7 @@ void build_boxes_sliced(sccd_ctx* c, double inflation_radius)
     if (c->comm_world < 1)
         throw std::logic_error("sccd_ccd_sharded: no communicator (sccd_comm_create)");
     join_sort_stream(c, c->stream);
+    drain_stats(c);
     const int W = c->comm_world, rank = c->rank;
     const int nV = c->nV, nE = c->nE, nF = c->nF;
     const long long n_list[2] = { (long long)nV + nF, (long long)nE };
@@ -279,12 +280,19 @@ void build_boxes_sliced(sccd_ctx* c, double inflation_radius)
         launch_box_stats(
             samp[k], S.ns, 1, base, base + kStatsBlocks * kNumStats, st, c->lc, (double)S.stride);
         SCCD_CUDA(cudaMemcpyAsync(
-            H.stats, base + kStatsBlocks * kNumStats, kNumStats * sizeof(double),
+            H.stats_next, base + kStatsBlocks * kNumStats, kNumStats * sizeof(double),
             cudaMemcpyDeviceToHost, st));
     }
     kt_end(c, kt_boxes);
     record(c, EV_BUILD);
-    host_sync(c, st); // sync 1: statistics
+    // frame-to-frame (as build_boxes): the previous build's statistics choose the grid at once;
+    // every rank holds the same history, hence takes the same decision
+    const bool reuse = stats_reusable(c, 0, n_list[0]) && stats_reusable(c, 1, n_list[1]);
+    if (!reuse) {
+        host_sync(c, st); // sync 1: statistics
+        adopt_stats(c, 0, n_list[0]);
+        adopt_stats(c, 1, n_list[1]);
+    }
 
     // next sweep axis from the sample variance (as build_boxes)
     for (int k = 0; k < 2; k++) {
@@ -510,6 +518,10 @@ void build_boxes_sliced(sccd_ctx* c, double inflation_radius)
     c->sort1_pending = true;
     c->gather_timed = c->opt.profile != 0;
     record(c, EV_SORT);
+    if (reuse) { // this build's statistics arrived with sync 2: they steer the next build
+        adopt_stats(c, 0, n_list[0]);
+        adopt_stats(c, 1, n_list[1]);
+    }
     c->have_boxes = true;
     c->sliced = true;
     c->runs[0].bp_kind = c->runs[1].bp_kind = -1;

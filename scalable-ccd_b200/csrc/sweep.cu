@@ -58,6 +58,52 @@ struct SweepSmem {
     uint32_t staged; // pairs this tile has parked (or tried to park) so far
 };
 
+// ---- TMA-staged variant of the count pass (SCCD_OPT_SWEEP_STAGED) --------------------------------
+// The window loop reads the prefilter stream of the records that FOLLOW the tile's owners: keys
+// (4 B) and, for candidates that pass the key tests, the f32 yz record (16 B).  Here one thread
+// of the CTA brings the next kStageRecs records of both arrays into shared memory with two bulk
+// async copies (cp.async.bulk, completion on an mbarrier) before the sweep starts; the loop then
+// reads shared memory and only falls back to global memory for windows that reach beyond the
+// staged records.  A/B against the L1-resident loop: DESIGN.md 3.3.
+constexpr int kStageRecs = 1024;
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase)
+{
+    unsigned done = 0;
+    while (!done)
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(phase)
+            : "memory");
+}
+struct __align__(16) StageSmem {
+    float4 yz[kStageRecs];
+    uint32_t key[kStageRecs];
+    unsigned long long bar;
+};
+
 struct Staging {
     sccd_pair* pairs = nullptr; // kStage per tile
     uint32_t* tags = nullptr;   // kStage per tile
@@ -152,13 +198,13 @@ __device__ __forceinline__ void drain32(
 // Sweep of the tile of kTile owners starting at tile0; only owners in [owner_lo, owner_hi)
 // take part.  FILL = false: count (counts[]) and park the pairs (staging, st_*);
 // FILL = true: write the pairs of the chunk that starts at owner chunk_lo to pairs[].
-template <bool FILL, bool TWO_LISTS>
+template <bool FILL, bool TWO_LISTS, bool STAGED = false>
 __device__ __forceinline__ void sweep_tile(
     SweepSmem& sm, const PrefilterArrays& pf, const BoxArrays& box, int n, int shard_lo,
     int tile0, int owner_lo, int owner_hi, int chunk_lo, uint32_t* __restrict__ counts,
     const unsigned long long* __restrict__ offsets, sccd_pair* __restrict__ pairs,
     unsigned long long* __restrict__ n_candidates, sccd_pair* __restrict__ st_pairs,
-    uint32_t* __restrict__ st_tags)
+    uint32_t* __restrict__ st_tags, const StageSmem* stg = nullptr, int staged = 0)
 {
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -197,7 +243,12 @@ __device__ __forceinline__ void sweep_tile(
 #pragma unroll
         for (int u = 0; u < kStep; u++) {
             const int j = i + k + u;
-            kj[u] = (valid && j < n) ? __ldg(&pf.key[j]) : 0xffffffffu;
+            if (STAGED)
+                kj[u] = (valid && j < n)
+                    ? (j - tile0 < staged ? stg->key[j - tile0] : __ldg(&pf.key[j]))
+                    : 0xffffffffu;
+            else
+                kj[u] = (valid && j < n) ? __ldg(&pf.key[j]) : 0xffffffffu;
         }
         // keys are sorted: nothing later can be in a window if the first of the trip is in none
         if (!__any_sync(kFull, valid && kj[0] <= my_reach && i + k < n))
@@ -212,7 +263,7 @@ __device__ __forceinline__ void sweep_tile(
                 p[u] = p[u] && ((kj[u] ^ my_flags) & kKeyFlagType) != 0u;
             b[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p[u])
-                b[u] = __ldg(&pf.yz[j]);
+                b[u] = (STAGED && j - tile0 < staged) ? stg->yz[j - tile0] : __ldg(&pf.yz[j]);
         }
 #pragma unroll
         for (int u = 0; u < kStep; u++) {
@@ -271,6 +322,40 @@ __global__ void __launch_bounds__(kTile) sweep_count_kernel(
         sm, pf, box, n, shard_lo, tile0, shard_lo, shard_hi, shard_lo, counts, nullptr, nullptr,
         n_candidates, st.pairs + (size_t)blockIdx.x * kStage,
         st.tags + (size_t)blockIdx.x * kStage);
+    __syncthreads();
+    if (threadIdx.x == 0)
+        st.count[blockIdx.x] = sm.staged;
+}
+
+// count pass with the prefilter stream of the tile staged in shared memory by bulk async copies
+template <bool TWO_LISTS>
+__global__ void __launch_bounds__(kTile) sweep_count_staged_kernel(
+    PrefilterArrays pf, BoxArrays box, int n, int shard_lo, int shard_hi,
+    uint32_t* __restrict__ counts, unsigned long long* __restrict__ n_candidates, Staging st)
+{
+    __shared__ SweepSmem sm;
+    __shared__ StageSmem stg;
+    const int tile0 = shard_lo + blockIdx.x * kTile;
+    // whole 16-byte units only, from a 16-byte aligned start (else: nothing staged)
+    int staged = min(kStageRecs, n - tile0) & ~3;
+    if ((tile0 & 3) != 0 || staged < 0)
+        staged = 0;
+    if (threadIdx.x == 0) {
+        sm.staged = 0;
+        mbar_init(&stg.bar, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && staged > 0) {
+        mbar_expect_tx(&stg.bar, (unsigned)staged * 20u);
+        bulk_g2s(stg.key, pf.key + tile0, (unsigned)staged * 4u, &stg.bar);
+        bulk_g2s(stg.yz, pf.yz + tile0, (unsigned)staged * 16u, &stg.bar);
+    }
+    if (staged > 0)
+        mbar_wait(&stg.bar, 0);
+    sweep_tile<false, TWO_LISTS, true>(
+        sm, pf, box, n, shard_lo, tile0, shard_lo, shard_hi, shard_lo, counts, nullptr, nullptr,
+        n_candidates, st.pairs + (size_t)blockIdx.x * kStage,
+        st.tags + (size_t)blockIdx.x * kStage, &stg, staged);
     __syncthreads();
     if (threadIdx.x == 0)
         st.count[blockIdx.x] = sm.staged;
@@ -368,7 +453,7 @@ void launch_sweep_windows(
 void launch_sweep_count(
     const SortedList& L, int owner_lo, int owner_hi, uint32_t* counts,
     unsigned long long* n_candidates, void* stage_pairs, void* stage_tags, uint32_t* stage_count,
-    cudaStream_t s, LaunchCounter& lc)
+    cudaStream_t s, LaunchCounter& lc, bool tma_staged)
 {
     if (L.n >= (1 << kRelBits))
         throw std::runtime_error("sweep: more than 2^27 records in one list is not supported");
@@ -380,7 +465,13 @@ void launch_sweep_count(
     st.tags = (uint32_t*)stage_tags;
     st.count = stage_count;
     const int grid = (owners + kTile - 1) / kTile;
-    if (L.two_lists)
+    if (tma_staged && L.two_lists)
+        sweep_count_staged_kernel<true><<<grid, kTile, 0, s>>>(
+            L.pf, L.box, L.n, owner_lo, owner_hi, counts, n_candidates, st);
+    else if (tma_staged)
+        sweep_count_staged_kernel<false><<<grid, kTile, 0, s>>>(
+            L.pf, L.box, L.n, owner_lo, owner_hi, counts, n_candidates, st);
+    else if (L.two_lists)
         sweep_count_kernel<true><<<grid, kTile, 0, s>>>(
             L.pf, L.box, L.n, owner_lo, owner_hi, counts, n_candidates, st);
     else

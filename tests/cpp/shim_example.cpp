@@ -46,6 +46,14 @@ int main(int argc, char** argv)
     const Scalar toi2 =
         ccd(V0, V1, E, F, min_distance, max_iterations, tolerance, allow_zero_toi, collisions);
     const Scalar toi3 = ipc_ccd_strategy(V0, V1, E, F, min_distance, max_iterations, tolerance);
+    // the reference's max_iter rule (drop) on request; without a cap both rules are the same
+    set_max_iter_mode(1);
+    const Scalar toi_drop = ccd(V0, V1, E, F, min_distance, max_iterations, tolerance, allow_zero_toi);
+    set_max_iter_mode(0);
+    if (toi_drop != toi) {
+        std::fprintf(stderr, "max_iter mode changed an uncapped result\n");
+        return 1;
+    }
 
     std::vector<AABB> vb, eb, fb;
     build_boxes(V0, V1, E, F, vb, eb, fb);

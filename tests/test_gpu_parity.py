@@ -703,3 +703,83 @@ def test_time_ordered_solve_skips_work_but_changes_no_result(sccd, orc, scene_c1
         assert c.stats()["n_skipped"] == [0, 0]
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("max_cells", [0, 1])
+def test_tma_staged_sweep_gives_the_same_list(sccd, scene_c1, scene_small, max_cells):
+    """SCCD_OPT_SWEEP_STAGED: the count pass reads its window from shared memory filled by bulk
+    async copies -- same pairs in the same order, also for owner slices that start at unaligned
+    records (one-axis sweep, 3 shards) and for tiles whose windows outrun the staged records."""
+    K = sccd.capi
+    c = sccd.Context(0)
+    try:
+        c.set_grid_cells(max_cells)
+        for s in (scene_small, scene_c1):
+            c.upload_mesh(s["V0"], s["V1"], s["E"], s["F"])
+            for world in (1, 3):
+                lists = {}
+                for staged in (0, 1):
+                    c.set_option(K.OPT_SWEEP_STAGED, staged)
+                    parts = []
+                    for r in range(world):
+                        c.set_shard(r, world)
+                        c.build_boxes(0.0)
+                        parts.append([c.broad_phase(0), c.broad_phase(1)])
+                    lists[staged] = parts
+                c.set_shard(0, 1)
+                for r in range(world):
+                    for k in (0, 1):
+                        assert np.array_equal(lists[0][r][k], lists[1][r][k])
+        c.set_option(K.OPT_SWEEP_STAGED, 1)
+        toi1 = c.ccd()
+        c.set_option(K.OPT_SWEEP_STAGED, 0)
+        assert c.ccd() == toi1
+    finally:
+        c.close()
+
+
+def test_frame_to_frame_grid_reuse(sccd, orc, scene_small):
+    """SCCD_OPT_REUSE_GRID: a build with the list sizes of the previous one takes its
+    cell grid and key quantisation from the PREVIOUS build's statistics (one host sync less); the
+    mesh may have moved, stretched or left the old bounding box altogether -- same pairs, same
+    TOI.  The first build after an upload of another size waits for its own statistics again."""
+    K = sccd.capi
+    s = scene_small
+    c = sccd.Context(0)
+    fresh = sccd.Context(0)
+    fresh.set_option(K.OPT_REUSE_GRID, 0)
+    try:
+        assert c.get_option(K.OPT_REUSE_GRID) == 1
+        c.upload_mesh(s["V0"], s["V1"], s["E"], s["F"])
+        toi = c.ccd()
+        first = c.stats()["n_host_syncs"]
+        assert toi == orc.ccd(s)["toi"]
+        c.ccd()
+        again = c.stats()["n_host_syncs"]
+        assert again == first - 1, (first, again)
+        # frames that leave the statistics of the previous build far behind
+        frames = [(1.0, np.zeros(3)), (1.0, np.array([50.0, -20.0, 3.0])), (7.5, np.array([-3.0, 0.5, 9.0])),
+                  (0.01, np.array([1e3, 1e3, 1e3])), (1.0, np.zeros(3))]
+        for scale, shift in frames:
+            V0 = np.asfortranarray(s["V0"] * scale + shift)
+            V1 = np.asfortranarray(s["V1"] * scale + shift)
+            c.update_vertices(V0, V1)
+            got = c.ccd()
+            assert c.stats()["n_host_syncs"] == again
+            fresh.upload_mesh(V0, V1, s["E"], s["F"])
+            assert fresh.ccd() == got
+            assert fresh.stats()["n_pairs"] == c.stats()["n_pairs"]
+            for k in (0, 1):
+                assert np.array_equal(orc.canonical(c.broad_phase(k)), orc.canonical(fresh.broad_phase(k)))
+        # another mesh size: no stale statistics
+        s2 = sccd.scenes.cloth_on_sphere(17, seed=3, sphere="uv")
+        c.upload_mesh(s2["V0"], s2["V1"], s2["E"], s2["F"])
+        assert c.ccd() == orc.ccd(s2)["toi"]
+        assert c.stats()["n_host_syncs"] == first
+        # the option off: every build waits for its own statistics
+        c.set_option(K.OPT_REUSE_GRID, 0)
+        c.ccd()
+        assert c.stats()["n_host_syncs"] == first
+    finally:
+        c.close()
+        fresh.close()

@@ -32,18 +32,32 @@ KEEP = [
     "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
 ]
 
-# report kernel name -> name used in bench.py's roofline table
-def bench_name(k, seen):
-    if "sweep_count_kernel" in k:
-        return "sweep_count_vf" if "<(bool)1>" in k or "<1>" in k else "sweep_count_ee"
+# report kernel name -> key of bench.py's roofline table ("<key>" = first word of the entry).
+# `state` carries what the launch order tells: the radix passes before the first gather of a
+# step sort the vertex-face list, those after it the edge list.
+def bench_name(k, state):
+    vf = "<(bool)1" in k or "<1," in k or "<1>" in k
+    if "sweep_count" in k:
+        return "sweep_count_vf" if vf else "sweep_count_ee"
     if "sweep_place_kernel" in k:
-        return "sweep_fill_vf" if "<(bool)1>" in k or "<1>" in k else "sweep_fill_ee"
-    if "narrow_round_kernel" in k or "narrow_cull_kernel" in k or "narrow_coop_kernel" in k:
-        return "narrow_vf" if "<(bool)1>" in k or "<1>" in k else "narrow_ee"
-    if "gather_sorted" in k:
+        return "sweep_place_vf" if vf else "sweep_place_ee"
+    if "narrow_cull_kernel" in k:
+        return "narrow_cull_vf" if vf else "narrow_cull_ee"
+    if "narrow_round_kernel" in k or "narrow_coop_kernel" in k or "narrow_group_kernel" in k:
+        # all solver launches of a pass (scout, bulk, later rounds) add up under one key: the
+        # kernel name does not tell the rounds apart
+        return "narrow_solve_vf" if vf else "narrow_solve_ee"
+    if "gather_sorted" in k or "gather_rebuild" in k:
+        state["list"] = 1 - state.get("list", 0)
         return "gather"
+    if "radix_pass_kernel" in k or "radix_hist_kernel" in k or "digit_hist_kernel" in k:
+        if "DestDigit" in k:
+            return "partition"
+        return "radix_sort_vf" if state.get("list", 0) == 0 else "radix_sort_ee"
     if "boxes_kernel" in k:
         return "boxes"
+    if "expand_" in k:
+        return "expand"
     return None
 
 
@@ -56,6 +70,7 @@ def main():
     hdr, units = rows[0], rows[1]
     name_i = hdr.index("Kernel Name")
     traffic = {}
+    state = {}
     with open(out, "w") as f:
         f.write(f"# ncu --set full --clock-control none --import-source on, workload {workload}. {comment}\n")
         f.write("# one block per profiled launch, in launch order; times are cold-cache and serialised\n")
@@ -66,7 +81,10 @@ def main():
                 if m in hdr:
                     i = hdr.index(m)
                     f.write(f"{m:90s} {r[i]:>18s} {units[i]}\n")
-            b = bench_name(k, traffic)
+            if "vertex_boxes_kernel" in k:      # a step begins; traffic is summed over the first
+                state["step"] = state.get("step", 0) + 1   # COMPLETE step of the capture
+                state["list"] = 0
+            b = bench_name(k, state) if state.get("step", 0) == 1 else None
             if b and "dram__bytes_read.sum" in hdr:
                 def val(m):
                     i = hdr.index(m)
