@@ -111,6 +111,9 @@ typedef struct {
     int32_t key_bits[2];     /* sort-key bits in use (cell + quantised major axis) per list       */
     int64_t n_skipped[2];    /* cull survivors never started: their toi lower bound was not below
                                 the running earliest toi (shared-bound mode, max_iter < 0)        */
+    int64_t n_relaunched;    /* narrow-phase batches whose solver kernels were chosen for the
+                                survivor-list length of the previous batch and had to be
+                                launched again because the length class changed              */
 } sccd_stats;
 /* sizeof(sccd_stats) of the library (binding sanity check) */
 size_t sccd_stats_size(void);

@@ -60,7 +60,7 @@ class Stats(C.Structure):
         ("n_records_sent", C.c_int64 * 2), ("n_records_received", C.c_int64 * 2),
         ("ms_exchange", C.c_float), ("ms_k_sort", C.c_float * 2), ("ms_k_expand", C.c_float * 2),
         ("ms_k_cull", C.c_float * 2), ("ms_k_round", (C.c_float * 5) * 2), ("pad2_", C.c_float),
-        ("key_bits", C.c_int32 * 2), ("n_skipped", C.c_int64 * 2),
+        ("key_bits", C.c_int32 * 2), ("n_skipped", C.c_int64 * 2), ("n_relaunched", C.c_int64),
     ]
 
     def as_dict(self):

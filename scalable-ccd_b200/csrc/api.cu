@@ -963,11 +963,13 @@ void narrow_enqueue(
             tev[2 + 2 * r] = c->ktimers[id].a, tev[3 + 2 * r] = c->ktimers[id].b;
         }
     const size_t kt = kt_begin(c, &c->stats.ms_k_narrow[kind]);
+    // (every round has its own timer in profile mode: all of them are launched then)
+    const int hint = (c->opt.profile || !c->opt.reuse_grid) ? -1 : c->np_hint[kind];
     launch_narrow_phase(
         kind == SCCD_VF, c->f32, in, P, R.b_counters.as<NarrowCounters>(), d_gtoi,
         R.b_items[0].as<WorkItem>(), R.b_items[1].as<WorkItem>(), R.item_cap, d_toi_per_query,
         checks, survivors, tlb, R.b_surv_sort.ptr, R.b_surv_sort.cap, c->num_sms, st, c->lc, tev,
-        solver_waits_for);
+        solver_waits_for, hint, false);
     kt_end(c, kt);
     SCCD_CUDA(cudaMemcpyAsync(
         R.h_counters, R.b_counters.ptr, sizeof(NarrowCounters), cudaMemcpyDeviceToHost, st));
@@ -979,6 +981,9 @@ void narrow_enqueue(
     R.pending.d_tq = d_toi_per_query;
     R.pending.checks = checks;
     R.pending.culling = survivors != nullptr;
+    R.pending.hint = hint;
+    R.pending.survivors = survivors;
+    R.pending.tlb = tlb;
 }
 
 void narrow_finish(sccd_ctx* c, double* d_gtoi)
@@ -990,6 +995,23 @@ void narrow_finish(sccd_ctx* c, double* d_gtoi)
     R.pending.active = false;
     const int kind = R.pending.kind;
     host_sync(c, st);
+    if (R.pending.hint >= 0 && R.h_counters->n_items[0] != 0 && R.h_counters->round0_ran == 0) {
+        // the survivor list is not of the length the launches were chosen for (a short list
+        // where rounds were launched, or the other way round): none of them found work.  Launch
+        // the solver again, every kernel this time.
+        launch_narrow_phase(
+            kind == SCCD_VF, c->f32, R.pending.in, R.pending.P, R.b_counters.as<NarrowCounters>(),
+            d_gtoi, R.b_items[0].as<WorkItem>(), R.b_items[1].as<WorkItem>(), R.item_cap,
+            R.pending.d_tq, R.pending.checks, R.pending.survivors, R.pending.tlb, R.b_surv_sort.ptr,
+            R.b_surv_sort.cap, c->num_sms, st, c->lc, nullptr, nullptr, -1, true);
+        SCCD_CUDA(cudaMemcpyAsync(
+            R.h_counters, R.b_counters.ptr, sizeof(NarrowCounters), cudaMemcpyDeviceToHost, st));
+        SCCD_CUDA(cudaMemcpyAsync(&c->h_gtoi[0], d_gtoi, 8, cudaMemcpyDeviceToHost, st));
+        host_sync(c, st);
+        c->stats.n_relaunched++;
+    }
+    if (R.h_counters->round0_ran)
+        c->np_hint[kind] = R.h_counters->round0_ran == 2 ? 1 : 0;
     // the last round only hands work on when a path outgrows the lane state: rerun it
     for (int extra = 0; R.h_counters->n_items[kNarrowRounds] != 0 && R.h_counters->overflow != 2;
          extra++) {

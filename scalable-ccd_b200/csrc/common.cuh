@@ -292,6 +292,7 @@ struct alignas(128) NarrowCounters {
     } queue[2];
     alignas(128) int overflow;                        // an item list was full (work kept local)
     int bad_input;                                    // a pair id is no element of the mesh
+    int round0_ran; // which launch found round 0's work: 1 lane-per-tree (long list), 2 work queue
     unsigned long long box_checks;
     unsigned long long round_checks[kNarrowRounds]; // box checks per round (load-balance report)
     unsigned long long donated;
@@ -442,7 +443,13 @@ void launch_narrow_phase(
     float* tlb /* in.n: lower bound of every surviving query's toi */, void* sort_temp,
     size_t sort_temp_bytes, int num_sms, cudaStream_t s, LaunchCounter& lc,
     const cudaEvent_t* tev = nullptr /* 2 * (1 + kNarrowRounds) optional timing events */,
-    cudaEvent_t solver_waits_for = nullptr /* the rounds (not the cull) start after this event */);
+    cudaEvent_t solver_waits_for = nullptr /* the rounds (not the cull) start after this event */,
+    // Which kernels solve a batch depends on the length of its survivor list, known on the device
+    // only; launching all of them costs ~6 kernels per batch that return at once.  mode_hint says
+    // what the previous batch of this kind needed (1: short list -> work queue only; 0: long list
+    // -> scout + rounds; -1: launch everything).  counters->round0_ran tells afterwards whether
+    // the guess was right; if not, call again with solver_only = true and mode_hint = -1.
+    int mode_hint = -1, bool solver_only = false);
 size_t sort_survivors_temp_bytes(long long n_max);
 // hist: the 256-bucket histogram of bits 32..39 the producer made (device).  The sort does
 // nothing when the buckets do not discriminate (2 * hist[0] >= *d_n; narrow.cu: ordering_on).

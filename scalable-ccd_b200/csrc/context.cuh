@@ -128,9 +128,15 @@ struct sccd_ctx {
             double* d_tq = nullptr;
             unsigned int* checks = nullptr;
             bool culling = false;
+            int hint = -1; // the guess the launches were chosen by (launch_narrow_phase)
+            unsigned long long* survivors = nullptr;
+            float* tlb = nullptr;
         } pending;
     } runs[2]; // [1]: the edge list's broad phase + narrow phase on the sort stream (pipeline)
     Run* cur = &runs[0];
+    // what the previous batch of each kind needed: 1 work queue (short survivor list), 0 rounds
+    // (long list), -1 unknown.  Frame to frame the list length hardly changes.
+    int np_hint[2] = { -1, -1 };
     DevBuf b_gtoi; // earliest toi shared by the two lists of a pipeline call
     double* h_gtoi = nullptr; // pinned
 

@@ -178,11 +178,13 @@ def np_env(ctx, sccd):
 
 
 # refill (6 bits) | no scout << 6 | no skip << 7 | first-round budget << 8 | later budget (7 bits)
-# << 16 | survivors not sorted by toi lower bound << 23 | never-cooperate << 24 |
+# << 16 | no pair step (warp-per-tree walker checks one box per step) << 22 |
+# survivors not sorted by toi lower bound << 23 | never-cooperate << 24 |
 # log2(coop budget) - 3 << 25 | log2(coop limit) - 13 << 28
 VARIANTS = {"unsorted": 1 << 23, "no_scout": 1 << 6, "no_skip": 1 << 7, "lane_only": 1 << 24, "tiny_budgets": 4 | (3 << 8) | (2 << 16) | (1 << 25),
             "refill_every_lane": 1, "refill_all_idle": 32, "coop_big_budget": 5 << 25,
-            "coop_small_limit": 1 << 28}
+            "coop_small_limit": 1 << 28, "no_pair_step": 1 << 22,
+            "no_pair_tiny_budgets": (1 << 22) | 4 | (3 << 8) | (2 << 16) | (1 << 25)}
 
 
 @pytest.mark.parametrize("variant", list(VARIANTS))
@@ -204,7 +206,7 @@ def test_narrow_phase_scheduling_does_not_change_results(ctx, orc, sccd, torch_c
         assert np.array_equal(tpq1, otpq)
 
 
-@pytest.mark.parametrize("flags", [0, 1 << 24])
+@pytest.mark.parametrize("flags", [0, 1 << 24, 1 << 22])
 def test_paths_deeper_than_the_lane_state_are_handed_on(ctx, orc, sccd, torch_cuda, np_env, flags):
     """With only 6 trackable levels every non-trivial tree outgrows the walk state in every
     round, including the last: the boxes are handed on and the host keeps adding rounds."""
@@ -783,3 +785,39 @@ def test_frame_to_frame_grid_reuse(sccd, orc, scene_small):
     finally:
         c.close()
         fresh.close()
+
+
+def test_solver_launches_follow_the_previous_batch(sccd, scene_small):
+    """Which solver kernels a batch needs depends on the length of its survivor list, known on
+    the device only; the host launches what the previous batch of that kind needed and launches
+    the rest when the length class changed (sccd_stats.n_relaunched).  Alternating a cloth scene
+    (hundreds of survivors: work queue) with a pile (tens of thousands: rounds) must give what a
+    context that always launches everything gives, collisions included."""
+    K = sccd.capi
+    pile = sccd.scenes.blob_pile(1000, seed=2)
+    a, b = sccd.Context(0), sccd.Context(0)
+    b.set_option(K.OPT_REUSE_GRID, 0)              # no frame-to-frame guesses at all
+    try:
+        relaunched = 0
+        for s in (scene_small, scene_small, pile, pile, scene_small, pile, pile):
+            for c in (a, b):
+                c.upload_mesh(s["V0"], s["V1"], s["E"], s["F"])
+            ta, tb = a.ccd(), b.ccd()
+            assert ta == tb
+            sa, sb = a.stats(), b.stats()
+            assert sa["n_pairs"] == sb["n_pairs"] and sa["n_culled"] == sb["n_culled"]
+            assert sb["n_relaunched"] == 0
+            relaunched += sa["n_relaunched"]
+            ca, cb = a.ccd_collisions(), b.ccd_collisions()
+            assert ca[0] == cb[0] == ta
+            for k in (1, 2):
+                oa, ob = np.lexsort(ca[k][0].T[::-1]), np.lexsort(cb[k][0].T[::-1])
+                assert np.array_equal(ca[k][0][oa], cb[k][0][ob])
+                assert np.array_equal(ca[k][1][oa], cb[k][1][ob])
+        assert relaunched >= 3                      # small -> pile, pile -> small, small -> pile
+        # the same scene again: the guess holds
+        a.ccd()
+        assert a.stats()["n_relaunched"] == 0
+    finally:
+        a.close()
+        b.close()

@@ -29,6 +29,9 @@ for rep in range(2):
         ctx.ccd(); ctx.ccd()
         st = ctx.stats()
         out[f"{v}#{rep}"] = {"ms_per_step": a.elapsed_time(b) / 10, "toi": toi, "ms_sweep": st["ms_sweep"],
-                             "ms_k_sweep_count": st["ms_k_sweep_count"], "n_pairs": st["n_pairs"]}
+                             "ms_k_sweep_count": st["ms_k_sweep_count"], "n_pairs": st["n_pairs"],
+                             "ms_narrow": st["ms_narrow"], "ms_k_cull": st["ms_k_cull"],
+                             "ms_k_round": st["ms_k_round"], "n_culled": st["n_culled"],
+                             "n_box_checks": st["n_box_checks"], "n_skipped": st["n_skipped"]}
 ctx.close()
 print(json.dumps(out))
