@@ -929,6 +929,14 @@ void narrow_enqueue(
     // lower bounds only where they can pay: the shared minimum (not the per-query list), and not
     // while the previous frames of this pass showed them useless (narrow_finish)
     P.want_tlb = !d_toi_per_query && c->tlb_pause[kind] == 0;
+    // Work-queue launch: warps for ~1/24 of the survivors the previous batch of this kind had (at
+    // least 32 CTAs).  Every resident warp starts a root at once, before any bound exists, and
+    // what it finds after the bound has dropped was wasted: config 2's vertex-face pass (14,600
+    // survivors) does 204 K box checks on 296 CTAs, 105 K on 148, 55 K on 74 (0.74 / 0.71 /
+    // 0.69 ms per step), 29 K on 37 (0.72: too few warps to cut the deep trees).
+    P.queue_ctas = c->opt.queue_ctas[kind];
+    if (P.queue_ctas == 0 && c->np_last_survivors[kind] > 0 && c->opt.reuse_grid)
+        P.queue_ctas = (int)std::max<long long>(32, (c->np_last_survivors[kind] + 191) / 192);
     if (!d_toi_per_query && c->tlb_pause[kind] > 0)
         c->tlb_pause[kind]--;
     SCCD_CUDA(cudaMemsetAsync(R.b_counters.ptr, 0, sizeof(NarrowCounters), st));
@@ -1012,6 +1020,8 @@ void narrow_finish(sccd_ctx* c, double* d_gtoi)
     }
     if (R.h_counters->round0_ran)
         c->np_hint[kind] = R.h_counters->round0_ran == 2 ? 1 : 0;
+    if (R.pending.culling)
+        c->np_last_survivors[kind] = (long long)R.h_counters->n_items[0];
     // the last round only hands work on when a path outgrows the lane state: rerun it
     for (int extra = 0; R.h_counters->n_items[kNarrowRounds] != 0 && R.h_counters->overflow != 2;
          extra++) {
@@ -1037,7 +1047,13 @@ void narrow_finish(sccd_ctx* c, double* d_gtoi)
             && (r.n_items[0] - r.started) * 2ull < r.n_items[0])
             // (measured: config 4's edge pass skips 25 % of its survivors and saves 7 % of its
             // box checks, for a cull that is 2 ms = 66 % longer; config 2 skips 66 % / 99 %)
-            c->tlb_pause[kind] = 15;
+        {
+            // (again useless: ask less and less often -- 15, 31 .. 255 batches)
+            c->tlb_pause_len[kind] = std::min(255, c->tlb_pause_len[kind] * 2 + 1);
+            c->tlb_pause[kind] = c->tlb_pause_len[kind];
+        } else if (R.pending.P.want_tlb) {
+            c->tlb_pause_len[kind] = 7;
+        }
     }
     c->stats.n_donated[kind] += (int64_t)r.donated;
     for (int i = 0; i <= kNarrowRounds; i++) {
@@ -1375,6 +1391,11 @@ int sccd_create(int device, void* stream, sccd_ctx** out)
         SCCD_CUDA(cudaEventCreateWithFlags(&c->ev_vf_done, cudaEventDisableTiming));
         SCCD_CUDA(cudaEventCreateWithFlags(&c->ev_boxes, cudaEventDisableTiming));
         SCCD_CUDA(cudaEventCreateWithFlags(&c->ev_stats, cudaEventDisableTiming));
+        if (const char* e = getenv("SCCD_QUEUE_CTAS")) { // "vf,ee" (experiments)
+            int a = 0, b = 0;
+            if (sscanf(e, "%d,%d", &a, &b) >= 1)
+                c->opt.queue_ctas[0] = a, c->opt.queue_ctas[1] = b;
+        }
         if (const char* e = getenv("SCCD_REUSE_GRID"))
             c->opt.reuse_grid = atoi(e) != 0;
         c->runs[1].stream = c->sort_stream;

@@ -100,6 +100,7 @@ struct sccd_ctx {
         int concurrent_passes = 0; // edge-edge solver does not wait for the vertex-face one
         int sweep_staged = 0;   // sweep count pass reads its window from TMA-staged shared memory
         int reuse_grid = 1;     // frame-to-frame: grid from the previous build's statistics
+        int queue_ctas[2] = { 0, 0 }; // CTAs of the work-queue launch per list (0: all that fit)
     } opt;
     int next_axis = 0;          // argmax of the box-centre variance of the last build
 
@@ -137,6 +138,7 @@ struct sccd_ctx {
     // what the previous batch of each kind needed: 1 work queue (short survivor list), 0 rounds
     // (long list), -1 unknown.  Frame to frame the list length hardly changes.
     int np_hint[2] = { -1, -1 };
+    long long np_last_survivors[2] = { 0, 0 }; // cull survivors of the previous batch of each kind
     DevBuf b_gtoi; // earliest toi shared by the two lists of a pipeline call
     double* h_gtoi = nullptr; // pinned
 
@@ -162,6 +164,7 @@ struct sccd_ctx {
     // that pass do not compute them (a third of the cull's arithmetic); every 16th batch probes
     // again.
     int tlb_pause[2] = { 0, 0 };
+    int tlb_pause_len[2] = { 7, 7 }; // doubles (+1) every time the bounds turn out useless again
     bool sliced = false;                // the mesh lists hold slices / received records
     DevBuf b_xcnt, b_xsplits;           // all ranks' send counts; both lists' cell splits
     unsigned long long* h_xcnt = nullptr; // pinned

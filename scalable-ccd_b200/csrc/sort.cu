@@ -120,7 +120,7 @@ struct SortSmem {
 
 // One digit pass.  status: n_tiles x 256 words, zero before the launch; ctr: tile ticket.
 template <typename Digit>
-__global__ void __launch_bounds__(kThreads) radix_pass_kernel(
+__global__ void __launch_bounds__(kThreads, 4) radix_pass_kernel(
     const unsigned long long* __restrict__ in, unsigned long long* __restrict__ out, long long n,
     Digit digit, const uint32_t* __restrict__ hist /* 256: this pass */,
     uint32_t* __restrict__ status, uint32_t* __restrict__ ctr,

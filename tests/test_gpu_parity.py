@@ -683,6 +683,7 @@ def test_time_ordered_solve_skips_work_but_changes_no_result(sccd, orc, scene_c1
     c = sccd.Context(0)
     try:
         c.upload_mesh(s["V0"], s["V1"], s["E"], s["F"])
+        c.ccd()      # (the work queue's grid follows the previous batch: same for every variant)
         checks = {}
         for name, flags in (("on", 0), ("no_scout", 1 << 6), ("no_skip", 1 << 7),
                             ("unsorted", 1 << 23), ("all_off", (1 << 6) | (1 << 7) | (1 << 23))):
