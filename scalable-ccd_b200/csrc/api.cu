@@ -934,6 +934,7 @@ void narrow_enqueue(
     // what it finds after the bound has dropped was wasted: config 2's vertex-face pass (14,600
     // survivors) does 204 K box checks on 296 CTAs, 105 K on 148, 55 K on 74 (0.74 / 0.71 /
     // 0.69 ms per step), 29 K on 37 (0.72: too few warps to cut the deep trees).
+    P.root_check = c->opt.np_cull == 1;
     P.queue_ctas = c->opt.queue_ctas[kind];
     if (P.queue_ctas == 0 && c->np_last_survivors[kind] > 0 && c->opt.reuse_grid)
         P.queue_ctas = (int)std::max<long long>(32, (c->np_last_survivors[kind] + 191) / 192);
@@ -994,12 +995,13 @@ void narrow_enqueue(
     R.pending.tlb = tlb;
 }
 
-void narrow_finish(sccd_ctx* c, double* d_gtoi)
+// returns whether it waited for the run's stream (which is then idle)
+bool narrow_finish(sccd_ctx* c, double* d_gtoi)
 {
     auto& R = *c->cur;
     cudaStream_t st = R.stream;
     if (!R.pending.active)
-        return;
+        return false;
     R.pending.active = false;
     const int kind = R.pending.kind;
     host_sync(c, st);
@@ -1073,6 +1075,7 @@ void narrow_finish(sccd_ctx* c, double* d_gtoi)
         throw std::runtime_error(
             "narrow phase: item list too small to hand on a sub-tree deeper than 128 levels; "
             "raise it with sccd_set_queue_capacity");
+    return true;
 }
 
 // the shared earliest-toi word of the context
@@ -1237,8 +1240,8 @@ void run_pipeline(
         }
         for (int kind = 0; kind < 2; kind++) {
             c->cur = &c->runs[kind];
-            narrow_finish(c, d_gtoi);
-            host_sync(c, c->cur->stream);
+            if (!narrow_finish(c, d_gtoi))
+                host_sync(c, c->cur->stream);
         }
         c->cur = &c->runs[0];
         if (sharded) {
@@ -1370,7 +1373,7 @@ int sccd_create(int device, void* stream, sccd_ctx** out)
         if (const char* e = getenv("SCCD_NP_DEPTH"))
             c->opt.np_depth = std::min(128, std::max(2, atoi(e)));
         if (const char* e = getenv("SCCD_NP_CULL"))
-            c->opt.np_cull = atoi(e) != 0;
+            c->opt.np_cull = std::max(0, std::min(2, atoi(e)));
         if (const char* e = getenv("SCCD_KEY_STEPS"))
             c->opt.key_steps = std::min(16, std::max(0, atoi(e)));
         if (const char* e = getenv("SCCD_SWEEP_STAGED"))
@@ -1473,7 +1476,11 @@ int sccd_set_option(sccd_ctx* ctx, int option, int64_t value)
         return SCCD_ERR_ARG;
     auto& o = ctx->opt;
     switch (option) {
-    case SCCD_OPT_NARROW_CULL: o.np_cull = value != 0; break;
+    case SCCD_OPT_NARROW_CULL:
+        if (value < 0 || value > 2)
+            throw std::invalid_argument("SCCD_OPT_NARROW_CULL: 0, 1 or 2");
+        o.np_cull = (int)value;
+        break;
     case SCCD_OPT_NARROW_FLAGS: o.np_flags = (int)value; break;
     case SCCD_OPT_NARROW_FLAGS_EE: o.np_flags_ee = (int)value; break;
     case SCCD_OPT_NARROW_MAX_DEPTH:

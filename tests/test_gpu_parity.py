@@ -236,12 +236,17 @@ def test_separating_axis_cull_changes_no_result(ctx, orc, sccd, torch_cuda, scen
         ctx.reset_stats()
         toi1, tpq1 = _narrow_gpu(ctx, torch_cuda, kind, q, **kw)
         culled = ctx.stats()["n_culled"][kind]
+        np_env(cull=2)                            # separating axes only, no root-box check
+        ctx.reset_stats()
+        toi2, tpq2 = _narrow_gpu(ctx, torch_cuda, kind, q, **kw)
+        assert 0 < ctx.stats()["n_culled"][kind] <= culled
         np_env(cull=0)
         ctx.reset_stats()
         toi0, tpq0 = _narrow_gpu(ctx, torch_cuda, kind, q, **kw)
         assert ctx.stats()["n_culled"][kind] == 0
         np_env()
         assert np.array_equal(tpq0, tpq1) and toi0 == toi1
+        assert np.array_equal(tpq0, tpq2) and toi0 == toi2
         otoi, otpq, _ = orc.narrow_phase(q, kind == 0, kw["ms"], -1, kw["tol"], True)
         assert np.array_equal(tpq1, otpq) and toi1 == otoi
         if kw["ms"] == 0.0 and kw["tol"] == 1e-6:
@@ -798,6 +803,8 @@ def test_solver_launches_follow_the_previous_batch(sccd, scene_small):
     pile = sccd.scenes.blob_pile(1000, seed=2)
     a, b = sccd.Context(0), sccd.Context(0)
     b.set_option(K.OPT_REUSE_GRID, 0)              # no frame-to-frame guesses at all
+    for c in (a, b):
+        c.set_option(K.OPT_NARROW_CULL, 2)         # (keeps the pile's survivor lists long)
     try:
         relaunched = 0
         for s in (scene_small, scene_small, pile, pile, scene_small, pile, pile):

@@ -24,7 +24,7 @@ for fv in flags:
         toi = ctx.ccd()
         b.record(); torch.cuda.synchronize()
         st = ctx.stats()
-        steps.append((round(a.elapsed_time(b), 3), st["n_box_checks"], st["n_skipped"], st["n_relaunched"]))
+        steps.append((round(a.elapsed_time(b), 3), st["n_box_checks"], st["n_skipped"], st["n_relaunched"], st["n_culled"]))
     out[hex(fv)] = {"toi": toi, "steps": steps}
 ctx.close()
 print(json.dumps(out))
