@@ -417,7 +417,9 @@ def main():
             e2e_v = {"error": repr(exc)[:200]}
 
     # ---- kernel-level pass (untimed for `value`): every solver round gets its own event pair
-    ctx.set_option(K.OPT_PROFILE, 1)
+    # (profile mode 2: both lists on one stream, so that a kernel's event pair brackets that
+    # kernel alone -- with two streams the pairs include waiting behind the other list's kernels)
+    ctx.set_option(K.OPT_PROFILE, 2)
     prof = []
     for _ in range(3):
         flush.zero_()

@@ -201,8 +201,10 @@ int sccd_set_scalar_type(sccd_ctx* ctx, int type);
                                        while this build's statistics are computed off the
                                        critical path for the next one.  Any grid gives the same
                                        overlap set; 0 = wait for this build's own statistics.    */
-#define SCCD_OPT_PROFILE 10         /* 1: time every solver round with its own event pair
-                                       (sccd_stats.ms_k_round); 0 (default): stage timers only */
+#define SCCD_OPT_PROFILE 10         /* 1: time every kernel with its own event pair
+                                       (sccd_stats.ms_k_*); 2: the same with BOTH lists on the
+                                       caller's stream, so that a pair brackets its kernel alone
+                                       (roofline measurements); 0 (default): total only         */
 #define SCCD_OPT_SWEEP_AXIS 9       /* axis the mesh pipeline sorts and sweeps along: 0 (default,
                                        the reference's GPU path, aabb.cu:86), 1, 2, or -1 = the
                                        axis sort_and_sweep would hand back for the NEXT call --

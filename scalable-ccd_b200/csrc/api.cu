@@ -1478,7 +1478,7 @@ int sccd_set_option(sccd_ctx* ctx, int option, int64_t value)
     switch (option) {
     case SCCD_OPT_NARROW_CULL:
         if (value < 0 || value > 2)
-            throw std::invalid_argument("SCCD_OPT_NARROW_CULL: 0, 1 or 2");
+            return SCCD_ERR_ARG;
         o.np_cull = (int)value;
         break;
     case SCCD_OPT_NARROW_FLAGS: o.np_flags = (int)value; break;
@@ -1508,7 +1508,22 @@ int sccd_set_option(sccd_ctx* ctx, int option, int64_t value)
             return SCCD_ERR_ARG;
         ctx->grid_repl = (double)value / 1000.0;
         break;
-    case SCCD_OPT_PROFILE: o.profile = value != 0; break;
+    case SCCD_OPT_PROFILE: {
+        if (value < 0 || value > 2)
+            return SCCD_ERR_ARG;
+        // 2: everything on the caller's stream, so that a kernel's event pair brackets that
+        // kernel alone (with two streams the pairs of one list include the time its kernels
+        // wait behind the other list's)
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess
+            || cudaStreamSynchronize(ctx->sort_stream) != cudaSuccess)
+            return SCCD_ERR_CUDA;
+        if (!ctx->sort_stream_own)
+            ctx->sort_stream_own = ctx->sort_stream;
+        ctx->sort_stream = value == 2 ? ctx->stream : ctx->sort_stream_own;
+        ctx->runs[1].stream = ctx->sort_stream;
+        o.profile = (int)value;
+        break;
+    }
     case SCCD_OPT_CONCURRENT_PASSES: o.concurrent_passes = value != 0; break;
     case SCCD_OPT_SWEEP_STAGED: o.sweep_staged = value != 0; break;
     case SCCD_OPT_REUSE_GRID: o.reuse_grid = value != 0; break;

@@ -67,6 +67,8 @@ struct sccd_ctx {
     // the sort of a 1 M-box list is a dozen latency-bound launches that leave the GPU mostly
     // idle.  ev_counts: both lists counted (main stream); ev_sorted1: edge list sorted.
     cudaStream_t sort_stream = nullptr;
+    cudaStream_t sort_stream_own = nullptr; // the stream created for it (SCCD_OPT_PROFILE 2 aliases
+                                            // sort_stream to the caller's stream)
     cudaEvent_t ev_counts = nullptr, ev_sorted1 = nullptr, ev_vf_done = nullptr;
     cudaEvent_t ev_boxes = nullptr, ev_stats = nullptr; // frame-to-frame statistics (build_boxes)
     bool stats_in_flight = false;
@@ -199,6 +201,8 @@ struct sccd_ctx {
         }
         if (h_gtoi)
             cudaFreeHost(h_gtoi);
+        if (sort_stream_own)
+            sort_stream = sort_stream_own;
         if (sort_stream)
             cudaStreamDestroy(sort_stream);
         if (ev_counts)

@@ -829,3 +829,33 @@ def test_solver_launches_follow_the_previous_batch(sccd, scene_small):
     finally:
         a.close()
         b.close()
+
+
+def test_profile_modes_change_no_result(sccd, orc, scene_c1):
+    """SCCD_OPT_PROFILE 1 (event pair per kernel) and 2 (the same with both lists on the caller's
+    stream, so that a pair brackets its kernel alone): same TOI and pair counts as the untimed
+    pipeline, kernel times reported; an out-of-range value is an error, not an abort."""
+    K = sccd.capi
+    s = scene_c1
+    want = orc.ccd(s)
+    c = sccd.Context(0)
+    try:
+        c.upload_mesh(s["V0"], s["V1"], s["E"], s["F"])
+        assert c.ccd() == want["toi"]
+        base = c.stats()["n_pairs"]
+        for mode in (1, 2, 0, 2, 1, 0):
+            c.set_option(K.OPT_PROFILE, mode)
+            for _ in range(2):
+                assert c.ccd() == want["toi"]
+            st = c.stats()
+            assert st["n_pairs"] == base
+            if mode:
+                assert st["ms_k_boxes"] > 0 and min(st["ms_k_cull"]) > 0 and st["ms_k_gather"] > 0
+                assert st["ms_k_round"][0][0] > 0 and st["ms_k_round"][1][0] > 0
+        for bad_opt, bad in ((K.OPT_PROFILE, 3), (K.OPT_NARROW_CULL, 5), (K.OPT_NARROW_SOLVER, 3)):
+            with pytest.raises(sccd.SccdError) as e:
+                c.set_option(bad_opt, bad)
+            assert e.value.code == K.ERR_ARG
+        assert c.ccd() == want["toi"]
+    finally:
+        c.close()

@@ -7,4 +7,4 @@ d=json.loads(open("gpurun_out/r2_bench_c4_n${N}_f.json").read().strip().splitlin
 print(d["value"], d["e2e"]["value"], d["single_gpu_ms_same_workload"], d["speedup_vs_single_gpu"], d["host_syncs_per_step"], d["n_box_checks"])
 for r in d["stage_ms_per_rank"]: print({k:(round(v,2) if isinstance(v,float) else v) for k,v in r.items() if k in ("build","sort","sweep_vf","sweep_ee","narrow_vf","narrow_ee","exchange","total_device","host_syncs")})
 PY
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 tests/mgpu_check.py c4 --quick 2>&1 | tail -2
+
