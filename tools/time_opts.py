@@ -25,13 +25,16 @@ for rep in range(2):
         for _ in range(10):
             toi = ctx.ccd()
         b.record(); torch.cuda.synchronize()
-        ctx.set_option(sccd.capi.OPT_PROFILE, 1)
+        ctx.set_option(sccd.capi.OPT_PROFILE, 2)
         ctx.ccd(); ctx.ccd()
         st = ctx.stats()
         out[f"{v}#{rep}"] = {"ms_per_step": a.elapsed_time(b) / 10, "toi": toi, "ms_sweep": st["ms_sweep"],
                              "ms_k_sweep_count": st["ms_k_sweep_count"], "n_pairs": st["n_pairs"],
                              "ms_narrow": st["ms_narrow"], "ms_k_cull": st["ms_k_cull"],
                              "ms_k_round": st["ms_k_round"], "n_culled": st["n_culled"],
-                             "n_box_checks": st["n_box_checks"], "n_skipped": st["n_skipped"]}
+                             "n_box_checks": st["n_box_checks"], "n_skipped": st["n_skipped"],
+                             "n_records": st["n_records"], "n_candidates": st["n_candidates"],
+                             "ms_k_sort": st["ms_k_sort"], "ms_k_gather": st["ms_k_gather"],
+                             "grid_cells": st["grid_cells"]}
 ctx.close()
 print(json.dumps(out))
