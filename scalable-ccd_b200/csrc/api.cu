@@ -935,6 +935,7 @@ void narrow_enqueue(
     // survivors) does 204 K box checks on 296 CTAs, 105 K on 148, 55 K on 74 (0.74 / 0.71 /
     // 0.69 ms per step), 29 K on 37 (0.72: too few warps to cut the deep trees).
     P.root_check = c->opt.np_cull == 1;
+    P.tail_lanes = c->opt.np_tail_lanes;
     P.queue_ctas = c->opt.queue_ctas[kind];
     if (P.queue_ctas == 0 && c->np_last_survivors[kind] > 0 && c->opt.reuse_grid)
         P.queue_ctas = (int)std::max<long long>(32, (c->np_last_survivors[kind] + 191) / 192);
@@ -1394,6 +1395,8 @@ int sccd_create(int device, void* stream, sccd_ctx** out)
         SCCD_CUDA(cudaEventCreateWithFlags(&c->ev_vf_done, cudaEventDisableTiming));
         SCCD_CUDA(cudaEventCreateWithFlags(&c->ev_boxes, cudaEventDisableTiming));
         SCCD_CUDA(cudaEventCreateWithFlags(&c->ev_stats, cudaEventDisableTiming));
+        if (const char* e = getenv("SCCD_NP_TAIL")) // (experiments)
+            c->opt.np_tail_lanes = std::max(0, std::min(32, atoi(e)));
         if (const char* e = getenv("SCCD_QUEUE_CTAS")) { // "vf,ee" (experiments)
             int a = 0, b = 0;
             if (sscanf(e, "%d,%d", &a, &b) >= 1)

@@ -249,6 +249,8 @@ struct NarrowParams {
     int cap_drops;  // max_iter reached: 0 = accept the box at t_lo (conservative), 1 = drop it
     int want_tlb;   // the cull computes every survivor's toi lower bound (else: 0 for all)
     int queue_ctas; // CTAs of the work-queue launch (0: as many as fit)
+    int tail_lanes; // lane-per-tree rounds: a warp with this few busy lanes and an empty pool
+                    // hands its trees on to the next round (0: never)
     int root_check; // the cull also runs the solver's first box check on its survivors
     int solver;     // 0: by list length -- lane per tree in rounds (long), persistent work queue
                     // (short); 1: rounds for short lists too; 4, 8: lanes per tree (group solver)

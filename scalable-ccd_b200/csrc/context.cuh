@@ -103,6 +103,7 @@ struct sccd_ctx {
         int sweep_staged = 0;   // sweep count pass reads its window from TMA-staged shared memory
         int reuse_grid = 1;     // frame-to-frame: grid from the previous build's statistics
         int queue_ctas[2] = { 0, 0 }; // CTAs of the work-queue launch per list (0: all that fit)
+        int np_tail_lanes = 16;       // see NarrowParams::tail_lanes (config 3: 5.04 -> 4.92-4.97 ms)
     } opt;
     int next_axis = 0;          // argmax of the box-centre variance of the last build
 
