@@ -163,7 +163,8 @@ int sccd_set_scalar_type(sccd_ctx* ctx, int type);
 #define SCCD_OPT_NARROW_CULL 1      /* cull in front of the solver: 1 (default) = separating-axis
                                        test + the solver's own first box check (root box) on the
                                        queries that pass it; 2 = the separating-axis test alone;
-                                       0 = none.  Results never depend on it.                    */
+                                       3 = as 1 without the float pre-test in front of the double
+                                       test (A/B); 0 = none.  Results never depend on it.        */
 #define SCCD_OPT_NARROW_FLAGS 2     /* narrow-phase scheduling knobs (budgets, refill, kernel
                                        choice; see csrc/narrow.cu); results never depend on it */
 #define SCCD_OPT_NARROW_FLAGS_EE 3  /* the same for the edge-edge pass alone; < 0 = follow (2)  */

@@ -934,7 +934,8 @@ void narrow_enqueue(
     // what it finds after the bound has dropped was wasted: config 2's vertex-face pass (14,600
     // survivors) does 204 K box checks on 296 CTAs, 105 K on 148, 55 K on 74 (0.74 / 0.71 /
     // 0.69 ms per step), 29 K on 37 (0.72: too few warps to cut the deep trees).
-    P.root_check = c->opt.np_cull == 1;
+    P.root_check = c->opt.np_cull == 1 || c->opt.np_cull == 3;
+    P.cull_float = c->opt.np_cull != 3;
     P.tail_lanes = c->opt.np_tail_lanes;
     P.queue_ctas = c->opt.queue_ctas[kind];
     if (P.queue_ctas == 0 && c->np_last_survivors[kind] > 0 && c->opt.reuse_grid)
@@ -1374,7 +1375,7 @@ int sccd_create(int device, void* stream, sccd_ctx** out)
         if (const char* e = getenv("SCCD_NP_DEPTH"))
             c->opt.np_depth = std::min(128, std::max(2, atoi(e)));
         if (const char* e = getenv("SCCD_NP_CULL"))
-            c->opt.np_cull = std::max(0, std::min(2, atoi(e)));
+            c->opt.np_cull = std::max(0, std::min(3, atoi(e)));
         if (const char* e = getenv("SCCD_KEY_STEPS"))
             c->opt.key_steps = std::min(16, std::max(0, atoi(e)));
         if (const char* e = getenv("SCCD_SWEEP_STAGED"))
@@ -1480,7 +1481,7 @@ int sccd_set_option(sccd_ctx* ctx, int option, int64_t value)
     auto& o = ctx->opt;
     switch (option) {
     case SCCD_OPT_NARROW_CULL:
-        if (value < 0 || value > 2)
+        if (value < 0 || value > 3)
             return SCCD_ERR_ARG;
         o.np_cull = (int)value;
         break;

@@ -252,6 +252,7 @@ struct NarrowParams {
     int tail_lanes; // lane-per-tree rounds: a warp with this few busy lanes and an empty pool
                     // hands its trees on to the next round (0: never)
     int root_check; // the cull also runs the solver's first box check on its survivors
+    int cull_float; // double build: float pre-test + per-CTA compaction in front of the double test
     int solver;     // 0: by list length -- lane per tree in rounds (long), persistent work queue
                     // (short); 1: rounds for short lists too; 4, 8: lanes per tree (group solver)
     // Multi-GPU (sccd_ccd_sharded): the earliest-toi words of the OTHER ranks, mapped into this
