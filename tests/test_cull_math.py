@@ -257,3 +257,85 @@ def test_fuzz_near_threshold_separations(orc, is_vf, tol, f32):
     culled = cull_mask(q, is_vf, tol, 0.0, f32)
     assert culled.any() and (~culled).any()                    # the sample straddles the bound
     assert not np.any(culled & (tpq < 1))
+
+
+def cull_mask_float_pretest(q, is_vf, tol, ms):
+    """numpy (float32) mirror of cull_query_float in csrc/narrow.cu: the pre-test in front of the
+    double test.  True = culled by the pre-test alone."""
+    f = q.astype(np.float32).reshape(-1, 2, 4, 3)
+    s, e = f[:, 0], f[:, 1]
+    n = len(f)
+    flat = f.reshape(n, -1)
+    mx = np.maximum(np.float32(1), np.abs(flat).max(1))
+    mxu = mx.astype(np.float64) * 1.000001
+    ok = mx <= np.float32(1e30)
+    ok &= (flat.max(1) - flat.min(1)).astype(np.float64) * 1.001 + 1e-6 * mxu <= tol * 1e12
+    if is_vf:
+        A = np.stack([s[:, 0], e[:, 0]], axis=1)
+        B = np.stack([s[:, 1], s[:, 2], s[:, 3], e[:, 1], e[:, 2], e[:, 3],
+                      s[:, 2] + s[:, 3] - s[:, 1], e[:, 2] + e[:, 3] - e[:, 1]], axis=1)
+        width_up = np.full(n, tol)
+    else:
+        A = np.stack([s[:, 0], s[:, 1], e[:, 0], e[:, 1]], axis=1)
+        B = np.stack([s[:, 2], s[:, 3], e[:, 2], e[:, 3]], axis=1)
+        L = np.zeros((3, n), np.float32)
+        for k in range(3):
+            s0, s1, s2, s3 = (s[:, j, k] for j in range(4))
+            e0, e1, e2, e3 = (e[:, j, k] for j in range(4))
+            p000, p001, p010, p011 = s0 - s2, s0 - s3, s1 - s2, s1 - s3
+            p100, p101, p110, p111 = e0 - e2, e0 - e3, e1 - e2, e1 - e3
+            L[0] = np.maximum(L[0], absmax((p000, p100), (p001, p101), (p011, p111), (p010, p110)))
+            L[1] = np.maximum(L[1], absmax((p000, p010), (p100, p110), (p101, p111), (p001, p011)))
+            L[2] = np.maximum(L[2], absmax((p000, p001), (p100, p101), (p110, p111), (p010, p011)))
+        dl = 1e-6 * mxu
+        l0, l1 = L[0].astype(np.float64) - dl, L[1].astype(np.float64) - dl
+        ok &= (l0 > 0) & (l1 > 0)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            width_up = tol * (1 + (L[1] + dl) / l0 + (L[2] + dl) / l1) / 3 * 1.00001
+        width_up = np.maximum(np.where(ok, width_up, np.inf), tol)
+    # float32 projections, one addition each (numpy keeps float32 for float32 operands)
+    seps = []
+    for i0, i1, sg in ((0, 1, 1), (0, 1, -1), (0, 2, 1), (0, 2, -1), (1, 2, 1), (1, 2, -1)):
+        pa = A[:, :, i0] + np.float32(sg) * A[:, :, i1]
+        pb = B[:, :, i0] + np.float32(sg) * B[:, :, i1]
+        seps.append(np.maximum(pa.min(1) - pb.max(1), pb.min(1) - pa.max(1)))
+    sep = np.max(np.stack(seps), axis=0).astype(np.float64)
+    bound_up = 2.0 * (width_up + ms + 2.0 * mxu ** 3 * 8e-15 + 1e-12 * mxu) * 1.000001
+    return ok & (0.5 * (sep - 1e-5 * mxu) > bound_up)
+
+
+@pytest.mark.parametrize("tol,ms", [(1e-6, 0.0), (1e-9, 0.0), (1e-6, 1e-8), (1e-3, 0.0), (1e-6, 1e-3)])
+def test_float_pretest_culls_a_subset_of_the_double_test(sccd, scene_c1, orc, tol, ms):
+    """The float pre-test (double build) may only cull what the double test culls -- its margin
+    must cover every float rounding: mesh queries (cloth, piles), adversarial queries, queries
+    with separations around the threshold and around the margin, huge coordinates."""
+    rng = np.random.default_rng(5)
+    sets = []
+    for scene in (scene_c1, sccd.scenes.blob_pile(40, seed=3)):
+        got = orc.ccd(scene)
+        for pairs, is_vf in ((got["vf"], True), (got["ee"], False)):
+            sets.append((orc.gather_queries(scene, np.ascontiguousarray(pairs[:60000]), is_vf), is_vf))
+    ee, vf = sccd.scenes.queries_c5(4000, seed=6)
+    sets += [(vf, True), (ee, False)]
+    # random primitives pushed apart by gaps from far below the threshold to far above the margin,
+    # at coordinate magnitudes from 1 to 1e6
+    for is_vf in (True, False):
+        n = 20000
+        base = rng.uniform(-1, 1, (n, 1, 4, 3))
+        motion = rng.uniform(-1, 1, (n, 1, 4, 3)) * 10.0 ** rng.uniform(-6, 0, (n, 1, 1, 1))
+        p = np.concatenate([base, base + motion], axis=1)
+        sl = slice(1, 4) if is_vf else slice(2, 4)
+        axis = DIAGS[rng.integers(0, 6, n)] * rng.choice([-1.0, 1.0], (n, 1))
+        gap = 10.0 ** rng.uniform(-8, 1, n)
+        p[:, :, sl] += (gap[:, None] * axis)[:, None, None, :]
+        p *= 10.0 ** rng.integers(0, 7, (n, 1, 1, 1))
+        p += rng.uniform(-1, 1, (n, 1, 1, 3)) * 10.0 ** rng.integers(0, 5, (n, 1, 1, 1))
+        sets.append((np.ascontiguousarray(p.reshape(n, 24)), is_vf))
+    n_pre = n_dbl = 0
+    for q, is_vf in sets:
+        pre = cull_mask_float_pretest(q, is_vf, tol, ms)
+        dbl = cull_mask(q, is_vf, tol, ms)
+        assert not np.any(pre & ~dbl), "the float pre-test culled a query the double test keeps"
+        n_pre += int(pre.sum())
+        n_dbl += int(dbl.sum())
+    assert n_dbl > 0 and n_pre > 0.5 * n_dbl      # ... and it does decide most of them
