@@ -296,8 +296,10 @@ void key_layout(
 }
 
 // enqueue the record count of grid L.g_try (and, multi-GPU, this rank's cell range)
-void sort_list_count(sccd_ctx* c, int which)
+void sort_list_count(sccd_ctx* c, int which, cudaStream_t st = nullptr)
 {
+    if (!st)
+        st = st;
     auto& L = c->lists[which];
     auto& H = list_host(c, which);
     const int n = L.n_boxes;
@@ -306,11 +308,11 @@ void sort_list_count(sccd_ctx* c, int which)
     L.try_sharded = false;
     if (cells == 1) { // plain 1-axis sweep: one record per box, nothing to ask the device
         H.m = (unsigned long long)n;
-        SCCD_CUDA(cudaMemsetAsync(L.copies.as<uint32_t>() + n, 0, 4, c->stream));
-        launch_expand_count(L.unsorted, n, g, nullptr, L.copies.as<uint32_t>(), c->stream, c->lc);
+        SCCD_CUDA(cudaMemsetAsync(L.copies.as<uint32_t>() + n, 0, 4, st));
+        launch_expand_count(L.unsorted, n, g, nullptr, L.copies.as<uint32_t>(), st, c->lc);
         launch_scan_u32_to_u64(
-            L.copies.as<uint32_t>(), L.offs.as<unsigned long long>(), n, c->b_scan_temp.ptr,
-            c->b_scan_temp.cap, c->stream, c->lc);
+            L.copies.as<uint32_t>(), L.offs.as<unsigned long long>(), n, L.scan_temp.ptr,
+            L.scan_temp.cap, st, c->lc);
         return;
     }
     const unsigned long long* d_range = nullptr;
@@ -326,19 +328,19 @@ void sort_list_count(sccd_ctx* c, int which)
         unsigned long long* d_out =
             (unsigned long long*)c->b_splits.reserve((size_t)3 * (2 * 16 + 2) * 8)
             + (size_t)which * (2 * 16 + 2);
-        launch_cell_splits(L.unsorted, n, L.try_stride, g, W, hist, d_out, c->stream, c->lc);
+        launch_cell_splits(L.unsorted, n, L.try_stride, g, W, hist, d_out, st, c->lc);
         SCCD_CUDA(cudaMemcpyAsync(
-            H.splits, d_out, (size_t)(2 * W + 2) * 8, cudaMemcpyDeviceToHost, c->stream));
+            H.splits, d_out, (size_t)(2 * W + 2) * 8, cudaMemcpyDeviceToHost, st));
         d_range = d_out + c->rank;
         L.try_sharded = true;
     }
-    SCCD_CUDA(cudaMemsetAsync(L.copies.as<uint32_t>() + n, 0, 4, c->stream));
-    launch_expand_count(L.unsorted, n, g, d_range, L.copies.as<uint32_t>(), c->stream, c->lc);
+    SCCD_CUDA(cudaMemsetAsync(L.copies.as<uint32_t>() + n, 0, 4, st));
+    launch_expand_count(L.unsorted, n, g, d_range, L.copies.as<uint32_t>(), st, c->lc);
     launch_scan_u32_to_u64(
-        L.copies.as<uint32_t>(), L.offs.as<unsigned long long>(), n, c->b_scan_temp.ptr,
-        c->b_scan_temp.cap, c->stream, c->lc);
+        L.copies.as<uint32_t>(), L.offs.as<unsigned long long>(), n, L.scan_temp.ptr,
+        L.scan_temp.cap, st, c->lc);
     SCCD_CUDA(cudaMemcpyAsync(
-        &H.m, L.offs.as<unsigned long long>() + n, 8, cudaMemcpyDeviceToHost, c->stream));
+        &H.m, L.offs.as<unsigned long long>() + n, 8, cudaMemcpyDeviceToHost, st));
 }
 
 // enqueue the statistics of a list towards list_host(c, which).stats_next (no sync)
@@ -388,7 +390,7 @@ void drain_stats(sccd_ctx* c)
 }
 
 // requires the list's statistics in list_host(c, which).stats
-void sort_list_begin(sccd_ctx* c, int which)
+void sort_list_begin(sccd_ctx* c, int which, cudaStream_t st = nullptr)
 {
     auto& L = c->lists[which];
     auto& H = list_host(c, which);
@@ -401,8 +403,8 @@ void sort_list_begin(sccd_ctx* c, int which)
     L.g_try = choose_grid(H.stats, n, c->grid_max_cells, c->grid_scale);
     L.copies.reserve(((size_t)n + 1) * 4);
     L.offs.reserve(((size_t)n + 1) * 8);
-    c->b_scan_temp.reserve(scan_temp_bytes(n));
-    sort_list_count(c, which);
+    L.scan_temp.reserve(scan_temp_bytes(n));
+    sort_list_count(c, which, st);
 }
 
 // st: the stream the fill / sort / gather are enqueued on (the retry path stays on c->stream)
@@ -470,10 +472,8 @@ void sort_list_finish(
     L.sorted.pf.reach = (uint32_t*)L.preach.reserve(mm * 4);
     L.sorted.pf.yz = (float4*)L.pyz.reserve(mm * sizeof(float4));
     L.sort_temp.reserve(sort_temp_bytes((int)m)); // per list: the two sorts may overlap
-    if (st != c->stream) { // everything counted so far (incl. a retry above) is on c->stream
-        SCCD_CUDA(cudaEventRecord(c->ev_counts, c->stream));
-        SCCD_CUDA(cudaStreamWaitEvent(st, c->ev_counts, 0));
-    }
+    // (no cross-stream wait: the host has waited for this list's count -- wherever it ran -- and
+    // for the boxes before it)
     const int slot = which == 1 ? 1 : 0;
     c->stats.key_bits[slot] = cell_bits + g.x_bits;
     const size_t kt_e = kt_begin(c, &c->stats.ms_k_expand[slot], st);
@@ -557,10 +557,7 @@ void build_boxes(sccd_ctx* c, double inflation_radius)
     if (reuse) {
         SCCD_CUDA(cudaEventRecord(c->ev_boxes, c->stream));
         SCCD_CUDA(cudaStreamWaitEvent(c->sort_stream, c->ev_boxes, 0));
-        list_stats(c, 0, c->sort_stream);
-        list_stats(c, 1, c->sort_stream);
-        SCCD_CUDA(cudaEventRecord(c->ev_stats, c->sort_stream));
-        c->stats_in_flight = true;
+        // (the statistics themselves are enqueued below, behind the edge list's record count)
     } else {
         // sync 1: statistics of both lists (sync 2: record counts of both lists)
         list_stats(c, 0);
@@ -590,15 +587,45 @@ void build_boxes(sccd_ctx* c, double inflation_radius)
         L.next_axis = L.n_boxes > 0 ? best : L.axis;
     }
     c->next_axis = LV.next_axis;
+    // The two lists count their records side by side: the vertex-face list on the main stream,
+    // the edge list on the sort stream (single GPU; the cell-range split of sccd_set_shard shares
+    // its histogram scratch between the lists and stays on one stream).  The host picks the
+    // vertex-face count up first and enqueues that list's fill / sort / gather at once.
+    const bool side_by_side = c->world == 1;
+    if (side_by_side) {
+        if (!reuse) { // (else: done above, the sort stream already waits for the boxes)
+            SCCD_CUDA(cudaEventRecord(c->ev_boxes, c->stream));
+            SCCD_CUDA(cudaStreamWaitEvent(c->sort_stream, c->ev_boxes, 0));
+        }
+        sort_list_begin(c, 1, c->sort_stream);
+        SCCD_CUDA(cudaEventRecord(c->ev_cnt1, c->sort_stream));
+    }
+    if (reuse) { // this build's statistics, for the next one: nobody waits for them now
+        list_stats(c, 0, c->sort_stream);
+        list_stats(c, 1, c->sort_stream);
+        SCCD_CUDA(cudaEventRecord(c->ev_stats, c->sort_stream));
+        c->stats_in_flight = true;
+    }
     sort_list_begin(c, 0);
-    sort_list_begin(c, 1);
+    if (!side_by_side)
+        sort_list_begin(c, 1);
     host_sync(c, c->stream);
     if (reuse && c->h_flags[0])
         throw std::invalid_argument("build_boxes: an edge / face refers to a vertex that does not exist");
     const bool prof = c->opt.profile != 0;
     sort_list_finish(c, 0, prof ? c->ev[EV_GA0] : nullptr, prof ? c->ev[EV_GB0] : nullptr);
+    if (side_by_side) // (no extra round trip: it ran beside the count the host just waited for)
+        SCCD_CUDA(cudaEventSynchronize(c->ev_cnt1));
+    // Large lists: the edge list's sort waits for the vertex-face list's, so that it runs under
+    // the vertex-face SWEEP -- a bandwidth-bound pass beside an issue-bound one -- instead of
+    // beside another sort (config 4: 28.5 ms this way, 29.1 with the sorts side by side).  Small
+    // lists are latency-bound and gain from starting at once (config 2: 0.676 -> 0.648 ms).
+    if ((unsigned long long)LV.sorted.n + list_host(c, 1).m > (4ull << 20)) {
+        SCCD_CUDA(cudaEventRecord(c->ev_counts, c->stream));
+        SCCD_CUDA(cudaStreamWaitEvent(c->sort_stream, c->ev_counts, 0));
+    }
     // (if the grid of list 1 has to be coarsened, its retry runs -- and syncs -- on the main
-    // stream before anything is enqueued on the sort stream)
+    // stream before anything more is enqueued on the sort stream)
     sort_list_finish(
         c, 1, prof ? c->ev[EV_GA1] : nullptr, prof ? c->ev[EV_GB1] : nullptr, c->sort_stream);
     SCCD_CUDA(cudaEventRecord(c->ev_sorted1, c->sort_stream));
@@ -1395,6 +1422,7 @@ int sccd_create(int device, void* stream, sccd_ctx** out)
         SCCD_CUDA(cudaEventCreateWithFlags(&c->ev_sorted1, cudaEventDisableTiming));
         SCCD_CUDA(cudaEventCreateWithFlags(&c->ev_vf_done, cudaEventDisableTiming));
         SCCD_CUDA(cudaEventCreateWithFlags(&c->ev_boxes, cudaEventDisableTiming));
+        SCCD_CUDA(cudaEventCreateWithFlags(&c->ev_cnt1, cudaEventDisableTiming));
         SCCD_CUDA(cudaEventCreateWithFlags(&c->ev_stats, cudaEventDisableTiming));
         if (const char* e = getenv("SCCD_NP_TAIL")) // (experiments)
             c->opt.np_tail_lanes = std::max(0, std::min(32, atoi(e)));

@@ -41,6 +41,7 @@ struct sccd_ctx {
     struct ListBufs {
         DevBuf ux, uyz, uid;     // unsorted exact records (one per box)
         DevBuf copies, offs;     // cells touched per box, and their exclusive scan
+        DevBuf scan_temp;        // scratch of that scan (per list: the two lists count together)
         DevBuf keys, keys_tmp;   // 64-bit (key, box index) records, one per (box, cell)
         DevBuf sx, syz, sid;     // sorted exact records
         DevBuf pkey, preach, pyz; // sorted prefilter view
@@ -71,6 +72,7 @@ struct sccd_ctx {
                                             // sort_stream to the caller's stream)
     cudaEvent_t ev_counts = nullptr, ev_sorted1 = nullptr, ev_vf_done = nullptr;
     cudaEvent_t ev_boxes = nullptr, ev_stats = nullptr; // frame-to-frame statistics (build_boxes)
+    cudaEvent_t ev_cnt1 = nullptr; // the edge list's record count has arrived (sort stream)
     bool stats_in_flight = false;
     bool sort1_pending = false;
     // pinned: per list, box statistics + record count + multi-GPU cell splits
@@ -212,6 +214,8 @@ struct sccd_ctx {
             cudaEventDestroy(ev_sorted1);
         if (ev_vf_done)
             cudaEventDestroy(ev_vf_done);
+        if (ev_cnt1)
+            cudaEventDestroy(ev_cnt1);
         if (ev_boxes)
             cudaEventDestroy(ev_boxes);
         if (ev_stats)
